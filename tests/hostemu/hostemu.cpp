@@ -1,0 +1,193 @@
+// tests/hostemu/hostemu.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Compiles the device query code of habitat-sim_b200/csrc/hbn_query.h for the host with a
+// one-lane group (HostGroup) so that the kernels' logic can be debugged against the oracle
+// on a box without a GPU.  It is never loaded by the product: libhbn.so contains only the
+// CUDA path and fails when no device is present.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "hbn_host.h"
+#include "hbn_query.h"
+
+using namespace hbn;
+
+struct Emu {
+  HostNavMesh mesh;
+  FlatNav flat;
+  NavView nav;
+  std::string err;
+};
+
+extern "C" {
+
+void* emu_create(const unsigned char* buf, long len) {
+  Emu* e = new Emu();
+  if (!e->mesh.loadMSET(buf, static_cast<size_t>(len), e->err)) {
+    fprintf(stderr, "emu_create: %s\n", e->err.c_str());
+    delete e;
+    return nullptr;
+  }
+  e->mesh.finish(nullptr);
+  e->mesh.flatten(e->flat);
+  e->nav = e->flat.view();
+  return e;
+}
+void emu_destroy(void* h) { delete static_cast<Emu*>(h); }
+
+// {numTilesPresent, numPolys, numLinks, numIslands}
+void emu_info(void* h, long* out4) {
+  Emu* e = static_cast<Emu*>(h);
+  long nt = 0;
+  for (auto& t : e->mesh.tiles()) nt += t.present ? 1 : 0;
+  out4[0] = nt;
+  out4[1] = static_cast<long>(e->flat.polys.size());
+  out4[2] = static_cast<long>(e->flat.links.size());
+  out4[3] = static_cast<long>(e->flat.islandRadius.size());
+}
+float emu_island_radius(void* h, int i) { return static_cast<Emu*>(h)->flat.islandRadius[i]; }
+float emu_island_area(void* h, int i) {
+  Emu* e = static_cast<Emu*>(h);
+  return i < 0 ? e->flat.totalArea : e->flat.islandArea[i];
+}
+void emu_bounds(void* h, float* out6) { memcpy(out6, static_cast<Emu*>(h)->flat.bounds, 24); }
+
+// finalised blob of the idx-th present tile (table order)
+int emu_tile_blob(void* h, int idx, unsigned char* out, int cap) {
+  Emu* e = static_cast<Emu*>(h);
+  int n = 0;
+  for (auto& t : e->mesh.tiles()) {
+    if (!t.present) continue;
+    if (n++ != idx) continue;
+    if (out && cap >= static_cast<int>(t.data.size())) memcpy(out, t.data.data(), t.data.size());
+    return static_cast<int>(t.data.size());
+  }
+  return -1;
+}
+long emu_poly_islands(void* h, int* out, unsigned* refs, long cap) {
+  Emu* e = static_cast<Emu*>(h);
+  const long n = static_cast<long>(e->flat.polys.size());
+  for (long i = 0; i < n && i < cap; ++i) {
+    if (out) out[i] = e->flat.polys[i].island;
+    if (refs) refs[i] = e->flat.polys[i].ref;
+  }
+  return n;
+}
+
+static const float kExt[3] = {2.f, 4.f, 2.f};  // polyPickExt, PathFinder.cpp:134
+
+void emu_snap(void* h, const float* pts, const int* islands, long n, float* out_pts,
+              unsigned* out_refs, int* out_isl) {
+  Emu* e = static_cast<Emu*>(h);
+  HostGroup grp;
+  uint32_t q[2];
+  for (long i = 0; i < n; ++i) {
+    const Nearest r = findNearestPoly(e->nav, grp, pts + 3 * i, kExt, islands ? islands[i] : -1, q);
+    const bool ok = r.g != kNoPoly;
+    for (int k = 0; k < 3; ++k) out_pts[3 * i + k] = ok ? r.pt[k] : NAN;
+    if (out_refs) out_refs[i] = ok ? e->nav.polys[r.g].ref : 0u;
+    if (out_isl) out_isl[i] = ok ? e->nav.polys[r.g].island : -1;
+  }
+}
+
+// out_info [n,8] like the oracle's ref_find_path_raw_batch
+void emu_find_path(void* h, const float* starts, const float* ends, long n, int cap, int fastFail,
+                   float* out_dist, int* out_npts, float* out_pts, int max_pts,
+                   unsigned* out_corridor, unsigned* out_info, int* out_overflow) {
+  Emu* e = static_cast<Emu*>(h);
+  HostGroup grp;
+  uint32_t q[2];
+  std::vector<char> buf(astarWsBytes(cap) + 64);
+  void* aligned = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(buf.data()) + 15) & ~uintptr_t(15));
+  AStarWs w = astarWsCarve(aligned, cap);
+  for (long i = 0; i < n; ++i) {
+    const Nearest s = findNearestPoly(e->nav, grp, starts + 3 * i, kExt, -1, q);
+    const Nearest t = findNearestPoly(e->nav, grp, ends + 3 * i, kExt, -1, q);
+    memset(w.hash, 0, sizeof(uint32_t) * 2 * cap);
+    PathResult r = findPathInternal(e->nav, w, starts + 3 * i, ends + 3 * i, s.g, s.pt, t.g, t.pt,
+                                    fastFail != 0, out_pts ? out_pts + static_cast<size_t>(i) * max_pts * 3 : nullptr,
+                                    max_pts, out_corridor ? out_corridor + i * 256 : nullptr);
+    out_dist[i] = r.dist;
+    if (out_npts) out_npts[i] = (r.flags & 4u) ? r.npts : 0;
+    if (out_overflow) out_overflow[i] = r.overflow ? 1 : 0;
+    if (out_info) {
+      unsigned* o = out_info + i * 8;
+      o[0] = s.g != kNoPoly ? e->nav.polys[s.g].ref : 0;
+      o[1] = (s.g != kNoPoly && t.g != kNoPoly) ? e->nav.polys[t.g].ref : 0;
+      o[2] = r.astarStatus; o[3] = r.straightStatus; o[4] = r.ncorridor; o[5] = r.npts;
+      o[6] = r.nodesUsed; o[7] = r.flags;
+    }
+  }
+}
+
+void emu_try_step(void* h, const float* starts, const float* ends, long n, int allowSliding,
+                  float* out) {
+  Emu* e = static_cast<Emu*>(h);
+  HostGroup grp;
+  uint32_t q[2];
+  for (long i = 0; i < n; ++i) {
+    const float* st = starts + 3 * i;
+    const float* en = ends + 3 * i;
+    const Nearest s = findNearestPoly(e->nav, grp, st, kExt, -1, q);
+    const Nearest t = findNearestPoly(e->nav, grp, en, kExt, -1, q);
+    float ep[3];
+    uint32_t last = kNoPoly;
+    if (!tryStepPhaseA(e->nav, s.g, s.pt, t.g, en, allowSliding != 0, ep, &last)) {
+      memcpy(out + 3 * i, st, 12);
+      continue;
+    }
+    const Nearest e2 = findNearestPoly(e->nav, grp, ep, kExt, -1, q);
+    tryStepPhaseB(e->nav, s.g, e2.g, last, ep);
+    memcpy(out + 3 * i, ep, 12);
+  }
+}
+
+// out [n,7]: hitPos, hitNormal, hitDist (closestObstacleSurfacePoint, PathFinder.cpp:1794-1812)
+void emu_obstacle(void* h, const float* pts, long n, float maxRadius, int cap, float* out,
+                  int* out_overflow) {
+  Emu* e = static_cast<Emu*>(h);
+  HostGroup grp;
+  uint32_t q[2];
+  std::vector<char> buf(astarWsBytes(cap) + 64);
+  void* aligned = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(buf.data()) + 15) & ~uintptr_t(15));
+  AStarWs w = astarWsCarve(aligned, cap);
+  for (long i = 0; i < n; ++i) {
+    float* o = out + 7 * i;
+    const Nearest s = findNearestPoly(e->nav, grp, pts + 3 * i, kExt, -1, q);
+    for (int k = 0; k < 6; ++k) o[k] = 0.f;
+    o[6] = INFINITY;
+    if (out_overflow) out_overflow[i] = 0;
+    if (s.g == kNoPoly) continue;
+    memset(w.hash, 0, sizeof(uint32_t) * 2 * cap);
+    float hitDist = NAN;
+    const uint32_t st = distanceToWall(e->nav, w, s.g, s.pt, maxRadius, &hitDist, o, o + 3);
+    if (st == 0xffffffffu && out_overflow) out_overflow[i] = 1;
+    o[6] = hitDist;
+  }
+}
+
+// get_random_navigable_point with the counter-based stream (PathFinder.cpp:1236-1281)
+void emu_random_points(void* h, long n, int maxTries, const int* islands, unsigned long long seed,
+                       unsigned long long query0, float* out_pts, unsigned* out_refs) {
+  Emu* e = static_cast<Emu*>(h);
+  HostGroup grp;
+  for (long i = 0; i < n; ++i) {
+    uint32_t draw = 0;
+    uint32_t g = kNoPoly;
+    float pt[3] = {NAN, NAN, NAN};
+    for (int t = 0; t < maxTries; ++t) {
+      uint32_t used = 0;
+      float p[3];
+      g = findRandomPoint(e->nav, grp, seed, query0 + i, draw, islands ? islands[i] : -1, p, &used);
+      draw += used;
+      if (g != kNoPoly) { memcpy(pt, p, 12); break; }
+    }
+    memcpy(out_pts + 3 * i, pt, 12);
+    if (out_refs) out_refs[i] = g != kNoPoly ? e->nav.polys[g].ref : 0;
+  }
+}
+
+}  // extern "C"
