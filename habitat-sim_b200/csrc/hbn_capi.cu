@@ -1,0 +1,657 @@
+// C ABI of libhbn.so (include/hbn.h): navmesh upload, kernel orchestration, host-buffer
+// wrappers.  No CPU query path exists in this library.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/hbn.h"
+#include "hbn_host.h"
+#include "hbn_kernels.cuh"
+
+using namespace hbn;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CK(expr)                                                                       \
+  do {                                                                                 \
+    cudaError_t e_ = (expr);                                                           \
+    if (e_ != cudaSuccess)                                                             \
+      return fail(HBN_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));   \
+  } while (0)
+
+// tier configuration (see DESIGN.md "A* workspace tiers")
+constexpr int kCapS = 256;    // small tier: whole workspace in shared memory
+constexpr int kCapL = 2048;   // reference pool size: heap+hash shared, nodes in L2
+constexpr int kWallCapS = 128;
+constexpr int kFpWarps = 4;   // warps per block of the path kernels
+constexpr int kSnapW = 8;     // lanes per point in k_snap
+constexpr int kRandW = 8;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return HBN_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) return fail(HBN_ERR_CUDA, std::string("cudaMalloc scratch: ") + cudaGetErrorString(e));
+    cap = want;
+    return HBN_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+}  // namespace
+
+struct hbn_navmesh {
+  int device = 0;
+  FlatNav flat;
+  NavView view{};
+  std::vector<void*> devArrays;
+  int64_t deviceBytes = 0;
+  cudaStream_t stream = nullptr;  // for the host-buffer entry points
+  int smCount = 0;
+  int64_t launches = 0;
+  std::recursive_mutex mu;
+  // scratch (device)
+  DevBuf sG, eG, e2G, sPt, ePt, epPt, lastPoly, lists, counters, wsL, io;
+  // pinned staging for the host-buffer entry points
+  void* pinned = nullptr;
+  size_t pinnedCap = 0;
+  int blocksFpS = 0, blocksFpL = 0, blocksWallS = 0;
+};
+
+namespace {
+
+template <class T>
+int upload(hbn_navmesh* nm, const std::vector<T>& v, const T** out) {
+  void* d = nullptr;
+  const size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+  CK(cudaMalloc(&d, bytes));
+  nm->devArrays.push_back(d);
+  nm->deviceBytes += static_cast<int64_t>(bytes);
+  if (!v.empty()) CK(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = static_cast<const T*>(d);
+  return HBN_OK;
+}
+
+int finishCreate(HostNavMesh& mesh, const int32_t* islands, int device, hbn_navmesh_t* out) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return fail(HBN_ERR_NO_DEVICE, "no CUDA device available (libhbn has no CPU path)");
+  if (device < 0 || device >= ndev) return fail(HBN_ERR_INVALID, "bad device index");
+  CK(cudaSetDevice(device));
+  hbn_navmesh* nm = new hbn_navmesh();
+  nm->device = device;
+  mesh.finish(islands);
+  mesh.flatten(nm->flat);
+  const FlatNav& f = nm->flat;
+  if (f.polys.size() >= (1u << 24) || f.links.size() >= (1u << 27)) {
+    delete nm;
+    return fail(HBN_ERR_LIMIT, "navmesh exceeds 2^24 polys or 2^27 links");
+  }
+  for (const PolyRec& p : f.polys)
+    if (p.linkCount > 31) {
+      delete nm;
+      return fail(HBN_ERR_LIMIT, "a polygon has more than 31 links");
+    }
+  NavView v = f.view();
+  int rc = HBN_OK;
+  auto up = [&](auto& vec, auto** dst) { if (rc == HBN_OK) rc = upload(nm, vec, dst); };
+  up(f.polys, &v.polys);
+  up(f.links, &v.links);
+  up(f.portals, &v.portals);
+  up(f.bv, &v.bv);
+  up(f.tiles, &v.tiles);
+  up(f.detTris, &v.detTris);
+  up(f.detVerts, &v.detVerts);
+  up(f.gridStart, &v.gridStart);
+  up(f.tileOrder, &v.tileOrder);
+  up(f.randEntries, &v.randEntries);
+  up(f.tileIslStart, &v.tileIslStart);
+  up(f.tileIslId, &v.tileIslId);
+  up(f.tileIslWin, &v.tileIslWin);
+  up(f.tileIslCnt, &v.tileIslCnt);
+  if (rc != HBN_OK) {
+    hbn_navmesh_destroy(nm);
+    return rc;
+  }
+  nm->view = v;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  nm->smCount = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&nm->stream, cudaStreamNonBlocking));
+
+  // opt in to large dynamic shared memory and size the persistent grids from occupancy
+  const int threads = kFpWarps * 32;
+  const size_t smS = kFpWarps * wsSharedBytes(kCapS, kWsShared);
+  const size_t smL = kFpWarps * wsSharedBytes(kCapL, kWsHybrid);
+  const size_t smW = kFpWarps * wsSharedBytes(kWallCapS, kWsShared);
+  CK(cudaFuncSetAttribute(k_findpath<kCapS, kWsShared>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smS)));
+  CK(cudaFuncSetAttribute(k_findpath<kCapL, kWsHybrid>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smL)));
+  CK(cudaFuncSetAttribute(k_wall<kWallCapS, kWsShared>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smW)));
+  CK(cudaFuncSetAttribute(k_wall<kCapL, kWsHybrid>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smL)));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_findpath<kCapS, kWsShared>, threads, smS));
+  nm->blocksFpS = std::max(1, occ) * nm->smCount;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_findpath<kCapL, kWsHybrid>, threads, smL));
+  nm->blocksFpL = std::max(1, occ) * nm->smCount;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wall<kWallCapS, kWsShared>, threads, smW));
+  nm->blocksWallS = std::max(1, occ) * nm->smCount;
+  // global node arrays of the large tier: one slot per resident warp
+  rc = nm->wsL.ensure(static_cast<size_t>(nm->blocksFpL) * kFpWarps * wsGlobalBytes(kCapL, kWsHybrid));
+  if (rc == HBN_OK) rc = nm->counters.ensure(64);
+  if (rc != HBN_OK) {
+    hbn_navmesh_destroy(nm);
+    return rc;
+  }
+  *out = nm;
+  return HBN_OK;
+}
+
+struct DeviceGuard {
+  int prev = 0;
+  bool ok;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+int snapLaunch(hbn_navmesh* nm, const float* pts, const int32_t* islands, int64_t n, float* out_pts,
+               uint32_t* out_g, uint32_t* out_refs, int32_t* out_isl, uint8_t* out_nav,
+               float maxYDelta, cudaStream_t st) {
+  if (n <= 0) return HBN_OK;
+  const int groupsPerBlock = 256 / kSnapW;
+  int64_t blocks = (n + groupsPerBlock - 1) / groupsPerBlock;
+  const int64_t maxBlocks = static_cast<int64_t>(nm->smCount) * 64;
+  if (blocks > maxBlocks) blocks = maxBlocks;
+  k_snap<kSnapW><<<static_cast<unsigned>(blocks), 256, 0, st>>>(nm->view, pts, islands, n, out_pts, out_g,
+                                                                out_refs, out_isl, out_nav, maxYDelta);
+  nm->launches++;
+  CK(cudaGetLastError());
+  return HBN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* hbn_last_error(void) { return g_err.c_str(); }
+
+int hbn_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+float hbn_uniform(uint64_t seed, uint64_t query, uint32_t draw) { return uniform01(seed, query, draw); }
+
+int hbn_navmesh_create_from_mset(const void* bytes, size_t len, int device, hbn_navmesh_t* out) {
+  if (!bytes || !out) return fail(HBN_ERR_INVALID, "null argument");
+  *out = nullptr;
+  HostNavMesh mesh;
+  std::string err;
+  if (!mesh.loadMSET(static_cast<const uint8_t*>(bytes), len, err)) return fail(HBN_ERR_FORMAT, err);
+  return finishCreate(mesh, nullptr, device, out);
+}
+
+int hbn_navmesh_create_from_tiles(const hbn_tile_blob* tiles, int n_tiles, const float* params5,
+                                  int max_tiles, int max_polys, const int32_t* poly_islands,
+                                  int device, hbn_navmesh_t* out) {
+  if (!tiles || n_tiles <= 0 || !params5 || !out) return fail(HBN_ERR_INVALID, "null argument");
+  *out = nullptr;
+  HostNavMesh mesh;
+  std::string err;
+  DtNavMeshParams p;
+  p.orig[0] = params5[0]; p.orig[1] = params5[1]; p.orig[2] = params5[2];
+  p.tileWidth = params5[3];
+  p.tileHeight = params5[4];
+  p.maxTiles = max_tiles;
+  p.maxPolys = max_polys;
+  if (!mesh.init(p, err)) return fail(HBN_ERR_FORMAT, err);
+  for (int i = 0; i < n_tiles; ++i)
+    if (!mesh.addFinalisedTile(static_cast<const uint8_t*>(tiles[i].data), tiles[i].size,
+                               tiles[i].tile_ref, err))
+      return fail(HBN_ERR_FORMAT, err);
+  return finishCreate(mesh, poly_islands, device, out);
+}
+
+void hbn_navmesh_destroy(hbn_navmesh_t nm) {
+  if (!nm) return;
+  DeviceGuard g(nm->device);
+  for (void* d : nm->devArrays) cudaFree(d);
+  for (DevBuf* b : {&nm->sG, &nm->eG, &nm->e2G, &nm->sPt, &nm->ePt, &nm->epPt, &nm->lastPoly,
+                    &nm->lists, &nm->counters, &nm->wsL, &nm->io})
+    b->release();
+  if (nm->pinned) cudaFreeHost(nm->pinned);
+  if (nm->stream) cudaStreamDestroy(nm->stream);
+  delete nm;
+}
+
+int hbn_navmesh_get_info(hbn_navmesh_t nm, hbn_navmesh_info* out) {
+  if (!nm || !out) return fail(HBN_ERR_INVALID, "null argument");
+  const FlatNav& f = nm->flat;
+  memset(out, 0, sizeof(*out));
+  out->device = nm->device;
+  for (const TileRec& t : f.tiles) out->num_tiles += t.pad[0] ? 1 : 0;
+  out->num_polys = static_cast<int32_t>(f.polys.size());
+  out->num_links = static_cast<int32_t>(f.links.size());
+  out->num_bv_nodes = static_cast<int32_t>(f.bv.size());
+  out->num_islands = static_cast<int32_t>(f.islandRadius.size());
+  out->poly_bits = f.polyBits;
+  out->tile_bits = f.tileBits;
+  out->salt_bits = f.saltBits;
+  out->has_settings = f.hasSettings ? 1 : 0;
+  for (int k = 0; k < 3; ++k) {
+    out->bounds_min[k] = f.bounds[k];
+    out->bounds_max[k] = f.bounds[3 + k];
+  }
+  out->navigable_area = f.totalArea;
+  out->device_bytes = nm->deviceBytes;
+  return HBN_OK;
+}
+
+int hbn_navmesh_island_info(hbn_navmesh_t nm, int island, float* radius, float* area) {
+  if (!nm) return fail(HBN_ERR_INVALID, "null argument");
+  if (island < 0 || island >= static_cast<int>(nm->flat.islandRadius.size()))
+    return fail(HBN_ERR_INVALID, "not a valid index for this island system");
+  if (radius) *radius = nm->flat.islandRadius[island];
+  if (area) *area = nm->flat.islandArea[island];
+  return HBN_OK;
+}
+
+int hbn_navmesh_get_settings(hbn_navmesh_t nm, void* out56) {
+  if (!nm || !out56) return fail(HBN_ERR_INVALID, "null argument");
+  if (!nm->flat.hasSettings) return fail(HBN_ERR_INVALID, "navmesh image carries no NavMeshSettings");
+  memcpy(out56, nm->flat.settings, 56);
+  return HBN_OK;
+}
+
+int64_t hbn_navmesh_launch_count(hbn_navmesh_t nm) { return nm ? nm->launches : 0; }
+
+int64_t hbn_navmesh_triangles(hbn_navmesh_t nm, int island, float* out, int64_t cap_tris) {
+  if (!nm) return -1;
+  const FlatNav& f = nm->flat;
+  int64_t n = 0;
+  for (const PolyRec& p : f.polys) {
+    if ((p.areaType >> 6) == 1) continue;
+    if ((p.flags & kFlagWalk) == 0) continue;
+    if (island >= 0 && p.island != island) continue;
+    for (int j = 0; j < p.detTriCount; ++j) {
+      const uint8_t* t = &f.detTris[static_cast<size_t>(p.detTriBase + j) * 4];
+      if (out && n < cap_tris)
+        for (int k = 0; k < 3; ++k) {
+          const float* v = t[k] < p.nv ? &p.v[t[k] * 3]
+                                       : &f.detVerts[static_cast<size_t>(p.detVertBase + (t[k] - p.nv)) * 3];
+          memcpy(out + n * 9 + k * 3, v, 12);
+        }
+      n++;
+    }
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------------------------
+int hbn_snap_point_dev(hbn_navmesh_t nm, const float* pts, const int32_t* islands, int64_t n,
+                       float* out_pts, uint32_t* out_refs, int32_t* out_islands, void* stream) {
+  if (!nm || (n > 0 && !pts)) return fail(HBN_ERR_INVALID, "null argument");
+  DeviceGuard g(nm->device);
+  return snapLaunch(nm, pts, islands, n, out_pts, nullptr, out_refs, out_islands, nullptr, 0.f,
+                    static_cast<cudaStream_t>(stream));
+}
+
+int hbn_is_navigable_dev(hbn_navmesh_t nm, const float* pts, int64_t n, float max_y_delta,
+                         uint8_t* out, void* stream) {
+  if (!nm || (n > 0 && (!pts || !out))) return fail(HBN_ERR_INVALID, "null argument");
+  DeviceGuard g(nm->device);
+  return snapLaunch(nm, pts, nullptr, n, nullptr, nullptr, nullptr, nullptr, out, max_y_delta,
+                    static_cast<cudaStream_t>(stream));
+}
+
+int hbn_find_path_dev(hbn_navmesh_t nm, const float* starts, const float* ends, int64_t n,
+                      float* out_dist, int32_t* out_npts, float* out_pts, int max_pts,
+                      uint32_t* out_corridor, int32_t* out_ncorridor, uint32_t* out_status,
+                      int flags, void* stream) {
+  if (!nm || (n > 0 && (!starts || !ends || !out_dist))) return fail(HBN_ERR_INVALID, "null argument");
+  if (n <= 0) return HBN_OK;
+  if (n >= (1ll << 31)) return fail(HBN_ERR_INVALID, "batch too large");
+  if (out_pts && max_pts <= 0) return fail(HBN_ERR_INVALID, "max_pts must be positive");
+  DeviceGuard g(nm->device);
+  std::lock_guard<std::recursive_mutex> lk(nm->mu);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc;
+  if ((rc = nm->sG.ensure(n * 4)) || (rc = nm->eG.ensure(n * 4)) || (rc = nm->sPt.ensure(n * 12)) ||
+      (rc = nm->ePt.ensure(n * 12)) || (rc = nm->lists.ensure(n * 4)))
+    return rc;
+  uint32_t* cnt = static_cast<uint32_t*>(nm->counters.p);
+  CK(cudaMemsetAsync(cnt, 0, 64, st));
+  if ((rc = snapLaunch(nm, starts, nullptr, n, static_cast<float*>(nm->sPt.p),
+                       static_cast<uint32_t*>(nm->sG.p), nullptr, nullptr, nullptr, 0.f, st)))
+    return rc;
+  if ((rc = snapLaunch(nm, ends, nullptr, n, static_cast<float*>(nm->ePt.p),
+                       static_cast<uint32_t*>(nm->eG.p), nullptr, nullptr, nullptr, 0.f, st)))
+    return rc;
+  FindPathArgs a{};
+  a.starts = starts; a.ends = ends;
+  a.sG = static_cast<uint32_t*>(nm->sG.p); a.sPt = static_cast<float*>(nm->sPt.p);
+  a.eG = static_cast<uint32_t*>(nm->eG.p); a.ePt = static_cast<float*>(nm->ePt.p);
+  a.n = n;
+  a.work = nullptr; a.workCount = nullptr;
+  a.counter = cnt + 0;
+  a.overflow = static_cast<uint32_t*>(nm->lists.p);
+  a.overflowCount = cnt + 1;
+  a.out_dist = out_dist; a.out_npts = out_npts; a.out_pts = out_pts; a.max_pts = max_pts;
+  a.out_corridor = out_corridor; a.out_ncorridor = out_ncorridor; a.out_status = out_status;
+  a.scratch = nullptr;
+  a.fastFail = (flags & HBN_FP_EXACT_STATUS) ? 0 : 1;
+  const int threads = kFpWarps * 32;
+  {
+    int64_t blocks = std::min<int64_t>(nm->blocksFpS, (n + kFpWarps - 1) / kFpWarps);
+    k_findpath<kCapS, kWsShared><<<static_cast<unsigned>(blocks), threads,
+                                  kFpWarps * wsSharedBytes(kCapS, kWsShared), st>>>(nm->view, a);
+    nm->launches++;
+    CK(cudaGetLastError());
+  }
+  // large tier over the overflow list (its length stays on the device)
+  FindPathArgs b = a;
+  b.work = a.overflow;
+  b.workCount = a.overflowCount;
+  b.counter = cnt + 2;
+  b.overflow = static_cast<uint32_t*>(nm->lists.p);  // cannot overflow: CAP == kMaxNodes
+  b.overflowCount = cnt + 3;
+  b.scratch = static_cast<char*>(nm->wsL.p);
+  k_findpath<kCapL, kWsHybrid><<<nm->blocksFpL, threads, kFpWarps * wsSharedBytes(kCapL, kWsHybrid), st>>>(nm->view, b);
+  nm->launches++;
+  CK(cudaGetLastError());
+  return HBN_OK;
+}
+
+int hbn_find_path_multigoal_dev(hbn_navmesh_t, const float*, const float*, int64_t, int, float*,
+                                int32_t*, int32_t*, float*, int, void*) {
+  return fail(HBN_ERR_INVALID, "hbn_find_path_multigoal_dev: not implemented yet");
+}
+
+int hbn_try_step_dev(hbn_navmesh_t nm, const float* starts, const float* ends, int64_t n,
+                     int allow_sliding, float* out_pts, void* stream) {
+  if (!nm || (n > 0 && (!starts || !ends || !out_pts))) return fail(HBN_ERR_INVALID, "null argument");
+  if (n <= 0) return HBN_OK;
+  DeviceGuard g(nm->device);
+  std::lock_guard<std::recursive_mutex> lk(nm->mu);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc;
+  if ((rc = nm->sG.ensure(n * 4)) || (rc = nm->eG.ensure(n * 4)) || (rc = nm->e2G.ensure(n * 4)) ||
+      (rc = nm->sPt.ensure(n * 12)) || (rc = nm->epPt.ensure(n * 12)) || (rc = nm->lastPoly.ensure(n * 4)))
+    return rc;
+  uint32_t* sG = static_cast<uint32_t*>(nm->sG.p);
+  uint32_t* eG = static_cast<uint32_t*>(nm->eG.p);
+  uint32_t* e2G = static_cast<uint32_t*>(nm->e2G.p);
+  float* sPt = static_cast<float*>(nm->sPt.p);
+  float* ep = static_cast<float*>(nm->epPt.p);
+  uint32_t* last = static_cast<uint32_t*>(nm->lastPoly.p);
+  if ((rc = snapLaunch(nm, starts, nullptr, n, sPt, sG, nullptr, nullptr, nullptr, 0.f, st))) return rc;
+  if ((rc = snapLaunch(nm, ends, nullptr, n, nullptr, eG, nullptr, nullptr, nullptr, 0.f, st))) return rc;
+  k_trystep_a<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(nm->view, ends, sG, sPt, eG, n,
+                                                                      allow_sliding, ep, last);
+  nm->launches++;
+  CK(cudaGetLastError());
+  if ((rc = snapLaunch(nm, ep, nullptr, n, nullptr, e2G, nullptr, nullptr, nullptr, 0.f, st))) return rc;
+  k_trystep_b<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(nm->view, starts, sG, e2G, last, ep, n, out_pts);
+  nm->launches++;
+  CK(cudaGetLastError());
+  return HBN_OK;
+}
+
+int hbn_closest_obstacle_dev(hbn_navmesh_t nm, const float* pts, int64_t n, float max_radius,
+                             float* out_hit_pos, float* out_hit_normal, float* out_hit_dist,
+                             void* stream) {
+  if (!nm || (n > 0 && (!pts || !out_hit_dist))) return fail(HBN_ERR_INVALID, "null argument");
+  if (n <= 0) return HBN_OK;
+  if (n >= (1ll << 31)) return fail(HBN_ERR_INVALID, "batch too large");
+  DeviceGuard g(nm->device);
+  std::lock_guard<std::recursive_mutex> lk(nm->mu);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc;
+  if ((rc = nm->sG.ensure(n * 4)) || (rc = nm->sPt.ensure(n * 12)) || (rc = nm->lists.ensure(n * 4))) return rc;
+  uint32_t* cnt = static_cast<uint32_t*>(nm->counters.p);
+  CK(cudaMemsetAsync(cnt, 0, 64, st));
+  if ((rc = snapLaunch(nm, pts, nullptr, n, static_cast<float*>(nm->sPt.p), static_cast<uint32_t*>(nm->sG.p),
+                       nullptr, nullptr, nullptr, 0.f, st)))
+    return rc;
+  WallArgs a{};
+  a.sG = static_cast<uint32_t*>(nm->sG.p);
+  a.sPt = static_cast<float*>(nm->sPt.p);
+  a.n = n;
+  a.counter = cnt + 0;
+  a.overflow = static_cast<uint32_t*>(nm->lists.p);
+  a.overflowCount = cnt + 1;
+  a.maxRadius = max_radius;
+  a.out_pos = out_hit_pos; a.out_normal = out_hit_normal; a.out_dist = out_hit_dist;
+  const int threads = kFpWarps * 32;
+  int64_t blocks = std::min<int64_t>(nm->blocksWallS, (n + kFpWarps - 1) / kFpWarps);
+  k_wall<kWallCapS, kWsShared><<<static_cast<unsigned>(blocks), threads,
+                                kFpWarps * wsSharedBytes(kWallCapS, kWsShared), st>>>(nm->view, a);
+  nm->launches++;
+  CK(cudaGetLastError());
+  WallArgs b = a;
+  b.work = a.overflow;
+  b.workCount = a.overflowCount;
+  b.counter = cnt + 2;
+  b.overflowCount = cnt + 3;
+  b.scratch = static_cast<char*>(nm->wsL.p);
+  k_wall<kCapL, kWsHybrid><<<nm->blocksFpL, threads, kFpWarps * wsSharedBytes(kCapL, kWsHybrid), st>>>(nm->view, b);
+  nm->launches++;
+  CK(cudaGetLastError());
+  return HBN_OK;
+}
+
+int hbn_random_points_dev(hbn_navmesh_t nm, uint64_t seed, uint64_t query0, int64_t n,
+                          const int32_t* islands, int max_tries, float* out_pts,
+                          uint32_t* out_refs, void* stream) {
+  if (!nm || (n > 0 && !out_pts)) return fail(HBN_ERR_INVALID, "null argument");
+  if (n <= 0) return HBN_OK;
+  if (nm->flat.totalArea <= 0.0f)
+    return fail(HBN_ERR_NO_AREA, "NavMesh has no navigable area, this indicates an issue with the NavMesh");
+  DeviceGuard g(nm->device);
+  const int groupsPerBlock = 256 / kRandW;
+  int64_t blocks = std::min<int64_t>((n + groupsPerBlock - 1) / groupsPerBlock,
+                                     static_cast<int64_t>(nm->smCount) * 64);
+  k_random<kRandW><<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      nm->view, seed, query0, n, islands, max_tries, out_pts, out_refs);
+  nm->launches++;
+  CK(cudaGetLastError());
+  return HBN_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------
+// host-buffer wrappers: stage through pinned memory on the handle's stream
+// ------------------------------------------------------------------------------------
+namespace {
+struct IoPlan {
+  hbn_navmesh* nm;
+  size_t off = 0;
+  struct Item { size_t off, bytes; const void* src; void* dst; };
+  std::vector<Item> items;
+  explicit IoPlan(hbn_navmesh* n) : nm(n) {}
+  size_t add(size_t bytes, const void* src, void* dst) {
+    const size_t o = off;
+    items.push_back({o, bytes, src, dst});
+    off += (bytes + 255) & ~size_t(255);
+    return o;
+  }
+  int prepare() {
+    int rc = nm->io.ensure(off);
+    if (rc) return rc;
+    if (off > nm->pinnedCap) {
+      if (nm->pinned) cudaFreeHost(nm->pinned);
+      nm->pinned = nullptr;
+      nm->pinnedCap = 0;
+      CK(cudaMallocHost(&nm->pinned, off + off / 4));
+      nm->pinnedCap = off + off / 4;
+    }
+    return HBN_OK;
+  }
+  template <class T> T* dev(size_t o) { return reinterpret_cast<T*>(static_cast<char*>(nm->io.p) + o); }
+  int h2d() {
+    for (auto& it : items)
+      if (it.src) {
+        memcpy(static_cast<char*>(nm->pinned) + it.off, it.src, it.bytes);
+        CK(cudaMemcpyAsync(static_cast<char*>(nm->io.p) + it.off, static_cast<char*>(nm->pinned) + it.off,
+                           it.bytes, cudaMemcpyHostToDevice, nm->stream));
+      }
+    return HBN_OK;
+  }
+  int d2h() {
+    for (auto& it : items)
+      if (it.dst)
+        CK(cudaMemcpyAsync(static_cast<char*>(nm->pinned) + it.off, static_cast<char*>(nm->io.p) + it.off,
+                           it.bytes, cudaMemcpyDeviceToHost, nm->stream));
+    CK(cudaStreamSynchronize(nm->stream));
+    for (auto& it : items)
+      if (it.dst) memcpy(it.dst, static_cast<char*>(nm->pinned) + it.off, it.bytes);
+    return HBN_OK;
+  }
+};
+}  // namespace
+
+extern "C" {
+
+#define HOST_PROLOGUE                                         \
+  if (!nm) return fail(HBN_ERR_INVALID, "null navmesh");      \
+  if (n <= 0) return HBN_OK;                                  \
+  DeviceGuard g_(nm->device);                                 \
+  std::lock_guard<std::recursive_mutex> lk_(nm->mu);          \
+  IoPlan io(nm);                                              \
+  int rc;
+
+int hbn_snap_point(hbn_navmesh_t nm, const float* pts, const int32_t* islands, int64_t n,
+                   float* out_pts, uint32_t* out_refs, int32_t* out_islands) {
+  HOST_PROLOGUE
+  const size_t oP = io.add(n * 12, pts, nullptr);
+  const size_t oI = islands ? io.add(n * 4, islands, nullptr) : 0;
+  const size_t oOP = out_pts ? io.add(n * 12, nullptr, out_pts) : 0;
+  const size_t oOR = out_refs ? io.add(n * 4, nullptr, out_refs) : 0;
+  const size_t oOI = out_islands ? io.add(n * 4, nullptr, out_islands) : 0;
+  if ((rc = io.prepare()) || (rc = io.h2d())) return rc;
+  if ((rc = hbn_snap_point_dev(nm, io.dev<float>(oP), islands ? io.dev<int32_t>(oI) : nullptr, n,
+                               out_pts ? io.dev<float>(oOP) : nullptr,
+                               out_refs ? io.dev<uint32_t>(oOR) : nullptr,
+                               out_islands ? io.dev<int32_t>(oOI) : nullptr, nm->stream)))
+    return rc;
+  return io.d2h();
+}
+
+int hbn_is_navigable(hbn_navmesh_t nm, const float* pts, int64_t n, float max_y_delta, uint8_t* out) {
+  HOST_PROLOGUE
+  const size_t oP = io.add(n * 12, pts, nullptr);
+  const size_t oO = io.add(n, nullptr, out);
+  if ((rc = io.prepare()) || (rc = io.h2d())) return rc;
+  if ((rc = hbn_is_navigable_dev(nm, io.dev<float>(oP), n, max_y_delta, io.dev<uint8_t>(oO), nm->stream)))
+    return rc;
+  return io.d2h();
+}
+
+int hbn_find_path(hbn_navmesh_t nm, const float* starts, const float* ends, int64_t n,
+                  float* out_dist, int32_t* out_npts, float* out_pts, int max_pts,
+                  uint32_t* out_corridor, int32_t* out_ncorridor, uint32_t* out_status, int flags) {
+  HOST_PROLOGUE
+  const size_t oS = io.add(n * 12, starts, nullptr);
+  const size_t oE = io.add(n * 12, ends, nullptr);
+  const size_t oD = io.add(n * 4, nullptr, out_dist);
+  const size_t oN = out_npts ? io.add(n * 4, nullptr, out_npts) : 0;
+  const size_t oP = out_pts ? io.add(static_cast<size_t>(n) * max_pts * 12, nullptr, out_pts) : 0;
+  const size_t oC = out_corridor ? io.add(static_cast<size_t>(n) * 256 * 4, nullptr, out_corridor) : 0;
+  const size_t oNC = out_ncorridor ? io.add(n * 4, nullptr, out_ncorridor) : 0;
+  const size_t oST = out_status ? io.add(n * 8, nullptr, out_status) : 0;
+  if ((rc = io.prepare()) || (rc = io.h2d())) return rc;
+  if (out_pts) CK(cudaMemsetAsync(io.dev<char>(oP), 0xff, static_cast<size_t>(n) * max_pts * 12, nm->stream));
+  if (out_corridor) CK(cudaMemsetAsync(io.dev<char>(oC), 0, static_cast<size_t>(n) * 256 * 4, nm->stream));
+  if ((rc = hbn_find_path_dev(nm, io.dev<float>(oS), io.dev<float>(oE), n, io.dev<float>(oD),
+                              out_npts ? io.dev<int32_t>(oN) : nullptr,
+                              out_pts ? io.dev<float>(oP) : nullptr, max_pts,
+                              out_corridor ? io.dev<uint32_t>(oC) : nullptr,
+                              out_ncorridor ? io.dev<int32_t>(oNC) : nullptr,
+                              out_status ? io.dev<uint32_t>(oST) : nullptr, flags, nm->stream)))
+    return rc;
+  return io.d2h();
+}
+
+int hbn_find_path_multigoal(hbn_navmesh_t nm, const float* starts, const float* ends, int64_t n,
+                            int g, float* out_dist, int32_t* out_index, int32_t* out_npts,
+                            float* out_pts, int max_pts) {
+  HOST_PROLOGUE
+  if (g <= 0) return fail(HBN_ERR_INVALID, "g must be positive");
+  const size_t oS = io.add(n * 12, starts, nullptr);
+  const size_t oE = io.add(static_cast<size_t>(n) * g * 12, ends, nullptr);
+  const size_t oD = io.add(n * 4, nullptr, out_dist);
+  const size_t oI = io.add(n * 4, nullptr, out_index);
+  const size_t oN = out_npts ? io.add(n * 4, nullptr, out_npts) : 0;
+  const size_t oP = out_pts ? io.add(static_cast<size_t>(n) * max_pts * 12, nullptr, out_pts) : 0;
+  if ((rc = io.prepare()) || (rc = io.h2d())) return rc;
+  if (out_pts) CK(cudaMemsetAsync(io.dev<char>(oP), 0xff, static_cast<size_t>(n) * max_pts * 12, nm->stream));
+  if ((rc = hbn_find_path_multigoal_dev(nm, io.dev<float>(oS), io.dev<float>(oE), n, g, io.dev<float>(oD),
+                                        io.dev<int32_t>(oI), out_npts ? io.dev<int32_t>(oN) : nullptr,
+                                        out_pts ? io.dev<float>(oP) : nullptr, max_pts, nm->stream)))
+    return rc;
+  return io.d2h();
+}
+
+int hbn_try_step(hbn_navmesh_t nm, const float* starts, const float* ends, int64_t n,
+                 int allow_sliding, float* out_pts) {
+  HOST_PROLOGUE
+  const size_t oS = io.add(n * 12, starts, nullptr);
+  const size_t oE = io.add(n * 12, ends, nullptr);
+  const size_t oO = io.add(n * 12, nullptr, out_pts);
+  if ((rc = io.prepare()) || (rc = io.h2d())) return rc;
+  if ((rc = hbn_try_step_dev(nm, io.dev<float>(oS), io.dev<float>(oE), n, allow_sliding, io.dev<float>(oO), nm->stream)))
+    return rc;
+  return io.d2h();
+}
+
+int hbn_closest_obstacle(hbn_navmesh_t nm, const float* pts, int64_t n, float max_radius,
+                         float* out_hit_pos, float* out_hit_normal, float* out_hit_dist) {
+  HOST_PROLOGUE
+  const size_t oP = io.add(n * 12, pts, nullptr);
+  const size_t oHP = out_hit_pos ? io.add(n * 12, nullptr, out_hit_pos) : 0;
+  const size_t oHN = out_hit_normal ? io.add(n * 12, nullptr, out_hit_normal) : 0;
+  const size_t oHD = io.add(n * 4, nullptr, out_hit_dist);
+  if ((rc = io.prepare()) || (rc = io.h2d())) return rc;
+  if ((rc = hbn_closest_obstacle_dev(nm, io.dev<float>(oP), n, max_radius,
+                                     out_hit_pos ? io.dev<float>(oHP) : nullptr,
+                                     out_hit_normal ? io.dev<float>(oHN) : nullptr, io.dev<float>(oHD), nm->stream)))
+    return rc;
+  return io.d2h();
+}
+
+int hbn_random_points(hbn_navmesh_t nm, uint64_t seed, uint64_t query0, int64_t n,
+                      const int32_t* islands, int max_tries, float* out_pts, uint32_t* out_refs) {
+  HOST_PROLOGUE
+  const size_t oI = islands ? io.add(n * 4, islands, nullptr) : 0;
+  const size_t oP = io.add(n * 12, nullptr, out_pts);
+  const size_t oR = out_refs ? io.add(n * 4, nullptr, out_refs) : 0;
+  if ((rc = io.prepare()) || (rc = io.h2d())) return rc;
+  if ((rc = hbn_random_points_dev(nm, seed, query0, n, islands ? io.dev<int32_t>(oI) : nullptr, max_tries,
+                                  io.dev<float>(oP), out_refs ? io.dev<uint32_t>(oR) : nullptr, nm->stream)))
+    return rc;
+  return io.d2h();
+}
+
+}  // extern "C"

@@ -1,0 +1,315 @@
+// CUDA kernels (sm_100a) of the batched navmesh query path.  The per-query algorithms live
+// in hbn_query.h; this file decides how queries map onto the machine.
+//
+//  k_snap<W>       W lanes per point: BV nodes are scanned W at a time with coalesced 16 B
+//                  loads, candidate polys evaluated W at a time (findNearestPoly).
+//  k_findpath<..>  one warp per query, pulled from an atomic work counter (query cost varies
+//                  by 1000x).  The A* node pool, open-list heap and hash live in a per-warp
+//                  workspace: shared memory for the small tier, shared heap+hash with
+//                  L2-resident node arrays for the 2048-node tier.  Queries that outgrow the
+//                  small tier are appended to an overflow list and re-run by the large tier
+//                  (the search is deterministic, so the re-run reproduces it).
+//  k_wall<..>      same workspace scheme for findDistanceToWall's Dijkstra.
+//  k_trystep_*     one thread per query (64-node BFS in local memory).
+//  k_random<W>     W lanes per sample; both reservoir scans run lane-parallel.
+#pragma once
+#include <cuda_runtime.h>
+#include "hbn_query.h"
+
+namespace hbn {
+
+constexpr float kPickExt[3] = {2.f, 4.f, 2.f};  // polyPickExt, PF.cpp:134
+
+// ------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(256) k_snap(NavView nav, const float* __restrict__ pts,
+                                              const int32_t* __restrict__ islands, int64_t n,
+                                              float* __restrict__ out_pts,
+                                              uint32_t* __restrict__ out_g,
+                                              uint32_t* __restrict__ out_refs,
+                                              int32_t* __restrict__ out_isl,
+                                              uint8_t* __restrict__ out_nav, float maxYDelta) {
+  __shared__ uint32_t queue[256 / W][2 * W];
+  WarpGroup<W> grp;
+  const int gInBlock = threadIdx.x / W;
+  const int64_t groupsPerGrid = static_cast<int64_t>(gridDim.x) * (blockDim.x / W);
+  const float ext[3] = {2.f, 4.f, 2.f};
+  for (int64_t q = static_cast<int64_t>(blockIdx.x) * (blockDim.x / W) + gInBlock; q < n;
+       q += groupsPerGrid) {
+    const float c[3] = {pts[3 * q], pts[3 * q + 1], pts[3 * q + 2]};
+    const int isl = islands ? islands[q] : -1;
+    const Nearest r = findNearestPoly(nav, grp, c, ext, isl, queue[gInBlock]);
+    grp.sync();
+    if (grp.lane() == 0) {
+      const bool ok = r.g != kNoPoly;
+      if (out_pts) {
+        out_pts[3 * q] = ok ? r.pt[0] : nanF();
+        out_pts[3 * q + 1] = ok ? r.pt[1] : nanF();
+        out_pts[3 * q + 2] = ok ? r.pt[2] : nanF();
+      }
+      if (out_g) out_g[q] = r.g;
+      if (out_refs) out_refs[q] = ok ? nav.polys[r.g].ref : 0u;
+      if (out_isl) out_isl[q] = ok ? nav.polys[r.g].island : -1;
+      if (out_nav) {  // isNavigable, PF.cpp:1814-1831
+        bool navOk = ok;
+        if (ok) {
+          const float dx = c[0] - r.pt[0], dz = c[2] - r.pt[2];
+          float d2 = 0.f;
+          d2 += dx * dx;
+          d2 += dz * dz;
+          if (fabsf(r.pt[1] - c[1]) > maxYDelta || fsqrt(d2) > 1e-2f) navOk = false;
+        }
+        out_nav[q] = navOk ? 1 : 0;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// workspace placement
+//   kWsShared : every array in shared memory
+//   kWsHybrid : heap (hkey/hidx) + hash in shared memory, node arrays in global scratch
+enum { kWsShared = 0, kWsHybrid = 1 };
+
+HBN_HD size_t wsSharedBytes(int cap, int place) {
+  return place == kWsShared ? astarWsBytes(cap) : static_cast<size_t>(cap) * (4 + 8 + 2);
+}
+HBN_HD size_t wsGlobalBytes(int cap, int place) {
+  return place == kWsShared ? 0 : static_cast<size_t>(cap) * (5 * 4 + 4 + 4 + 2 + 2);
+}
+
+__device__ __forceinline__ AStarWs wsCarveHybrid(void* sm, void* gl, int cap) {
+  AStarWs w;
+  char* p = static_cast<char*>(gl);
+  w.px = reinterpret_cast<float*>(p); p += 4 * cap;
+  w.py = reinterpret_cast<float*>(p); p += 4 * cap;
+  w.pz = reinterpret_cast<float*>(p); p += 4 * cap;
+  w.cost = reinterpret_cast<float*>(p); p += 4 * cap;
+  w.total = reinterpret_cast<float*>(p); p += 4 * cap;
+  w.gid = reinterpret_cast<uint32_t*>(p); p += 4 * cap;
+  w.lnk = reinterpret_cast<uint32_t*>(p); p += 4 * cap;
+  w.pidx = reinterpret_cast<uint16_t*>(p); p += 2 * cap;
+  w.hpos = reinterpret_cast<uint16_t*>(p); p += 2 * cap;
+  char* s = static_cast<char*>(sm);
+  w.hkey = reinterpret_cast<float*>(s); s += 4 * cap;
+  w.hash = reinterpret_cast<uint32_t*>(s); s += 8 * cap;
+  w.hidx = reinterpret_cast<uint16_t*>(s); s += 2 * cap;
+  w.cap = cap;
+  w.hashMask = 2 * cap - 1;
+  return w;
+}
+
+struct FindPathArgs {
+  const float* starts;    // requested points
+  const float* ends;
+  const uint32_t* sG;     // projectToPoly results
+  const float* sPt;
+  const uint32_t* eG;
+  const float* ePt;
+  int64_t n;              // total queries (when work == nullptr)
+  const uint32_t* work;   // optional list of query indices
+  const uint32_t* workCount;
+  uint32_t* counter;      // atomic work cursor
+  uint32_t* overflow;     // queries that outgrew this tier
+  uint32_t* overflowCount;
+  float* out_dist;
+  int32_t* out_npts;
+  float* out_pts;
+  int max_pts;
+  uint32_t* out_corridor;
+  int32_t* out_ncorridor;
+  uint32_t* out_status;
+  char* scratch;          // global workspace, one slot per warp of the grid (hybrid)
+  int fastFail;
+};
+
+template <int CAP, int PLACE>
+__global__ void __launch_bounds__(128) k_findpath(NavView nav, FindPathArgs a) {
+  extern __shared__ __align__(16) char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warpsPerBlock = blockDim.x >> 5;
+  AStarWs w;
+  if (PLACE == kWsShared) {
+    w = astarWsCarve(smem + static_cast<size_t>(warp) * astarWsBytes(CAP), CAP);
+  } else {
+    const size_t slot = static_cast<size_t>(blockIdx.x) * warpsPerBlock + warp;
+    w = wsCarveHybrid(smem + static_cast<size_t>(warp) * wsSharedBytes(CAP, PLACE),
+                      a.scratch + slot * wsGlobalBytes(CAP, PLACE), CAP);
+  }
+  const uint32_t total = a.work ? *a.workCount : static_cast<uint32_t>(a.n);
+  for (;;) {
+    uint32_t wi = 0;
+    if (lane == 0) wi = atomicAdd(a.counter, 1u);
+    wi = __shfl_sync(0xffffffffu, wi, 0);
+    if (wi >= total) break;
+    const int64_t q = a.work ? a.work[wi] : wi;
+    for (int i = lane; i < 2 * CAP; i += 32) w.hash[i] = 0u;
+    __syncwarp();
+    if (lane == 0) {
+      const float rs[3] = {a.starts[3 * q], a.starts[3 * q + 1], a.starts[3 * q + 2]};
+      const float re[3] = {a.ends[3 * q], a.ends[3 * q + 1], a.ends[3 * q + 2]};
+      const float sp[3] = {a.sPt[3 * q], a.sPt[3 * q + 1], a.sPt[3 * q + 2]};
+      const float ep[3] = {a.ePt[3 * q], a.ePt[3 * q + 1], a.ePt[3 * q + 2]};
+      const PathResult r = findPathInternal(
+          nav, w, rs, re, a.sG[q], sp, a.eG[q], ep, a.fastFail != 0,
+          a.out_pts ? a.out_pts + static_cast<size_t>(q) * a.max_pts * 3 : nullptr, a.max_pts,
+          a.out_corridor ? a.out_corridor + static_cast<size_t>(q) * kMaxPathPolys : nullptr);
+      if (r.overflow) {
+        const uint32_t o = atomicAdd(a.overflowCount, 1u);
+        a.overflow[o] = static_cast<uint32_t>(q);
+      } else {
+        a.out_dist[q] = r.dist;
+        if (a.out_npts) a.out_npts[q] = (r.flags & 4u) ? r.npts : 0;
+        if (a.out_ncorridor) a.out_ncorridor[q] = r.ncorridor;
+        if (a.out_status) {
+          a.out_status[2 * q] = r.astarStatus;
+          a.out_status[2 * q + 1] = r.straightStatus;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------
+struct WallArgs {
+  const uint32_t* sG;
+  const float* sPt;
+  int64_t n;
+  const uint32_t* work;
+  const uint32_t* workCount;
+  uint32_t* counter;
+  uint32_t* overflow;
+  uint32_t* overflowCount;
+  float maxRadius;
+  float* out_pos;
+  float* out_normal;
+  float* out_dist;
+  char* scratch;
+};
+
+template <int CAP, int PLACE>
+__global__ void __launch_bounds__(128) k_wall(NavView nav, WallArgs a) {
+  extern __shared__ __align__(16) char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warpsPerBlock = blockDim.x >> 5;
+  AStarWs w;
+  if (PLACE == kWsShared) {
+    w = astarWsCarve(smem + static_cast<size_t>(warp) * astarWsBytes(CAP), CAP);
+  } else {
+    const size_t slot = static_cast<size_t>(blockIdx.x) * warpsPerBlock + warp;
+    w = wsCarveHybrid(smem + static_cast<size_t>(warp) * wsSharedBytes(CAP, PLACE),
+                      a.scratch + slot * wsGlobalBytes(CAP, PLACE), CAP);
+  }
+  const uint32_t total = a.work ? *a.workCount : static_cast<uint32_t>(a.n);
+  for (;;) {
+    uint32_t wi = 0;
+    if (lane == 0) wi = atomicAdd(a.counter, 1u);
+    wi = __shfl_sync(0xffffffffu, wi, 0);
+    if (wi >= total) break;
+    const int64_t q = a.work ? a.work[wi] : wi;
+    for (int i = lane; i < 2 * CAP; i += 32) w.hash[i] = 0u;
+    __syncwarp();
+    if (lane == 0) {
+      // closestObstacleSurfacePoint, PF.cpp:1794-1812
+      float hp[3] = {0.f, 0.f, 0.f}, hn[3] = {0.f, 0.f, 0.f};
+      float hd = infF();
+      bool overflow = false;
+      const uint32_t g = a.sG[q];
+      if (g != kNoPoly) {
+        const float c[3] = {a.sPt[3 * q], a.sPt[3 * q + 1], a.sPt[3 * q + 2]};
+        hd = nanF();
+        const uint32_t st = distanceToWall(nav, w, g, c, a.maxRadius, &hd, hp, hn);
+        overflow = st == 0xffffffffu;
+      }
+      if (overflow) {
+        const uint32_t o = atomicAdd(a.overflowCount, 1u);
+        a.overflow[o] = static_cast<uint32_t>(q);
+      } else {
+        if (a.out_pos) { a.out_pos[3 * q] = hp[0]; a.out_pos[3 * q + 1] = hp[1]; a.out_pos[3 * q + 2] = hp[2]; }
+        if (a.out_normal) { a.out_normal[3 * q] = hn[0]; a.out_normal[3 * q + 1] = hn[1]; a.out_normal[3 * q + 2] = hn[2]; }
+        a.out_dist[q] = hd;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// tryStep phase A / B (PF.cpp:1575-1722), one thread per query
+__global__ void __launch_bounds__(128) k_trystep_a(NavView nav, const float* __restrict__ ends,
+                                                   const uint32_t* __restrict__ sG,
+                                                   const float* __restrict__ sPt,
+                                                   const uint32_t* __restrict__ eG, int64_t n,
+                                                   int allowSliding, float* __restrict__ endPoint,
+                                                   uint32_t* __restrict__ lastPoly) {
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const float sp[3] = {sPt[3 * q], sPt[3 * q + 1], sPt[3 * q + 2]};
+  const float en[3] = {ends[3 * q], ends[3 * q + 1], ends[3 * q + 2]};
+  float ep[3];
+  uint32_t last = kNoPoly;
+  const bool ok = tryStepPhaseA(nav, sG[q], sp, eG[q], en, allowSliding != 0, ep, &last);
+  endPoint[3 * q] = ok ? ep[0] : nanF();
+  endPoint[3 * q + 1] = ok ? ep[1] : nanF();
+  endPoint[3 * q + 2] = ok ? ep[2] : nanF();
+  lastPoly[q] = ok ? last : kNoPoly;
+}
+
+__global__ void __launch_bounds__(256) k_trystep_b(NavView nav, const float* __restrict__ starts,
+                                                   const uint32_t* __restrict__ sG,
+                                                   const uint32_t* __restrict__ e2G,
+                                                   const uint32_t* __restrict__ lastPoly,
+                                                   const float* __restrict__ endPoint, int64_t n,
+                                                   float* __restrict__ out) {
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const uint32_t last = lastPoly[q];
+  if (last == kNoPoly) {  // tryStep returned `start` unchanged
+    out[3 * q] = starts[3 * q];
+    out[3 * q + 1] = starts[3 * q + 1];
+    out[3 * q + 2] = starts[3 * q + 2];
+    return;
+  }
+  float ep[3] = {endPoint[3 * q], endPoint[3 * q + 1], endPoint[3 * q + 2]};
+  tryStepPhaseB(nav, sG[q], e2G[q], last, ep);
+  out[3 * q] = ep[0];
+  out[3 * q + 1] = ep[1];
+  out[3 * q + 2] = ep[2];
+}
+
+// ------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(256) k_random(NavView nav, uint64_t seed, uint64_t query0,
+                                                int64_t n, const int32_t* __restrict__ islands,
+                                                int maxTries, float* __restrict__ out_pts,
+                                                uint32_t* __restrict__ out_refs) {
+  WarpGroup<W> grp;
+  const int gInBlock = threadIdx.x / W;
+  const int64_t groupsPerGrid = static_cast<int64_t>(gridDim.x) * (blockDim.x / W);
+  for (int64_t q = static_cast<int64_t>(blockIdx.x) * (blockDim.x / W) + gInBlock; q < n;
+       q += groupsPerGrid) {
+    const int isl = islands ? islands[q] : -1;
+    uint32_t draw = 0;
+    uint32_t g = kNoPoly;
+    float pt[3] = {nanF(), nanF(), nanF()};
+    for (int t = 0; t < maxTries; ++t) {
+      uint32_t used = 0;
+      float p[3];
+      g = findRandomPoint(nav, grp, seed, query0 + static_cast<uint64_t>(q), draw, isl, p, &used);
+      draw += used;
+      if (g != kNoPoly) {
+        pt[0] = p[0]; pt[1] = p[1]; pt[2] = p[2];
+        break;
+      }
+    }
+    if (grp.lane() == 0) {
+      out_pts[3 * q] = pt[0];
+      out_pts[3 * q + 1] = pt[1];
+      out_pts[3 * q + 2] = pt[2];
+      if (out_refs) out_refs[q] = g != kNoPoly ? nav.polys[g].ref : 0u;
+    }
+  }
+}
+
+}  // namespace hbn

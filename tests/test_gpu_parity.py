@@ -1,0 +1,269 @@
+"""GPU parity tests: the CUDA path, called through the C ABI of libhbn.so (ctypes ->
+hbn_* host/device entry points), against the oracle on the same seeded inputs, against the
+committed golden vectors, and through size-independent properties at larger sizes.
+Bar: poly refs, corridors, island ids bit-exact; floats within 1e-5 relative (they are in
+fact compared bit for bit, NaN == NaN)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import beq, gpu_pathfinder, navmesh_image, query_points, ref_pathfinder
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+SCENES = ["c1_room", "c2_apartment", "c3_multiroom", "t_building"]
+RTOL = 1e-5  # north_star tolerance for float outputs
+
+
+def close(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    both_nan = np.isnan(a) & np.isnan(b)
+    both_inf = np.isinf(a) & np.isinf(b) & (np.sign(a) == np.sign(b))
+    with np.errstate(invalid="ignore"):
+        ok = np.abs(a - b) <= RTOL * np.maximum(np.abs(a), np.abs(b)) + 1e-7
+    return ok | both_nan | both_inf
+
+
+@pytest.fixture(scope="module", params=SCENES)
+def scene(request):
+    name = request.param
+    return name, gpu_pathfinder(name), ref_pathfinder(name)
+
+
+def test_native_library_is_the_loaded_one(scene):
+    name, pf, _ = scene
+    import habitat_sim_b200
+    maps = open("/proc/self/maps").read()
+    assert habitat_sim_b200.library_path() in maps
+    assert pf.launch_count >= 0
+
+
+def test_islands_and_properties(scene):
+    name, pf, ref = scene
+    assert pf.num_islands == ref.num_islands
+    for i in range(ref.num_islands):
+        assert pf.island_radius(i) == ref.island_radius(i)
+        assert pf.island_area(i) == ref.navigable_area(i)
+    assert close(pf.navigable_area, ref.navigable_area())
+    lo, hi = pf.get_bounds()
+    rlo, rhi = ref.get_bounds()
+    assert (lo == rlo).all() and (hi == rhi).all()
+
+
+def test_snap_point(scene):
+    name, pf, ref = scene
+    pts = query_points(name, 20000, 31)
+    lo, hi = ref.get_bounds()
+    rng = np.random.default_rng(1)
+    pts[:2000] = rng.uniform(lo - 3, hi + 3, (2000, 3)).astype(np.float32)
+    pts[2000:2004] = np.nan
+    pts[2004] = np.inf
+    want_p, want_r, want_i = ref.snap_batch(pts, 8)
+    got_p, got_r, got_i = pf.snap_points(pts)
+    assert (got_r == want_r).all(), "nearest-poly refs must be bit-exact"
+    assert (got_i == want_i).all(), "island ids must be bit-exact"
+    assert close(got_p, want_p).all()
+    assert beq(got_p, want_p).all()
+    # island restricted (PathFinder.cpp:1725-1757)
+    isl = rng.integers(0, ref.num_islands, 500).astype(np.int32)
+    wp, wr = ref.snap_island_batch(pts[:500], isl)
+    gp, gr, gi = pf.snap_points(pts[:500], isl)
+    assert (gr == wr).all() and beq(gp, wp).all()
+    # is_navigable
+    assert (pf.are_navigable(pts[:5000]) == ref.is_navigable_batch(pts[:5000], 0.5, 8)).all()
+
+
+def test_find_path(scene):
+    name, pf, ref = scene
+    n = 6000
+    pts = query_points(name, 2 * n, 32)
+    st, en = pts[:n].copy(), pts[n:].copy()
+    rng = np.random.default_rng(2)
+    en[:300] = st[:300] + rng.normal(0, 0.01, (300, 3)).astype(np.float32)
+    en[300:310] = st[300:310]
+    st[310:314] = np.nan
+    lo, hi = ref.get_bounds()
+    st[314:320] = (hi + 40).astype(np.float32)
+    want = ref.find_path_raw_batch(st, en, max_pts=64, nthreads=8)
+    got = pf.find_paths(st, en, max_points=64, corridors=True)
+    assert close(got["geodesic_distance"], want["dist"]).all()
+    assert beq(got["geodesic_distance"], want["dist"]).all()
+    found = (want["flags"] & 4) != 0
+    assert found.mean() > 0.3
+    assert (got["num_points"][found] == want["num_points"][found]).all()
+    assert (got["num_points"][~found] == 0).all()
+    ran = found & ((want["flags"] & 1) == 0)  # A* / same-poly corridor exists
+    assert (got["num_corridor"][ran] == want["num_polys"][ran]).all()
+    for i in np.nonzero(ran)[0]:
+        k = want["num_polys"][i]
+        assert (got["corridor"][i, :k] == want["corridor"][i, :k]).all(), "corridors must be bit-exact"
+    for i in np.nonzero(found)[0]:
+        m = min(want["num_points"][i], 64)
+        assert beq(got["points"][i, :m], want["pts"][i, :m]).all()
+    # Detour-exact mode: status words and corridors of failed queries as well
+    got2 = pf.find_paths(st, en, corridors=True, exact_status=True)
+    astar_ran = ((want["flags"] & 2) != 0)
+    assert (got2["status"][astar_ran, 0] == want["astar_status"][astar_ran]).all()
+    for i in np.nonzero(astar_ran)[0]:
+        k = want["num_polys"][i]
+        assert got2["num_corridor"][i] == k and (got2["corridor"][i, :k] == want["corridor"][i, :k]).all()
+    assert beq(got2["geodesic_distance"], want["dist"]).all()
+
+
+def test_try_step(scene):
+    name, pf, ref = scene
+    from workloads.scenes import step_targets
+    n = 8000
+    s = ref.snap_batch(query_points(name, n, 33), 8)[0]
+    s[np.isnan(s)] = 0
+    t = step_targets(s, 5, 0.25)
+    t[:2000] = step_targets(s[:2000], 6, 2.5)
+    for sliding in (True, False):
+        want = ref.try_step_batch(s, t, sliding, 8)
+        got = pf.try_steps(s, t, sliding)
+        assert close(got, want).all()
+        assert beq(got, want).all()
+
+
+def test_closest_obstacle(scene):
+    name, pf, ref = scene
+    pts = query_points(name, 10000, 34)
+    hp, hn, hd = ref.obstacle_batch(pts, 2.0, 8)
+    gp, gn, gd = pf.closest_obstacle_surface_points(pts, 2.0)
+    assert close(gd, hd).all() and beq(gd, hd).all()
+    assert beq(gp, hp).all() and beq(gn, hn).all()
+    hd5 = ref.obstacle_batch(pts[:2000], 0.5, 8)[2]
+    assert beq(pf.distances_to_closest_obstacle(pts[:2000], 0.5), hd5).all()
+
+
+def test_random_points(scene):
+    name, pf, ref = scene
+    n = 3000
+    rng = np.random.default_rng(3)
+    isl = np.full(n, -1, np.int32)
+    isl[n // 2:] = rng.integers(0, ref.num_islands, n - n // 2)
+    want_p, want_r = ref.random_points(n, 10, isl, mode=1, seed=77, query0=123)
+    got_p, got_r = pf.random_navigable_points(n, 10, isl, seed=77, query0=123)
+    assert (got_r == want_r).all()
+    assert beq(got_p, want_p).all()
+    ok = ~np.isnan(got_p[:, 0])
+    assert pf.are_navigable(got_p[ok]).all()
+    # shard-count invariance: sample i only depends on (seed, query0 + i)
+    a, _ = pf.random_navigable_points(100, 10, -1, seed=5, query0=40)
+    b, _ = pf.random_navigable_points(50, 10, -1, seed=5, query0=90)
+    assert beq(a[50:], b).all()
+
+
+@pytest.mark.parametrize("name", ["c1_room", "c2_apartment", "t_building"])
+def test_golden_vectors(name):
+    """committed fixtures (tests/golden/*.npz, made by make_golden.py from the oracle)"""
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    from habitat_sim_b200.nav import PathFinder
+    pf = PathFinder(0)
+    assert pf.load_nav_mesh_bytes(g["image"].tobytes())
+    sp, sr, si = pf.snap_points(g["starts"])
+    assert (sr == g["snap_refs"]).all() and (si == g["snap_isl"]).all() and beq(sp, g["snap_pts"]).all()
+    r = pf.find_paths(g["starts"], g["ends"], max_points=32, corridors=True, exact_status=True)
+    assert beq(r["geodesic_distance"], g["dist"]).all()
+    ran = (g["flags"] & 2) != 0
+    assert (r["num_corridor"][ran] == g["num_polys"][ran]).all()
+    k = np.minimum(g["num_polys"], 64)
+    for i in np.nonzero(ran)[0]:
+        assert (r["corridor"][i, :k[i]] == g["corridor"][i, :k[i]]).all()
+    assert beq(pf.try_steps(g["snap_pts"], g["step_targets"], True), g["step_sliding"]).all()
+    assert beq(pf.try_steps(g["snap_pts"], g["step_targets"], False), g["step_nosliding"]).all()
+    hp, hn, hd = pf.closest_obstacle_surface_points(g["starts"], 2.0)
+    assert beq(hd, g["hit_dist"]).all() and beq(hp, g["hit_pos"]).all() and beq(hn, g["hit_normal"]).all()
+    seed = {"c1_room": 11, "c2_apartment": 12, "t_building": 13}[name]
+    rp, rr = pf.random_navigable_points(len(g["rand_islands"]), 10, g["rand_islands"], seed=seed, query0=1000)
+    assert (rr == g["rand_refs"]).all() and beq(rp, g["rand_pts"]).all()
+    assert pf.num_islands == int(g["num_islands"])
+
+
+def test_device_pointer_path_matches_host_path():
+    import torch
+    pf = gpu_pathfinder("t_building")
+    pts = query_points("t_building", 4000, 35)
+    st, en = pts[:2000], pts[2000:]
+    host = pf.find_paths(st, en, max_points=16)
+    dev = pf.find_paths(torch.from_numpy(st).cuda(), torch.from_numpy(en).cuda(), max_points=16)
+    torch.cuda.synchronize()
+    assert beq(dev["geodesic_distance"].cpu().numpy(), host["geodesic_distance"]).all()
+    assert (dev["num_points"].cpu().numpy() == host["num_points"]).all()
+    sp = pf.snap_points(torch.from_numpy(st).cuda())
+    assert beq(sp[0].cpu().numpy(), pf.snap_points(st)[0]).all()
+
+
+def test_scalar_api_matches_reference_conventions():
+    """SPB.cpp:177-270 failure sentinels through the scalar drop-in methods"""
+    from habitat_sim_b200.nav import ShortestPath
+    pf = gpu_pathfinder("c1_room")
+    ref = ref_pathfinder("c1_room")
+    lo, hi = pf.get_bounds()
+    far = hi + 100
+    assert np.isnan(pf.snap_point(far)).all()
+    assert pf.get_island(far) == -1
+    assert not pf.is_navigable(far)
+    assert np.isinf(pf.distance_to_closest_obstacle(far))
+    hr = pf.closest_obstacle_surface_point(far)
+    assert np.isinf(hr.hit_dist) and (hr.hit_pos == 0).all() and (hr.hit_normal == 0).all()
+    assert (pf.try_step(far, far + 1) == far.astype(np.float32)).all()
+    p = ShortestPath()
+    p.requested_start = far
+    p.requested_end = far + 1
+    assert not pf.find_path(p) and np.isinf(p.geodesic_distance) and p.points == []
+    a = ref.random_points(2, 10, [0, 0], mode=1, seed=1)[0]
+    p.requested_start, p.requested_end = a[0], a[1]
+    assert pf.find_path(p)
+    d, n, pts = ref.find_path_batch(a[:1], a[1:], 256)
+    assert p.geodesic_distance == d[0] and len(p.points) == n[0]
+    with pytest.raises(ValueError):
+        pf.snap_point(a[0], island_index=99)
+
+
+def test_topdown_views_match_reference_loops():
+    pf = gpu_pathfinder("c2_apartment")
+    ref = ref_pathfinder("c2_apartment")
+    mpp, height = 0.1, 0.1
+    view = pf.get_topdown_view(mpp, height)
+    isl = pf.get_topdown_island_view(mpp, height)
+    pts = pf._topdown_grid(mpp, height).reshape(-1, 3)
+    want = ref.is_navigable_batch(pts, 0.5, 8).reshape(view.shape)
+    assert (view == want).all() and view.any()
+    wi = np.where(want.reshape(-1), ref.snap_batch(pts, 8)[2], -1).reshape(view.shape)
+    assert (isl == wi).all()
+
+
+def test_full_size_properties():
+    """BASELINE config C4 sizes: properties that need no oracle pass over the full batch."""
+    from workloads.scenes import NavMeshGeom, pointnav_pairs
+    pf = gpu_pathfinder("c4_building")
+    ref = ref_pathfinder("c4_building")
+    geom = NavMeshGeom(navmesh_image("c4_building"))
+    n = 200_000
+    st, en = pointnav_pairs(geom, n, 7)
+    r = pf.find_paths(st, en)
+    d = r["geodesic_distance"]
+    sp, sr, si = pf.snap_points(st)
+    ep, er, ei = pf.snap_points(en)
+    found = np.isfinite(d)
+    assert 0.2 < found.mean() < 1.0
+    # geodesic >= euclid between the snapped end points (1e-4 slack), same island required
+    eu = np.linalg.norm(sp - ep, axis=1)
+    assert (d[found] >= eu[found] * (1 - 1e-4) - 1e-4).all()
+    assert (si[found] == ei[found]).all()
+    # idempotence of snapping, navigability of snapped points
+    ok = sr != 0
+    sp2, sr2, _ = pf.snap_points(sp[ok])
+    assert (sr2 != 0).all()
+    assert pf.are_navigable(sp[ok]).all()
+    # batch-split invariance (multi-GPU sharding is a plain split of the batch)
+    d2 = np.concatenate([pf.find_paths(st[:n // 3], en[:n // 3])["geodesic_distance"],
+                         pf.find_paths(st[n // 3:], en[n // 3:])["geodesic_distance"]])
+    assert beq(d, d2).all()
+    # success fraction and values equal the oracle's on a bounded sample
+    m = 4000
+    want = ref.find_path_batch(st[:m], en[:m], 0, 8)[0]
+    assert beq(d[:m], want).all()
