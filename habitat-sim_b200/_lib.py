@@ -18,6 +18,7 @@ u8p = C.POINTER(C.c_uint8)
 HBN_OK = 0
 HBN_ERR_NO_AREA = 5
 HBN_FP_EXACT_STATUS = 1
+HBN_FP_COUNT_WORK = 2
 
 
 class HbnError(RuntimeError):
@@ -55,7 +56,8 @@ SYMBOLS = [
     "hbn_last_error", "hbn_device_count", "hbn_navmesh_create_from_mset",
     "hbn_navmesh_create_from_tiles", "hbn_navmesh_destroy", "hbn_navmesh_get_info",
     "hbn_navmesh_island_info", "hbn_navmesh_get_settings", "hbn_navmesh_launch_count",
-    "hbn_navmesh_triangles", "hbn_snap_point_dev", "hbn_is_navigable_dev", "hbn_find_path_dev",
+    "hbn_navmesh_triangles", "hbn_navmesh_work_counters", "hbn_navmesh_set_profiling",
+    "hbn_navmesh_phase_times", "hbn_snap_point_dev", "hbn_is_navigable_dev", "hbn_find_path_dev",
     "hbn_find_path_multigoal_dev", "hbn_try_step_dev", "hbn_closest_obstacle_dev",
     "hbn_random_points_dev", "hbn_uniform", "hbn_snap_point", "hbn_is_navigable",
     "hbn_find_path", "hbn_find_path_multigoal", "hbn_try_step", "hbn_closest_obstacle",
@@ -75,6 +77,9 @@ def lib():
         l.hbn_uniform.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32]
         l.hbn_navmesh_launch_count.restype = C.c_int64
         l.hbn_navmesh_launch_count.argtypes = [C.c_void_p]
+        l.hbn_navmesh_work_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        l.hbn_navmesh_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        l.hbn_navmesh_phase_times.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         l.hbn_navmesh_triangles.restype = C.c_int64
         l.hbn_navmesh_triangles.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]
         l.hbn_navmesh_create_from_mset.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]

@@ -69,11 +69,15 @@ struct hbn_navmesh {
   int64_t launches = 0;
   std::recursive_mutex mu;
   // scratch (device)
-  DevBuf sG, eG, e2G, sPt, ePt, epPt, lastPoly, lists, counters, wsL, io;
+  DevBuf sG, eG, e2G, sPt, ePt, epPt, lastPoly, lists, counters, wsL, io, work;
   // pinned staging for the host-buffer entry points
   void* pinned = nullptr;
   size_t pinnedCap = 0;
   int blocksFpS = 0, blocksFpL = 0, blocksWallS = 0;
+  // optional phase timing of hbn_find_path_dev (hbn_navmesh_set_profiling)
+  bool profile = false;
+  struct PhaseEv { cudaEvent_t e[3]; };
+  std::vector<PhaseEv> phaseEvents;
 };
 
 namespace {
@@ -156,6 +160,8 @@ int finishCreate(HostNavMesh& mesh, const int32_t* islands, int device, hbn_navm
   // global node arrays of the large tier: one slot per resident warp
   rc = nm->wsL.ensure(static_cast<size_t>(nm->blocksFpL) * kFpWarps * wsGlobalBytes(kCapL, kWsHybrid));
   if (rc == HBN_OK) rc = nm->counters.ensure(64);
+  if (rc == HBN_OK) rc = nm->work.ensure(64);
+  if (rc == HBN_OK && cudaMemset(nm->work.p, 0, 64) != cudaSuccess) rc = fail(HBN_ERR_CUDA, "cudaMemset");
   if (rc != HBN_OK) {
     hbn_navmesh_destroy(nm);
     return rc;
@@ -238,7 +244,7 @@ void hbn_navmesh_destroy(hbn_navmesh_t nm) {
   DeviceGuard g(nm->device);
   for (void* d : nm->devArrays) cudaFree(d);
   for (DevBuf* b : {&nm->sG, &nm->eG, &nm->e2G, &nm->sPt, &nm->ePt, &nm->epPt, &nm->lastPoly,
-                    &nm->lists, &nm->counters, &nm->wsL, &nm->io})
+                    &nm->lists, &nm->counters, &nm->wsL, &nm->io, &nm->work})
     b->release();
   if (nm->pinned) cudaFreeHost(nm->pinned);
   if (nm->stream) cudaStreamDestroy(nm->stream);
@@ -285,6 +291,41 @@ int hbn_navmesh_get_settings(hbn_navmesh_t nm, void* out56) {
 }
 
 int64_t hbn_navmesh_launch_count(hbn_navmesh_t nm) { return nm ? nm->launches : 0; }
+
+int hbn_navmesh_set_profiling(hbn_navmesh_t nm, int enable) {
+  if (!nm) return fail(HBN_ERR_INVALID, "null argument");
+  std::lock_guard<std::recursive_mutex> lk(nm->mu);
+  nm->profile = enable != 0;
+  return HBN_OK;
+}
+
+int hbn_navmesh_phase_times(hbn_navmesh_t nm, double* out_ms2, int64_t* out_calls) {
+  if (!nm || !out_ms2) return fail(HBN_ERR_INVALID, "null argument");
+  DeviceGuard g(nm->device);
+  std::lock_guard<std::recursive_mutex> lk(nm->mu);
+  out_ms2[0] = out_ms2[1] = 0.0;
+  if (out_calls) *out_calls = static_cast<int64_t>(nm->phaseEvents.size());
+  for (auto& pe : nm->phaseEvents) {
+    CK(cudaEventSynchronize(pe.e[2]));
+    float a = 0.f, b = 0.f;
+    CK(cudaEventElapsedTime(&a, pe.e[0], pe.e[1]));
+    CK(cudaEventElapsedTime(&b, pe.e[1], pe.e[2]));
+    out_ms2[0] += a;
+    out_ms2[1] += b;
+    for (auto& e : pe.e) cudaEventDestroy(e);
+  }
+  nm->phaseEvents.clear();
+  return HBN_OK;
+}
+
+int hbn_navmesh_work_counters(hbn_navmesh_t nm, uint64_t* out8, int reset) {
+  if (!nm || !out8) return fail(HBN_ERR_INVALID, "null argument");
+  DeviceGuard g(nm->device);
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out8, nm->work.p, 64, cudaMemcpyDeviceToHost));
+  if (reset) CK(cudaMemset(nm->work.p, 0, 64));
+  return HBN_OK;
+}
 
 int64_t hbn_navmesh_triangles(hbn_navmesh_t nm, int island, float* out, int64_t cap_tris) {
   if (!nm) return -1;
@@ -342,12 +383,18 @@ int hbn_find_path_dev(hbn_navmesh_t nm, const float* starts, const float* ends, 
     return rc;
   uint32_t* cnt = static_cast<uint32_t*>(nm->counters.p);
   CK(cudaMemsetAsync(cnt, 0, 64, st));
+  hbn_navmesh::PhaseEv pe{};
+  if (nm->profile) {
+    for (auto& e : pe.e) CK(cudaEventCreate(&e));
+    CK(cudaEventRecord(pe.e[0], st));
+  }
   if ((rc = snapLaunch(nm, starts, nullptr, n, static_cast<float*>(nm->sPt.p),
                        static_cast<uint32_t*>(nm->sG.p), nullptr, nullptr, nullptr, 0.f, st)))
     return rc;
   if ((rc = snapLaunch(nm, ends, nullptr, n, static_cast<float*>(nm->ePt.p),
                        static_cast<uint32_t*>(nm->eG.p), nullptr, nullptr, nullptr, 0.f, st)))
     return rc;
+  if (nm->profile) CK(cudaEventRecord(pe.e[1], st));
   FindPathArgs a{};
   a.starts = starts; a.ends = ends;
   a.sG = static_cast<uint32_t*>(nm->sG.p); a.sPt = static_cast<float*>(nm->sPt.p);
@@ -361,6 +408,7 @@ int hbn_find_path_dev(hbn_navmesh_t nm, const float* starts, const float* ends, 
   a.out_corridor = out_corridor; a.out_ncorridor = out_ncorridor; a.out_status = out_status;
   a.scratch = nullptr;
   a.fastFail = (flags & HBN_FP_EXACT_STATUS) ? 0 : 1;
+  a.workCtr = (flags & HBN_FP_COUNT_WORK) ? static_cast<unsigned long long*>(nm->work.p) : nullptr;
   const int threads = kFpWarps * 32;
   {
     int64_t blocks = std::min<int64_t>(nm->blocksFpS, (n + kFpWarps - 1) / kFpWarps);
@@ -380,6 +428,10 @@ int hbn_find_path_dev(hbn_navmesh_t nm, const float* starts, const float* ends, 
   k_findpath<kCapL, kWsHybrid><<<nm->blocksFpL, threads, kFpWarps * wsSharedBytes(kCapL, kWsHybrid), st>>>(nm->view, b);
   nm->launches++;
   CK(cudaGetLastError());
+  if (nm->profile) {
+    CK(cudaEventRecord(pe.e[2], st));
+    nm->phaseEvents.push_back(pe);
+  }
   return HBN_OK;
 }
 

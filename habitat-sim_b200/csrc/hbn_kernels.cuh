@@ -121,6 +121,10 @@ struct FindPathArgs {
   uint32_t* out_status;
   char* scratch;          // global workspace, one slot per warp of the grid (hybrid)
   int fastFail;
+  // optional work counters (HBN_FP_COUNT_WORK): [0] expanded polys, [1] their links,
+  // [2] their non-null neighbours, [3] corridor polys, [4] corridor links, [5] path points,
+  // [6] queries that ran A*, [7] queries
+  unsigned long long* workCtr;
 };
 
 template <int CAP, int PLACE>
@@ -153,7 +157,18 @@ __global__ void __launch_bounds__(128) k_findpath(NavView nav, FindPathArgs a) {
       const PathResult r = findPathInternal(
           nav, w, rs, re, a.sG[q], sp, a.eG[q], ep, a.fastFail != 0,
           a.out_pts ? a.out_pts + static_cast<size_t>(q) * a.max_pts * 3 : nullptr, a.max_pts,
-          a.out_corridor ? a.out_corridor + static_cast<size_t>(q) * kMaxPathPolys : nullptr);
+          a.out_corridor ? a.out_corridor + static_cast<size_t>(q) * kMaxPathPolys : nullptr,
+          a.workCtr != nullptr);
+      if (a.workCtr && !r.overflow) {
+        atomicAdd(a.workCtr + 0, static_cast<unsigned long long>(r.expanded));
+        atomicAdd(a.workCtr + 1, static_cast<unsigned long long>(r.links));
+        atomicAdd(a.workCtr + 2, static_cast<unsigned long long>(r.neighbours));
+        atomicAdd(a.workCtr + 3, static_cast<unsigned long long>(r.ncorridor));
+        atomicAdd(a.workCtr + 4, static_cast<unsigned long long>(r.corridorLinks));
+        atomicAdd(a.workCtr + 5, static_cast<unsigned long long>((r.flags & 4u) ? r.npts : 0));
+        atomicAdd(a.workCtr + 6, static_cast<unsigned long long>(r.expanded ? 1 : 0));
+        atomicAdd(a.workCtr + 7, 1ull);
+      }
       if (r.overflow) {
         const uint32_t o = atomicAdd(a.overflowCount, 1u);
         a.overflow[o] = static_cast<uint32_t>(q);

@@ -543,6 +543,8 @@ struct AStarResult {
   uint32_t status;  // Detour status word of findPath, or 0xffffffff = tier overflow (retry)
   int lastBest;     // node index the corridor ends at
   int nodeCount;
+  // work counters for the roofline's algorithmic bytes
+  uint32_t expanded, links, neighbours;
 };
 
 // dtNavMeshQuery::findPath, DQ.cpp:973-1165.  The hash table must be zeroed by the caller.
@@ -555,6 +557,7 @@ HBN_HD AStarResult astarSearch(const NavView& nav, const AStarWs& w, uint32_t st
   r.status = kDtSuccess;
   r.nodeCount = 0;
   r.lastBest = 0;
+  r.expanded = r.links = r.neighbours = 0;
   Heap heap;
   heap.size = 0;
   bool isNew;
@@ -588,9 +591,12 @@ HBN_HD AStarResult astarSearch(const NavView& nav, const AStarWs& w, uint32_t st
     const float bcost = w.cost[best];
     const uint32_t lw = w.lnk[best];
     const uint32_t l0 = lw & 0x07ffffffu, ln = lw >> 27;
+    r.expanded++;
+    r.links += ln;
     for (uint32_t j = 0; j < ln; ++j) {
       const LinkRec L = nav.links[l0 + j];
       const uint32_t nei = L.nei;
+      r.neighbours += (nei != kNoPoly) ? 1u : 0u;
       if (nei == kNoPoly || nei == parentG) continue;
       if ((L.meta & kLinkPassBit) == 0) continue;
       const uint32_t state = (L.meta >> kLinkStateShift) & 3u;
@@ -717,9 +723,10 @@ HBN_HD uint32_t funnelAppend(Funnel& f, const float* pos, bool isEnd) {
   return 0;
 }
 
+// staged (nullable): the corridor's portals already gathered, staged[i] == nav.portals[pathLink[i]].
 HBN_HD uint32_t funnelStraightPath(const NavView& nav, const float* startPos, const float* endPos,
                                    const uint32_t* path, const uint32_t* pathLink, int pathSize,
-                                   Funnel& f) {
+                                   Funnel& f, const PortalRec* staged = nullptr) {
   f.count = 0;
   f.length = 0.0f;
   if (!vfinite(startPos) || !vfinite(endPos) || pathSize <= 0) return kDtFailure | kDtInvalidParam;
@@ -746,7 +753,7 @@ HBN_HD uint32_t funnelStraightPath(const NavView& nav, const float* startPos, co
           return kDtSuccess | kDtPartialResult |
                  ((f.count >= kMaxPathPolys) ? kDtBufferTooSmall : 0u);
         }
-        const PortalRec po = nav.portals[li];
+        const PortalRec& po = staged ? staged[i] : nav.portals[li];
         vcopy(left, po.l);
         vcopy(right, po.r);
         if (i == 0) {
@@ -1213,6 +1220,7 @@ struct PathResult {
   int32_t ncorridor; // polys in the corridor handed to the funnel (0 if A* did not run/ fail)
   uint32_t astarStatus, straightStatus;
   int32_t nodesUsed;
+  uint32_t expanded, links, neighbours, corridorLinks;  // work counters
   uint32_t flags;    // bit0 trivial, bit1 connected, bit2 found
   bool overflow;     // workspace tier too small: rerun with a larger one
 };
@@ -1238,7 +1246,8 @@ HBN_HD float nanF() {
 HBN_HD PathResult findPathInternal(const NavView& nav, const AStarWs& w, const float* reqStart,
                                    const float* reqEnd, uint32_t sG, const float* sPt,
                                    uint32_t eG, const float* ePt, bool fastFail,
-                                   float* outPts, int maxPts, uint32_t* outCorridor) {
+                                   float* outPts, int maxPts, uint32_t* outCorridor,
+                                   bool countWork = false) {
   PathResult r;
   r.dist = infF();
   r.npts = 0;
@@ -1246,6 +1255,7 @@ HBN_HD PathResult findPathInternal(const NavView& nav, const AStarWs& w, const f
   r.astarStatus = 0;
   r.straightStatus = 0;
   r.nodesUsed = 0;
+  r.expanded = r.links = r.neighbours = r.corridorLinks = 0;
   r.flags = 0;
   r.overflow = false;
   if (sG == kNoPoly || eG == kNoPoly) return r;
@@ -1276,13 +1286,20 @@ HBN_HD PathResult findPathInternal(const NavView& nav, const AStarWs& w, const f
       return r;
     }
     r.nodesUsed = a.nodeCount;
+    r.expanded = a.expanded;
+    r.links = a.links;
+    r.neighbours = a.neighbours;
     int fullLen = 0;
     npath = astarExtractPath(w, a.lastBest, path, kMaxPathPolys < w.cap ? kMaxPathPolys : w.cap, &fullLen);
     r.astarStatus = a.status | ((fullLen > kMaxPathPolys) ? kDtBufferTooSmall : 0u);
   }
   r.ncorridor = npath;
-  if (outCorridor)
-    for (int i = 0; i < npath; ++i) outCorridor[i] = nav.polys[path[i]].ref;
+  if (outCorridor || countWork)
+    for (int i = 0; i < npath; ++i) {
+      const PolyRec* cp = &nav.polys[path[i]];
+      r.corridorLinks += cp->linkCount;
+      if (outCorridor) outCorridor[i] = cp->ref;
+    }
   if (r.astarStatus != kDtSuccess || npath == 0) return r;  // PF.cpp:1450
   uint32_t* pathLink = w.hash;
   for (int i = 0; i + 1 < npath; ++i) pathLink[i] = findLinkTo(nav, path[i], path[i + 1]);

@@ -324,14 +324,33 @@ class PathFinder:
         check(L.hbn_is_navigable(h, p.ctypes.data, len(p), float(max_y_delta), out.ctypes.data))
         return out.astype(bool)
 
+    def set_profiling(self, enable: bool):
+        check(_lib.lib().hbn_navmesh_set_profiling(self._need(), 1 if enable else 0))
+
+    def phase_times(self) -> dict:
+        """Device milliseconds spent in find_paths' snap / path kernels since the last call."""
+        ms = (C.c_double * 2)()
+        calls = C.c_int64()
+        check(_lib.lib().hbn_navmesh_phase_times(self._need(), ms, C.byref(calls)))
+        return {"snap_ms": ms[0], "path_ms": ms[1], "calls": calls.value}
+
+    def work_counters(self, reset: bool = True) -> dict:
+        """Totals of the find_paths(count_work=True) calls so far (hbn_navmesh_work_counters)."""
+        out = np.zeros(8, np.uint64)
+        check(_lib.lib().hbn_navmesh_work_counters(self._need(), out.ctypes.data, 1 if reset else 0))
+        keys = ["expanded", "links", "neighbours", "corridor", "corridor_links", "points",
+                "astar_queries", "queries"]
+        return {k: int(v) for k, v in zip(keys, out)}
+
     def find_paths(self, starts, ends, max_points: int = 0, corridors: bool = False,
-                   exact_status: bool = False):
+                   exact_status: bool = False, count_work: bool = False):
         """Batched find_path(ShortestPath).  Returns a dict with `geodesic_distance` [N] and,
         on request, `num_points`, `points` [N,max_points,3] (NaN padded), `corridor` [N,256]
         poly refs, `num_corridor`, `status` [N,2]."""
         h = self._need()
         L = _lib.lib()
-        flags = _lib.HBN_FP_EXACT_STATUS if exact_status else 0
+        flags = (_lib.HBN_FP_EXACT_STATUS if exact_status else 0) | \
+                (_lib.HBN_FP_COUNT_WORK if count_work else 0)
         if _is_torch(starts):
             torch, dev, (s, e), st = self._torch_args(starts.float().reshape(-1, 3), ends.float().reshape(-1, 3))
             n = s.shape[0]

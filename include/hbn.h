@@ -87,6 +87,16 @@ int hbn_navmesh_island_info(hbn_navmesh_t nm, int island, float* radius, float* 
 int hbn_navmesh_get_settings(hbn_navmesh_t nm, void* out56);
 /* kernels launched through this handle so far (bench.py's gpu_launches evidence) */
 int64_t hbn_navmesh_launch_count(hbn_navmesh_t nm);
+/* Phase timing of hbn_find_path_dev for bench.py's roofline: while enabled, every call
+ * records CUDA events on ITS stream around the two projectToPoly launches and around the
+ * A* + funnel launches.  hbn_navmesh_phase_times waits for those events and returns the
+ * accumulated milliseconds {snap, path} and the number of calls, then resets. */
+int hbn_navmesh_set_profiling(hbn_navmesh_t nm, int enable);
+int hbn_navmesh_phase_times(hbn_navmesh_t nm, double* out_ms2, int64_t* out_calls);
+/* Work counters accumulated by HBN_FP_COUNT_WORK calls: out8 = {expanded polys, links of the
+ * expanded polys, their non-null neighbours, corridor polys, links of the corridor polys,
+ * straight-path points, queries that ran A*, queries}.  Synchronises the device. */
+int hbn_navmesh_work_counters(hbn_navmesh_t nm, uint64_t* out8, int reset);
 /* navmesh triangles for build_navmesh_vertices/indices (getNavMeshData, PF.cpp:1898-1968):
  * detail triangles of every walkable poly of `island` (-1 = all), 9 floats each.
  * Two-call pattern: returns the triangle count; fills `out` when cap_tris is large enough. */
@@ -111,8 +121,10 @@ int hbn_is_navigable_dev(hbn_navmesh_t nm, const float* pts, int64_t n, float ma
  * flags: HBN_FP_EXACT_STATUS keeps searching after the node pool is exhausted, like
  * DetourNavMeshQuery.cpp:1074-1078, so that corridors / status words of FAILED queries match
  * Detour too; by default such a query stops there (its PathFinder result, "no path",
- * is already decided: PF.cpp:1450). */
-enum { HBN_FP_EXACT_STATUS = 1 };
+ * is already decided: PF.cpp:1450).  HBN_FP_COUNT_WORK adds this call's work counters
+ * (expanded polys, links, neighbours, ... see hbn_navmesh_work_counters) to the handle's
+ * totals; bench.py derives the roofline's algorithmic bytes from them in an untimed pass. */
+enum { HBN_FP_EXACT_STATUS = 1, HBN_FP_COUNT_WORK = 2 };
 int hbn_find_path_dev(hbn_navmesh_t nm, const float* starts, const float* ends, int64_t n,
                       float* out_dist, int32_t* out_npts, float* out_pts, int max_pts,
                       uint32_t* out_corridor, int32_t* out_ncorridor, uint32_t* out_status,

@@ -234,6 +234,17 @@ class RefPathFinder:
                     num_polys=info[:, 4].astype(np.int32), num_points=info[:, 5].astype(np.int32),
                     nodes_used=info[:, 6].astype(np.int32), flags=info[:, 7], pts=pts)
 
+    def find_path_stats_batch(self, starts, ends, nthreads: int = 1):
+        """Work counters for the roofline's algorithmic bytes: dict of [n] arrays
+        expanded, links, neighbours, corridor, corridor_links, points."""
+        s = _f32(starts).reshape(-1, 3)
+        e = _f32(ends).reshape(-1, 3)
+        out = np.zeros((len(s), 6), np.uint32)
+        self._l.ref_find_path_stats_batch(self._h, _p(s, f32p), _p(e, f32p), C.c_int64(len(s)),
+                                          _p(out, u32p), C.c_int(nthreads))
+        keys = ["expanded", "links", "neighbours", "corridor", "corridor_links", "points"]
+        return {k: out[:, i].astype(np.int64) for i, k in enumerate(keys)}
+
     def find_path_multigoal_batch(self, starts, ends, max_pts: int = 0, nthreads: int = 1):
         s = _f32(starts).reshape(-1, 3)
         e = _f32(ends)

@@ -1445,6 +1445,59 @@ void ref_find_path_raw_batch(ref_pf_t h, const float* starts, const float* ends,
   });
 }
 
+// Work counters of one find_path for the roofline's ALGORITHMIC bytes:
+// out_stats is [n, 6] = {expanded polys (CLOSED nodes left in the pool after findPath),
+// links of the expanded polys, their non-null neighbours, corridor polys, links of the
+// corridor polys, straight-path points}.  From these
+//   B_astar  = 32*expanded + 12*links + (32+24)*neighbours      (dtPoly 32 B, dtLink 12 B,
+//   B_funnel = (32+24)*corridor + 12*corridorLinks                two portal verts 24 B)
+// Re-expansions of re-opened nodes are not counted (a lower bound).
+void ref_find_path_stats_batch(ref_pf_t h, const float* starts, const float* ends, int64_t n,
+                               uint32_t* out_stats, int nthreads) {
+  auto* pf = static_cast<RefPathFinder*>(h);
+  const dtNavMesh* nav = pf->nav();
+  parallelFor(pf, n, nthreads, [&](dtNavMeshQuery* q, int64_t i) {
+    uint32_t* st6 = out_stats + i * 6;
+    memset(st6, 0, 24);
+    dtStatus s0, s1;
+    dtPolyRef startRef = 0, endRef = 0;
+    V3 pathStart, pathEnd;
+    const V3 start = ld(starts, i), end = ld(ends, i);
+    std::tie(s0, startRef, pathStart) = pf->projectToPoly(start, q);
+    if (s0 != DT_SUCCESS || startRef == 0) return;
+    std::tie(s1, endRef, pathEnd) = pf->projectToPoly(end, q);
+    if (s1 != DT_SUCCESS || endRef == 0) return;
+    RefPathFinder::RawPath raw;
+    float len;
+    std::vector<V3> pts;
+    const bool found = pf->findPathInternal(q, start, startRef, pathStart, end, endRef, pathEnd,
+                                            len, pts, &raw);
+    auto linkStats = [&](dtPolyRef ref, uint32_t& links, uint32_t& neis) {
+      const dtMeshTile* tile = nullptr;
+      const dtPoly* poly = nullptr;
+      if (dtStatusFailed(nav->getTileAndPolyByRef(ref, &tile, &poly))) return;
+      for (unsigned int k = poly->firstLink; k != DT_NULL_LINK; k = tile->links[k].next) {
+        links++;
+        if (tile->links[k].ref) neis++;
+      }
+    };
+    if (raw.connected && startRef != endRef) {
+      dtNodePool* pool = q->getNodePool();
+      const int cnt = pool->getNodeCount();
+      for (int k = 0; k < cnt; ++k) {
+        const dtNode* node = pool->getNodeAtIdx(k + 1);
+        if (!node || !(node->flags & DT_NODE_CLOSED)) continue;
+        st6[0]++;
+        linkStats(node->id, st6[1], st6[2]);
+      }
+    }
+    st6[3] = raw.numPolys;
+    uint32_t dummy = 0;
+    for (int k = 0; k < raw.numPolys; ++k) linkStats(raw.polys[k], st6[4], dummy);
+    st6[5] = found ? static_cast<uint32_t>(pts.size()) : 0;
+  });
+}
+
 // find_path(MultiGoalShortestPath), fresh object per start (no cache).
 // ends is [n, g, 3].  Outputs: dist[n], idx[n], npts[n], pts [n,max_pts,3]|null.
 void ref_find_path_multigoal_batch(ref_pf_t h, const float* starts, const float* ends,

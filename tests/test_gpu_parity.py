@@ -250,9 +250,12 @@ def test_full_size_properties():
     ep, er, ei = pf.snap_points(en)
     found = np.isfinite(d)
     assert 0.2 < found.mean() < 1.0
-    # geodesic >= euclid between the snapped end points (1e-4 slack), same island required
-    eu = np.linalg.norm(sp - ep, axis=1)
-    assert (d[found] >= eu[found] * (1 - 1e-4) - 1e-4).all()
+    # geodesic >= horizontal distance between the path's end points (the funnel starts / ends at
+    # the REQUESTED points clamped in xz to the first / last poly, trap T2; on ramps their
+    # heights differ from the snapped ones), same island required
+    eu = np.linalg.norm((sp - ep)[:, [0, 2]], axis=1)
+    eu -= np.linalg.norm((sp - st)[:, [0, 2]], axis=1) + np.linalg.norm((ep - en)[:, [0, 2]], axis=1)
+    assert (d[found] >= eu[found] * (1 - 1e-4) - 1e-3).all()
     assert (si[found] == ei[found]).all()
     # idempotence of snapping, navigability of snapped points
     ok = sr != 0

@@ -46,9 +46,10 @@ def navmesh_bytes(name: str, cache: bool = True) -> bytes:
     data = pf.save_bytes()
     if cache:
         os.makedirs(_CACHE, exist_ok=True)
-        with open(path + ".tmp", "wb") as f:
+        tmp = f"{path}.{os.getpid()}.tmp"  # ranks of one torchrun job may race here
+        with open(tmp, "wb") as f:
             f.write(data)
-        os.replace(path + ".tmp", path)
+        os.replace(tmp, path)
     return data
 
 
@@ -97,7 +98,8 @@ class NavMeshGeom:
 def pointnav_pairs(geom: NavMeshGeom, n: int, seed: int, local_frac: float = 0.5,
                    local_radius: float = 15.0, jitter: float = 0.05):
     """C4 find_path mix: `local_frac` PointNav-like pairs whose goal lies within
-    `local_radius` metres of the start, the rest uniformly random pairs."""
+    `local_radius` metres of the start on the same storey (|dy| <= 0.5 m, the episode filter
+    PointNav generators apply), the rest uniformly random pairs."""
     from scipy.spatial import cKDTree
     rng = np.random.default_rng(seed)
     starts = geom.sample(n, rng)
@@ -105,8 +107,9 @@ def pointnav_pairs(geom: NavMeshGeom, n: int, seed: int, local_frac: float = 0.5
     n_local = int(n * local_frac)
     if n_local:
         pool = geom.sample(max(20000, n_local // 4), rng)
-        tree = cKDTree(pool)
-        nb = tree.query_ball_point(starts[:n_local], local_radius, return_sorted=False)
+        ys = np.array([1.0, local_radius / 0.5, 1.0])  # |dy| > 0.5 m lies outside the ball
+        tree = cKDTree(pool * ys)
+        nb = tree.query_ball_point(starts[:n_local] * ys, local_radius, return_sorted=False)
         pick = rng.random(n_local)
         for i, lst in enumerate(nb):
             if lst:
