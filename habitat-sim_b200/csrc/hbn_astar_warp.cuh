@@ -13,7 +13,7 @@
 //     record fetch, the two dtVdist square roots, the open/closed tests;
 //   * node allocation order (the 2048-node limit of PF.cpp:937 is part of the result) is a
 //     ballot prefix; pushes / modifies are then replayed in link order.
-// Node storage: a 4096-slot open-addressing table of 32-bit keys in shared memory (slot ==
+// Node storage: a 2560-slot open-addressing table of 32-bit keys in shared memory (slot ==
 // node id) and one 32 B record per slot in an L2-resident per-warp scratch.  `modify` finds
 // the heap position with a warp-wide scan instead of keeping back pointers.
 #pragma once
@@ -22,11 +22,14 @@
 
 namespace hbn {
 
-constexpr int kTabSize = 4096;  // >= 2 * kMaxNodes
-constexpr uint32_t kTabMask = kTabSize - 1;
+constexpr int kTabSize = 2560;  // node table slots: load <= 0.8 at the 2048-node limit
+__device__ __forceinline__ uint32_t tabHome(uint32_t key) { return __umulhi(nodeHash(key), kTabSize); }
+__device__ __forceinline__ uint32_t tabNext(uint32_t slot) { return slot + 1 == kTabSize ? 0u : slot + 1; }
 constexpr uint32_t kEntValid = 1u << 31;  // entry = valid | closed | open | state << 24 | g
 constexpr uint32_t kFullMask = 0xffffffffu;
 constexpr uint32_t kSearchOverflow = 0xffffffffu;  // heap tier too small: rerun in the next tier
+constexpr uint32_t kSearchWatchdog = 0xfffffffeu;  // iteration cap hit: a bug, reported to the host
+constexpr uint32_t kMaxExpansions = 1u << 18;      // >> any legal search (2048 nodes, re-opens)
 
 struct __align__(16) NodeRec {
   float px, py, pz, cost;
@@ -51,8 +54,8 @@ struct WarpWs {
   uint32_t* tab;
   HeapEnt* heap;  // logical index 0 is heap[0] of this pointer (already shifted)
   NodeRec* rec;
-  static constexpr size_t sharedBytes() { return kTabSize * 4 + (OC + 2) * sizeof(HeapEnt); }
-  static constexpr size_t globalBytes() { return static_cast<size_t>(kTabSize) * sizeof(NodeRec); }
+  __host__ __device__ static constexpr size_t sharedBytes() { return kTabSize * 4 + (OC + 2) * sizeof(HeapEnt); }
+  __host__ __device__ static constexpr size_t globalBytes() { return static_cast<size_t>(kTabSize) * sizeof(NodeRec); }
   __device__ static WarpWs carve(char* sm, char* gl) {
     WarpWs w;
     w.tab = reinterpret_cast<uint32_t*>(sm);
@@ -113,7 +116,7 @@ __device__ WarpSearch astarWarp(const NavView& nav, const WarpWs<OC>& ws, uint32
   for (int i = lane; i < kTabSize / 4; i += 32) t4[i] = make_uint4(0u, 0u, 0u, 0u);
   const PolyRec* spoly = &nav.polys[startG];
   const uint32_t slnk = spoly->linkStart | (static_cast<uint32_t>(spoly->linkCount) << 27);
-  const uint32_t sslot = nodeHash(startG) & kTabMask;
+  const uint32_t sslot = tabHome(startG);
   const float stotal = vdist(sp, ep) * kHScale;
   __syncwarp();
   if (lane == 0) {
@@ -145,6 +148,7 @@ __device__ WarpSearch astarWarp(const NavView& nav, const WarpWs<OC>& ws, uint32
       Lb = __ldg(lp + 1);
     }
     size--;
+    __syncwarp();  // every lane has read hp[0] before lane 0 rewrites the heap
     if (lane == 0) heapPopSift(hp, size);
     const uint32_t bent = ws.tab[bslot];
     const uint32_t bestG = bent & kNodeGMask;
@@ -161,6 +165,10 @@ __device__ WarpSearch astarWarp(const NavView& nav, const WarpWs<OC>& ws, uint32
 
     const uint32_t nei = La.w;
     const uint32_t meta = Lb.y;
+    if (r.expanded >= kMaxExpansions) {
+      r.status = kSearchWatchdog;
+      return r;
+    }
     r.expanded++;
     r.links += ln;
     r.neighbours += __popc(__ballot_sync(kFullMask, nei != kNoPoly));
@@ -168,31 +176,45 @@ __device__ WarpSearch astarWarp(const NavView& nav, const WarpWs<OC>& ws, uint32
     const uint32_t key = nei | (((meta >> kLinkStateShift) & 3u) << 24);
     uint32_t pend = __ballot_sync(kFullMask, cand);
 
+    // Two links of one poly can lead to the same neighbour (flagged at flatten time): such a
+    // link must see its twin's node, so a round ends in front of it.  Usually one round.
+    const uint32_t dupLanes = __ballot_sync(kFullMask, cand && (meta & kLinkDupBit) != 0);
     while (pend) {
-      // this round: the longest prefix of pending lanes whose keys are pairwise distinct
-      // (two links of one poly can lead to the same neighbour; those must be serialised)
-      const bool mineP = (pend >> lane) & 1u;
-      const uint32_t grp = __match_any_sync(kFullMask, mineP ? key : (0x80000000u | lane));
-      const uint32_t dupMask = __ballot_sync(kFullMask, mineP && (grp & ltMask) != 0);
-      const uint32_t cur = dupMask ? (pend & ((1u << (__ffs(dupMask) - 1)) - 1u)) : pend;
+      uint32_t cur = pend;
+      if (dupLanes) {
+        const int first = __ffs(pend) - 1;
+        const uint32_t later = dupLanes & pend & ~((2u << first) - 1u);
+        if (later) cur = pend & ((1u << (__ffs(later) - 1)) - 1u);
+      }
       pend &= ~cur;
       const bool mine = (cur >> lane) & 1u;
 
       // dtNodePool::getNode, DNode.cpp:121-152: lookup ...
-      uint32_t slot = nodeHash(key) & kTabMask;
+      uint32_t slot = tabHome(key);
       uint32_t ent = 0;
       bool found = false;
+      bool bad = false;
       if (mine) {
-        for (;;) {
+        for (int probes = 0;; ++probes) {
           ent = ws.tab[slot];
           if (ent == 0) break;
           if ((ent & kNodeKeyMask) == key) {
             found = true;
             break;
           }
-          slot = (slot + 1) & kTabMask;
+          if (probes >= kTabSize) {
+            bad = true;
+            break;
+          }
+          slot = tabNext(slot);
         }
       }
+      if (__any_sync(kFullMask, bad)) {
+        r.status = kSearchWatchdog;
+        r.expanded |= 0x40000000u;
+        return r;
+      }
+      __syncwarp();  // lookups done before this round's inserts / flag updates
       // ... allocation in link order against the 2048-node limit
       const bool isNew = mine && !found;
       const uint32_t newMask = __ballot_sync(kFullMask, isNew);
@@ -205,9 +227,9 @@ __device__ WarpSearch astarWarp(const NavView& nav, const WarpWs<OC>& ws, uint32
       nodeCount += __popc(newMask & ~failMask);
       const bool ok = mine && !allocFail;
       if (ok && isNew) {
-        for (;;) {  // distinct keys in a round: only the slot can be contended
+        for (int probes = 0; probes < 2 * kTabSize; ++probes) {  // distinct keys in a round: only the slot can be contended
           if (atomicCAS(&ws.tab[slot], 0u, kEntValid | key) == 0u) break;
-          slot = (slot + 1) & kTabMask;
+          slot = tabNext(slot);
         }
       }
       float npos[3] = {__uint_as_float(La.x), __uint_as_float(La.y), __uint_as_float(La.z)};
@@ -247,45 +269,38 @@ __device__ WarpSearch astarWarp(const NavView& nav, const WarpWs<OC>& ws, uint32
       const uint32_t accMask = __ballot_sync(kFullMask, acc);
       __syncwarp();
       // heap updates replayed in link order (DQ.cpp:1140-1152)
+      const uint32_t openMask = __ballot_sync(kFullMask, acc && wasOpen);
+      const HeapEnt myEnt{total, slot, nlnk, 0u};
       uint32_t m = accMask;
       while (m) {
         const int b = __ffs(m) - 1;
         m &= m - 1;
-        const float t = __shfl_sync(kFullMask, total, b);
-        const uint32_t s = __shfl_sync(kFullMask, slot, b);
-        const uint32_t lk = __shfl_sync(kFullMask, nlnk, b);
-        const int wo = __shfl_sync(kFullMask, wasOpen ? 1 : 0, b);
-        if (wo) {  // dtNodeQueue::modify, DNode.h:132-142: locate, then bubbleUp
+        if ((openMask >> b) & 1u) {  // dtNodeQueue::modify, DNode.h:132-142: locate, then bubbleUp
+          const uint32_t s = __shfl_sync(kFullMask, slot, b);
           int pos = -1;
           for (int i = lane; i < size; i += 32)
             if (hp[i].slot == s) pos = i;
           const uint32_t pm = __ballot_sync(kFullMask, pos >= 0);
           pos = __shfl_sync(kFullMask, pos, pm ? (__ffs(pm) - 1) : 0);
-          if (lane == 0 && pos >= 0) heapUp(hp, pos, HeapEnt{t, s, lk, 0u});
+          __syncwarp();
+          if (lane == b && pos >= 0) heapUp(hp, pos, myEnt);
         } else {
           if (size >= OC) {
             r.status = kSearchOverflow;
             return r;
           }
-          if (lane == 0) heapUp(hp, size, HeapEnt{t, s, lk, 0u});
+          if (lane == b) heapUp(hp, size, myEnt);
           size++;
         }
         __syncwarp();
       }
       // DQ.cpp:1154-1159: first neighbour (link order) with the smallest heuristic
-      {
-        float hv = acc ? heuristic : kFltMax;
-        int hl = lane;
-        for (int off = 16; off > 0; off >>= 1) {
-          const float ov = __shfl_xor_sync(kFullMask, hv, off);
-          const int ol = __shfl_xor_sync(kFullMask, hl, off);
-          if (ov < hv || (ov == hv && ol < hl)) {
-            hv = ov;
-            hl = ol;
-          }
-        }
-        if (accMask && hv < lastBestCost) {
-          lastBestCost = hv;
+      if (accMask) {  // heuristics are >= +0, so their bit patterns order like the floats
+        const uint32_t hb = acc ? __float_as_uint(heuristic) : 0xffffffffu;
+        const uint32_t mn = __reduce_min_sync(kFullMask, hb);
+        if (__uint_as_float(mn) < lastBestCost) {
+          const int hl = __ffs(__ballot_sync(kFullMask, hb == mn)) - 1;
+          lastBestCost = __uint_as_float(mn);
           lastBest = __shfl_sync(kFullMask, slot, hl);
         }
       }

@@ -2,6 +2,7 @@
 // wrappers.  No CPU query path exists in this library.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <mutex>
 #include <string>
@@ -28,10 +29,13 @@ int fail(int code, const std::string& msg) {
   } while (0)
 
 // tier configuration (see DESIGN.md "A* workspace tiers")
-constexpr int kCapS = 256;    // small tier: whole workspace in shared memory
 constexpr int kCapL = 2048;   // reference pool size: heap+hash shared, nodes in L2
 constexpr int kWallCapS = 128;
-constexpr int kFpWarps = 4;   // warps per block of the path kernels
+constexpr int kFpWarps = 4;   // warps per block of the wall-distance kernels
+// find_path (hbn_astar_warp.cuh): open-list capacity of the two tiers, warps per block
+constexpr int kOpenS = 256;
+constexpr int kOpenL = 2048;
+constexpr int kFpWpb = 1;
 constexpr int kSnapW = 8;     // lanes per point in k_snap
 constexpr int kRandW = 8;
 
@@ -69,12 +73,14 @@ struct hbn_navmesh {
   int64_t launches = 0;
   std::recursive_mutex mu;
   // scratch (device)
-  DevBuf sG, eG, e2G, sPt, ePt, epPt, lastPoly, lists, counters, wsL, io, work;
+  DevBuf sG, eG, e2G, sPt, ePt, epPt, lastPoly, lists, counters, wsL, wsFp, io, work;
   // pinned staging for the host-buffer entry points
   void* pinned = nullptr;
   size_t pinnedCap = 0;
-  int blocksFpS = 0, blocksFpL = 0, blocksWallS = 0;
+  int blocksFpS = 0, blocksFpL = 0, blocksWallS = 0, blocksWallL = 0;
   // optional phase timing of hbn_find_path_dev (hbn_navmesh_set_profiling)
+  unsigned int* faultHost = nullptr;  // mapped pinned memory the kernels report bugs through
+  unsigned int* faultDev = nullptr;
   bool profile = false;
   struct PhaseEv { cudaEvent_t e[3]; };
   std::vector<PhaseEv> phaseEvents;
@@ -143,30 +149,58 @@ int finishCreate(HostNavMesh& mesh, const int32_t* islands, int device, hbn_navm
 
   // opt in to large dynamic shared memory and size the persistent grids from occupancy
   const int threads = kFpWarps * 32;
-  const size_t smS = kFpWarps * wsSharedBytes(kCapS, kWsShared);
   const size_t smL = kFpWarps * wsSharedBytes(kCapL, kWsHybrid);
   const size_t smW = kFpWarps * wsSharedBytes(kWallCapS, kWsShared);
-  CK(cudaFuncSetAttribute(k_findpath<kCapS, kWsShared>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smS)));
-  CK(cudaFuncSetAttribute(k_findpath<kCapL, kWsHybrid>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smL)));
+  const size_t smFpS = kFpWpb * WarpWs<kOpenS>::sharedBytes();
+  const size_t smFpL = kFpWpb * WarpWs<kOpenL>::sharedBytes();
+  CK(cudaFuncSetAttribute(k_findpath_w<kOpenS, kFpWpb>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smFpS)));
+  CK(cudaFuncSetAttribute(k_findpath_w<kOpenL, kFpWpb>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smFpL)));
+  CK(cudaFuncSetAttribute(k_findpath_w<kOpenS, kFpWpb>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   CK(cudaFuncSetAttribute(k_wall<kWallCapS, kWsShared>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smW)));
   CK(cudaFuncSetAttribute(k_wall<kCapL, kWsHybrid>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smL)));
   int occ = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_findpath<kCapS, kWsShared>, threads, smS));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_findpath_w<kOpenS, kFpWpb>, 32 * kFpWpb, smFpS));
   nm->blocksFpS = std::max(1, occ) * nm->smCount;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_findpath<kCapL, kWsHybrid>, threads, smL));
+  if (const char* e = getenv("HBN_FP_BLOCKS_PER_SM")) nm->blocksFpS = std::max(1, std::min(occ, atoi(e))) * nm->smCount;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_findpath_w<kOpenL, kFpWpb>, 32 * kFpWpb, smFpL));
   nm->blocksFpL = std::max(1, occ) * nm->smCount;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wall<kWallCapS, kWsShared>, threads, smW));
   nm->blocksWallS = std::max(1, occ) * nm->smCount;
-  // global node arrays of the large tier: one slot per resident warp
-  rc = nm->wsL.ensure(static_cast<size_t>(nm->blocksFpL) * kFpWarps * wsGlobalBytes(kCapL, kWsHybrid));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wall<kCapL, kWsHybrid>, threads, smL));
+  nm->blocksWallL = std::max(1, occ) * nm->smCount;
+  // global scratch: one slot per resident warp
+  rc = nm->wsL.ensure(static_cast<size_t>(nm->blocksWallL) * kFpWarps * wsGlobalBytes(kCapL, kWsHybrid));
+  if (rc == HBN_OK)
+    rc = nm->wsFp.ensure(static_cast<size_t>(std::max(nm->blocksFpS, nm->blocksFpL)) * kFpWpb *
+                         WarpWs<kOpenS>::globalBytes());
   if (rc == HBN_OK) rc = nm->counters.ensure(64);
   if (rc == HBN_OK) rc = nm->work.ensure(64);
+  if (rc == HBN_OK) {
+    if (cudaHostAlloc(reinterpret_cast<void**>(&nm->faultHost), 64, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(reinterpret_cast<void**>(&nm->faultDev), nm->faultHost, 0) != cudaSuccess)
+      rc = fail(HBN_ERR_CUDA, "cudaHostAlloc(fault flags)");
+    else
+      memset(nm->faultHost, 0, 64);
+  }
   if (rc == HBN_OK && cudaMemset(nm->work.p, 0, 64) != cudaSuccess) rc = fail(HBN_ERR_CUDA, "cudaMemset");
   if (rc != HBN_OK) {
     hbn_navmesh_destroy(nm);
     return rc;
   }
   *out = nm;
+  return HBN_OK;
+}
+
+// kernels report internal inconsistencies (iteration caps) through mapped host memory; call
+// after a synchronisation
+int checkFault(hbn_navmesh* nm) {
+  if (nm->faultHost && nm->faultHost[0]) {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "kernel watchdog tripped %u time(s); query %u, site %u", nm->faultHost[0],
+             nm->faultHost[1], nm->faultHost[2]);
+    memset(nm->faultHost, 0, 64);
+    return fail(HBN_ERR_CUDA, buf);
+  }
   return HBN_OK;
 }
 
@@ -244,9 +278,10 @@ void hbn_navmesh_destroy(hbn_navmesh_t nm) {
   DeviceGuard g(nm->device);
   for (void* d : nm->devArrays) cudaFree(d);
   for (DevBuf* b : {&nm->sG, &nm->eG, &nm->e2G, &nm->sPt, &nm->ePt, &nm->epPt, &nm->lastPoly,
-                    &nm->lists, &nm->counters, &nm->wsL, &nm->io, &nm->work})
+                    &nm->lists, &nm->counters, &nm->wsL, &nm->wsFp, &nm->io, &nm->work})
     b->release();
   if (nm->pinned) cudaFreeHost(nm->pinned);
+  if (nm->faultHost) cudaFreeHost(nm->faultHost);
   if (nm->stream) cudaStreamDestroy(nm->stream);
   delete nm;
 }
@@ -315,16 +350,21 @@ int hbn_navmesh_phase_times(hbn_navmesh_t nm, double* out_ms2, int64_t* out_call
     for (auto& e : pe.e) cudaEventDestroy(e);
   }
   nm->phaseEvents.clear();
-  return HBN_OK;
+  return checkFault(nm);
 }
 
 int hbn_navmesh_work_counters(hbn_navmesh_t nm, uint64_t* out8, int reset) {
   if (!nm || !out8) return fail(HBN_ERR_INVALID, "null argument");
   DeviceGuard g(nm->device);
   CK(cudaDeviceSynchronize());
+  if (getenv("HBN_DEBUG_SLOW") && nm->faultHost) {
+    fprintf(stderr, "[hbn] slowest find_path query: %u kcycles, q=%u, expansions=%u, tier OC=%u\n",
+            nm->faultHost[4], nm->faultHost[5], nm->faultHost[6], nm->faultHost[7]);
+    nm->faultHost[4] = 0;
+  }
   CK(cudaMemcpy(out8, nm->work.p, 64, cudaMemcpyDeviceToHost));
   if (reset) CK(cudaMemset(nm->work.p, 0, 64));
-  return HBN_OK;
+  return checkFault(nm);
 }
 
 int64_t hbn_navmesh_triangles(hbn_navmesh_t nm, int island, float* out, int64_t cap_tris) {
@@ -378,6 +418,7 @@ int hbn_find_path_dev(hbn_navmesh_t nm, const float* starts, const float* ends, 
   std::lock_guard<std::recursive_mutex> lk(nm->mu);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc;
+  if ((rc = checkFault(nm))) return rc;  // reported by an earlier launch
   if ((rc = nm->sG.ensure(n * 4)) || (rc = nm->eG.ensure(n * 4)) || (rc = nm->sPt.ensure(n * 12)) ||
       (rc = nm->ePt.ensure(n * 12)) || (rc = nm->lists.ensure(n * 4)))
     return rc;
@@ -406,14 +447,14 @@ int hbn_find_path_dev(hbn_navmesh_t nm, const float* starts, const float* ends, 
   a.overflowCount = cnt + 1;
   a.out_dist = out_dist; a.out_npts = out_npts; a.out_pts = out_pts; a.max_pts = max_pts;
   a.out_corridor = out_corridor; a.out_ncorridor = out_ncorridor; a.out_status = out_status;
-  a.scratch = nullptr;
+  a.scratch = static_cast<char*>(nm->wsFp.p);
+  a.fault = nm->faultDev;
   a.fastFail = (flags & HBN_FP_EXACT_STATUS) ? 0 : 1;
   a.workCtr = (flags & HBN_FP_COUNT_WORK) ? static_cast<unsigned long long*>(nm->work.p) : nullptr;
-  const int threads = kFpWarps * 32;
   {
-    int64_t blocks = std::min<int64_t>(nm->blocksFpS, (n + kFpWarps - 1) / kFpWarps);
-    k_findpath<kCapS, kWsShared><<<static_cast<unsigned>(blocks), threads,
-                                  kFpWarps * wsSharedBytes(kCapS, kWsShared), st>>>(nm->view, a);
+    int64_t blocks = std::min<int64_t>(nm->blocksFpS, (n + kFpWpb - 1) / kFpWpb);
+    k_findpath_w<kOpenS, kFpWpb><<<static_cast<unsigned>(blocks), 32 * kFpWpb,
+                                   kFpWpb * WarpWs<kOpenS>::sharedBytes(), st>>>(nm->view, a);
     nm->launches++;
     CK(cudaGetLastError());
   }
@@ -422,10 +463,9 @@ int hbn_find_path_dev(hbn_navmesh_t nm, const float* starts, const float* ends, 
   b.work = a.overflow;
   b.workCount = a.overflowCount;
   b.counter = cnt + 2;
-  b.overflow = static_cast<uint32_t*>(nm->lists.p);  // cannot overflow: CAP == kMaxNodes
+  b.overflow = static_cast<uint32_t*>(nm->lists.p);  // cannot overflow: open list <= kMaxNodes
   b.overflowCount = cnt + 3;
-  b.scratch = static_cast<char*>(nm->wsL.p);
-  k_findpath<kCapL, kWsHybrid><<<nm->blocksFpL, threads, kFpWarps * wsSharedBytes(kCapL, kWsHybrid), st>>>(nm->view, b);
+  k_findpath_w<kOpenL, kFpWpb><<<nm->blocksFpL, 32 * kFpWpb, kFpWpb * WarpWs<kOpenL>::sharedBytes(), st>>>(nm->view, b);
   nm->launches++;
   CK(cudaGetLastError());
   if (nm->profile) {
@@ -507,7 +547,7 @@ int hbn_closest_obstacle_dev(hbn_navmesh_t nm, const float* pts, int64_t n, floa
   b.counter = cnt + 2;
   b.overflowCount = cnt + 3;
   b.scratch = static_cast<char*>(nm->wsL.p);
-  k_wall<kCapL, kWsHybrid><<<nm->blocksFpL, threads, kFpWarps * wsSharedBytes(kCapL, kWsHybrid), st>>>(nm->view, b);
+  k_wall<kCapL, kWsHybrid><<<nm->blocksWallL, threads, kFpWarps * wsSharedBytes(kCapL, kWsHybrid), st>>>(nm->view, b);
   nm->launches++;
   CK(cudaGetLastError());
   return HBN_OK;
@@ -579,7 +619,7 @@ struct IoPlan {
     CK(cudaStreamSynchronize(nm->stream));
     for (auto& it : items)
       if (it.dst) memcpy(it.dst, static_cast<char*>(nm->pinned) + it.off, it.bytes);
-    return HBN_OK;
+    return checkFault(nm);
   }
 };
 }  // namespace

@@ -626,6 +626,8 @@ void HostNavMesh::flatten(FlatNav& out) const {
         const uint32_t side = t.links[l].side;
         const uint32_t state = side != 0xff ? (side >> 1) & 3u : 0u;
         lr.meta = t.links[l].edge | (side << kLinkSideShift) | (state << kLinkStateShift);
+        for (uint32_t l2 = p.firstLink; l2 != l; l2 = t.links[l2].next)
+          if (lr.nei != kNoPoly && t.links[l2].ref == t.links[l].ref) { lr.meta |= kLinkDupBit; break; }
         out.links.push_back(lr);
         // portal of the FIRST link of this poly with the same ref (getPortalPoints :2276-2285)
         PortalRec po{};

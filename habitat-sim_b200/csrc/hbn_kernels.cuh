@@ -15,6 +15,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "hbn_query.h"
+#include "hbn_astar_warp.cuh"
 
 namespace hbn {
 
@@ -125,21 +126,27 @@ struct FindPathArgs {
   // [2] their non-null neighbours, [3] corridor polys, [4] corridor links, [5] path points,
   // [6] queries that ran A*, [7] queries
   unsigned long long* workCtr;
+  // mapped host memory: [0] number of watchdog trips (kernel bugs), [1] a query index, [2] where
+  unsigned int* fault;
 };
 
-template <int CAP, int PLACE>
-__global__ void __launch_bounds__(128) k_findpath(NavView nav, FindPathArgs a) {
+// One warp per query (hbn_astar_warp.cuh); WPB warps per block, each with its own shared
+// table + heap and its own slot of the global node-record scratch.  OC = open-list capacity of
+// this tier; a query whose open list outgrows it is appended to the overflow list and re-run
+// from scratch by the next tier (the search is deterministic).
+template <int OC, int WPB>
+__global__ void __launch_bounds__(32 * WPB) k_findpath_w(NavView nav, FindPathArgs a) {
   extern __shared__ __align__(16) char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int warpsPerBlock = blockDim.x >> 5;
-  AStarWs w;
-  if (PLACE == kWsShared) {
-    w = astarWsCarve(smem + static_cast<size_t>(warp) * astarWsBytes(CAP), CAP);
-  } else {
-    const size_t slot = static_cast<size_t>(blockIdx.x) * warpsPerBlock + warp;
-    w = wsCarveHybrid(smem + static_cast<size_t>(warp) * wsSharedBytes(CAP, PLACE),
-                      a.scratch + slot * wsGlobalBytes(CAP, PLACE), CAP);
-  }
+  const size_t slot = static_cast<size_t>(blockIdx.x) * WPB + warp;
+  const WarpWs<OC> ws = WarpWs<OC>::carve(smem + static_cast<size_t>(warp) * WarpWs<OC>::sharedBytes(),
+                                          a.scratch + slot * WarpWs<OC>::globalBytes());
+  // after the search the heap area holds the corridor, the table area the staged portals
+  uint32_t* pathG = reinterpret_cast<uint32_t*>(ws.heap - 1);
+  uint32_t* pathVia = pathG + kMaxPathPolys;
+  PortalRec* staged = reinterpret_cast<PortalRec*>(ws.tab);
+  static_assert((OC + 2) * sizeof(HeapEnt) >= 2 * kMaxPathPolys * 4, "corridor buffers");
+  static_assert(kTabSize * 4 >= kMaxPathPolys * sizeof(PortalRec), "portal staging");
   const uint32_t total = a.work ? *a.workCount : static_cast<uint32_t>(a.n);
   for (;;) {
     uint32_t wi = 0;
@@ -147,38 +154,129 @@ __global__ void __launch_bounds__(128) k_findpath(NavView nav, FindPathArgs a) {
     wi = __shfl_sync(0xffffffffu, wi, 0);
     if (wi >= total) break;
     const int64_t q = a.work ? a.work[wi] : wi;
-    for (int i = lane; i < 2 * CAP; i += 32) w.hash[i] = 0u;
+    const long long tq0 = clock64();
+    const uint32_t sG = a.sG[q], eG = a.eG[q];
+    const float rs[3] = {a.starts[3 * q], a.starts[3 * q + 1], a.starts[3 * q + 2]};
+    const float re[3] = {a.ends[3 * q], a.ends[3 * q + 1], a.ends[3 * q + 2]};
+    const float sp[3] = {a.sPt[3 * q], a.sPt[3 * q + 1], a.sPt[3 * q + 2]};
+    const float ep[3] = {a.ePt[3 * q], a.ePt[3 * q + 1], a.ePt[3 * q + 2]};
+    float* outPts = a.out_pts ? a.out_pts + static_cast<size_t>(q) * a.max_pts * 3 : nullptr;
+    uint32_t* outCorr = a.out_corridor ? a.out_corridor + static_cast<size_t>(q) * kMaxPathPolys : nullptr;
+    // findPathInternal, PF.cpp:1426-1468 (same decision sequence as hbn_query.h findPathInternal)
+    float dist = infF();
+    int npts = 0, ncorr = 0;
+    uint32_t stA = 0, stS = 0;
+    WarpSearch sr;
+    sr.expanded = sr.links = sr.neighbours = 0;
+    uint32_t corrLinks = 0;
+    bool overflow = false;
+    do {
+      if (sG == kNoPoly || eG == kNoPoly) break;
+      if (vfuzzyEq(sp, ep)) {  // PF.cpp:1434-1436
+        dist = 0.f;
+        npts = 2;
+        if (outPts && lane == 0) {
+          if (a.max_pts > 0) { outPts[0] = sp[0]; outPts[1] = sp[1]; outPts[2] = sp[2]; }
+          if (a.max_pts > 1) { outPts[3] = ep[0]; outPts[4] = ep[1]; outPts[5] = ep[2]; }
+        }
+        break;
+      }
+      const int32_t si = nav.polys[sG].island, ei = nav.polys[eG].island;
+      if (si < 0 || si != ei) break;  // hasConnection, PF.cpp:209-221
+      int first = 0;                  // corridor = pathG[first .. first + ncorr)
+      int fullLen = 1;
+      if (sG == eG) {                 // DQ.cpp:996-1001
+        if (lane == 0) { pathG[0] = sG; pathVia[0] = kNoPoly; }
+        ncorr = 1;
+        stA = kDtSuccess;
+        __syncwarp();
+      } else {
+        if (!vfinite(sp) || !vfinite(ep)) { stA = kDtFailure | kDtInvalidParam; break; }
+        sr = astarWarp<OC>(nav, ws, sG, eG, sp, ep, a.fastFail != 0);
+        if (sr.status == kSearchOverflow) { overflow = true; break; }
+        if (sr.status == kSearchWatchdog) {
+          if (lane == 0) { atomicAdd(a.fault, 1u); a.fault[1] = static_cast<unsigned>(q); a.fault[2] = 1u | (sr.expanded & 0x40000000u) | (OC << 8); }
+          stA = kDtFailure;
+          break;
+        }
+        // getPathToNode, DQ.cpp:1167-1205: walk the parent chain from the end; the circular
+        // buffer keeps the kMaxPathPolys polys nearest the start
+        __syncwarp();
+        if (lane == 0) {
+          int k = 0;
+          uint32_t cur = sr.lastBest;
+          for (;;) {
+            const uint4 nb = reinterpret_cast<const uint4*>(&ws.rec[cur])[1];
+            const int idx = (kMaxPathPolys - 1 - k) & (kMaxPathPolys - 1);
+            pathG[idx] = ws.tab[cur] & kNodeGMask;
+            pathVia[idx] = nb.z;
+            corrLinks += nb.y >> 27;
+            k++;
+            if (!nb.w) break;  // start node
+            if (k > kTabSize) {  // a parent cycle would be a bug
+              atomicAdd(a.fault, 1u); a.fault[1] = static_cast<unsigned>(q); a.fault[2] = 2u;
+              break;
+            }
+            cur = nb.w - 1;
+          }
+          fullLen = k;
+        }
+        fullLen = __shfl_sync(0xffffffffu, fullLen, 0);
+        __syncwarp();
+        ncorr = fullLen < kMaxPathPolys ? fullLen : kMaxPathPolys;
+        first = (kMaxPathPolys - fullLen) & (kMaxPathPolys - 1);
+        stA = sr.status | ((fullLen > kMaxPathPolys) ? kDtBufferTooSmall : 0u);
+      }
+      if (outCorr)
+        for (int i = lane; i < ncorr; i += 32)
+          outCorr[i] = nav.polys[pathG[(first + i) & (kMaxPathPolys - 1)]].ref;
+      if (stA != kDtSuccess || ncorr == 0) break;  // PF.cpp:1450
+      // here fullLen <= kMaxPathPolys, so the corridor is contiguous from `first`
+      for (int i = lane; i + 1 < ncorr; i += 32) staged[i] = nav.portals[pathVia[first + i + 1]];
+      __syncwarp();
+      if (lane == 0) {
+        Funnel f;
+        f.out = outPts;
+        f.maxOut = a.max_pts;
+        stS = funnelStraightPath(nav, rs, re, pathG + first, pathVia + first + 1, ncorr, f, staged);
+        npts = f.count;
+        if (stS == kDtSuccess && f.count != 0) dist = f.length;  // PF.cpp:1459
+      }
+      dist = __shfl_sync(0xffffffffu, dist, 0);
+      npts = __shfl_sync(0xffffffffu, npts, 0);
+      stS = __shfl_sync(0xffffffffu, stS, 0);
+    } while (false);
     __syncwarp();
     if (lane == 0) {
-      const float rs[3] = {a.starts[3 * q], a.starts[3 * q + 1], a.starts[3 * q + 2]};
-      const float re[3] = {a.ends[3 * q], a.ends[3 * q + 1], a.ends[3 * q + 2]};
-      const float sp[3] = {a.sPt[3 * q], a.sPt[3 * q + 1], a.sPt[3 * q + 2]};
-      const float ep[3] = {a.ePt[3 * q], a.ePt[3 * q + 1], a.ePt[3 * q + 2]};
-      const PathResult r = findPathInternal(
-          nav, w, rs, re, a.sG[q], sp, a.eG[q], ep, a.fastFail != 0,
-          a.out_pts ? a.out_pts + static_cast<size_t>(q) * a.max_pts * 3 : nullptr, a.max_pts,
-          a.out_corridor ? a.out_corridor + static_cast<size_t>(q) * kMaxPathPolys : nullptr,
-          a.workCtr != nullptr);
-      if (a.workCtr && !r.overflow) {
-        atomicAdd(a.workCtr + 0, static_cast<unsigned long long>(r.expanded));
-        atomicAdd(a.workCtr + 1, static_cast<unsigned long long>(r.links));
-        atomicAdd(a.workCtr + 2, static_cast<unsigned long long>(r.neighbours));
-        atomicAdd(a.workCtr + 3, static_cast<unsigned long long>(r.ncorridor));
-        atomicAdd(a.workCtr + 4, static_cast<unsigned long long>(r.corridorLinks));
-        atomicAdd(a.workCtr + 5, static_cast<unsigned long long>((r.flags & 4u) ? r.npts : 0));
-        atomicAdd(a.workCtr + 6, static_cast<unsigned long long>(r.expanded ? 1 : 0));
-        atomicAdd(a.workCtr + 7, 1ull);
-      }
-      if (r.overflow) {
+      if (overflow) {
         const uint32_t o = atomicAdd(a.overflowCount, 1u);
         a.overflow[o] = static_cast<uint32_t>(q);
       } else {
-        a.out_dist[q] = r.dist;
-        if (a.out_npts) a.out_npts[q] = (r.flags & 4u) ? r.npts : 0;
-        if (a.out_ncorridor) a.out_ncorridor[q] = r.ncorridor;
+        const bool found = dist < infF();
+        a.out_dist[q] = dist;
+        if (a.out_npts) a.out_npts[q] = found ? npts : 0;
+        if (a.out_ncorridor) a.out_ncorridor[q] = ncorr;
         if (a.out_status) {
-          a.out_status[2 * q] = r.astarStatus;
-          a.out_status[2 * q + 1] = r.straightStatus;
+          a.out_status[2 * q] = stA;
+          a.out_status[2 * q + 1] = stS;
+        }
+        {  // slowest query so far (debug aid): fault[4] = kilo-cycles, [5] = query, [6] = expansions
+          const unsigned kc = static_cast<unsigned>((clock64() - tq0) >> 10);
+          if (kc > a.fault[4] && atomicMax(a.fault + 4, kc) < kc) {
+            a.fault[5] = static_cast<unsigned>(q);
+            a.fault[6] = sr.expanded;
+            a.fault[7] = OC;
+          }
+        }
+        if (a.workCtr) {
+          atomicAdd(a.workCtr + 0, static_cast<unsigned long long>(sr.expanded));
+          atomicAdd(a.workCtr + 1, static_cast<unsigned long long>(sr.links));
+          atomicAdd(a.workCtr + 2, static_cast<unsigned long long>(sr.neighbours));
+          atomicAdd(a.workCtr + 3, static_cast<unsigned long long>(ncorr));
+          atomicAdd(a.workCtr + 4, static_cast<unsigned long long>(corrLinks));
+          atomicAdd(a.workCtr + 5, static_cast<unsigned long long>(found ? npts : 0));
+          atomicAdd(a.workCtr + 6, static_cast<unsigned long long>(sr.expanded ? 1 : 0));
+          atomicAdd(a.workCtr + 7, 1ull);
         }
       }
     }

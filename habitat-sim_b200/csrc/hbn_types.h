@@ -61,6 +61,7 @@ constexpr uint32_t kLinkSideShift = 8;            // dtLink::side (8 bits)
 constexpr uint32_t kLinkStateShift = 16;          // crossSide = side>>1 (0 if side==0xff), 2 bits
 constexpr uint32_t kLinkPassBit = 1u << 18;       // neighbour passes the default filter
 constexpr uint32_t kLinkOffmeshBit = 1u << 19;    // neighbour is an off-mesh connection poly
+constexpr uint32_t kLinkDupBit = 1u << 20;        // an earlier link of this poly has the same neighbour
 constexpr uint32_t kLinkNeiCountShift = 24;       // neighbour's linkCount (8 bits)
 
 struct HBN_ALIGN(16) LinkRec {
