@@ -33,7 +33,7 @@ constexpr uint32_t kMaxExpansions = 1u << 18;      // >> any legal search (2048 
 
 struct __align__(16) NodeRec {
   float px, py, pz, cost;
-  float total;
+  float heur;     // heuristic term of the node's total (a function of its fixed position only)
   uint32_t lnk;   // link window: start (27 bits) | count << 27
   uint32_t via;   // LinkRec index this node was (last) entered through; kNoPoly for the start
   uint32_t pidx;  // parent slot + 1, 0 = none
@@ -43,8 +43,8 @@ static_assert(sizeof(NodeRec) == 32, "NodeRec");
 struct __align__(16) HeapEnt {
   float key;
   uint32_t slot;
-  uint32_t lnk;
-  uint32_t pad;
+  uint32_t lnk;   // the node's link window, so that a pop can fetch the links at once
+  uint32_t pidx;  // the node's parent slot + 1 (0 = none), for the "skip the parent" test
 };
 
 // Shared memory of one warp: [tab: kTabSize u32][heap: OC + 2 entries].  The heap is stored
@@ -123,7 +123,7 @@ __device__ WarpSearch astarWarp(const NavView& nav, const WarpWs<OC>& ws, uint32
     ws.tab[sslot] = kEntValid | kNodeOpen | startG;
     float4* ra = reinterpret_cast<float4*>(&ws.rec[sslot]);
     ra[0] = make_float4(sp[0], sp[1], sp[2], 0.f);
-    reinterpret_cast<uint4*>(ra)[1] = make_uint4(__float_as_uint(stotal), slnk, kNoPoly, 0u);
+    reinterpret_cast<uint4*>(ra)[1] = make_uint4(__float_as_uint(stotal), slnk, kNoPoly, 0u);  // heur = total (cost 0)
     hp[0] = HeapEnt{stotal, sslot, slnk, 0u};
   }
   __syncwarp();
@@ -140,7 +140,7 @@ __device__ WarpSearch astarWarp(const NavView& nav, const WarpWs<OC>& ws, uint32
     const int ln = static_cast<int>(top.lnk >> 27);
     // early loads: the node's record (broadcast) and one link per lane
     const float4 ba = reinterpret_cast<const float4*>(&ws.rec[bslot])[0];
-    const uint32_t bpidx = reinterpret_cast<const uint4*>(&ws.rec[bslot])[1].w;
+    const uint32_t bpidx = top.pidx;
     uint4 La = make_uint4(0u, 0u, 0u, kNoPoly), Lb = make_uint4(0u, 0u, 0u, 0u);
     if (lane < ln) {
       const uint4* lp = reinterpret_cast<const uint4*>(&nav.links[l0 + lane]);
@@ -233,16 +233,18 @@ __device__ WarpSearch astarWarp(const NavView& nav, const WarpWs<OC>& ws, uint32
         }
       }
       float npos[3] = {__uint_as_float(La.x), __uint_as_float(La.y), __uint_as_float(La.z)};
-      float ntotal = 0.f;
+      float ntotal = 0.f, nheur = 0.f;
       uint32_t nlnk = Lb.x | ((meta >> kLinkNeiCountShift) << 27);
       if (ok && found) {
         const float4 na = reinterpret_cast<const float4*>(&ws.rec[slot])[0];
-        const uint4 nb = reinterpret_cast<const uint4*>(&ws.rec[slot])[1];
+        const uint2 nb = reinterpret_cast<const uint2*>(&ws.rec[slot])[2];
         npos[0] = na.x; npos[1] = na.y; npos[2] = na.z;
-        ntotal = __uint_as_float(nb.x);
+        nheur = __uint_as_float(nb.x);
+        ntotal = na.w + nheur;  // the node's total, as it was formed: cost + heuristic
         nlnk = nb.y;
       }
-      // DQ.cpp:1088-1121
+      // DQ.cpp:1088-1121.  A node's position never changes after its first visit, so neither
+      // does its heuristic term: it is computed once and kept in the record.
       float cost, heuristic;
       {
         const float curCost = vdist(bpos, npos);
@@ -252,7 +254,7 @@ __device__ WarpSearch astarWarp(const NavView& nav, const WarpWs<OC>& ws, uint32
           heuristic = 0.f;
         } else {
           cost = bcost + curCost;
-          heuristic = vdist(npos, ep) * kHScale;
+          heuristic = found ? nheur : vdist(npos, ep) * kHScale;
         }
       }
       const float total = cost + heuristic;
@@ -263,14 +265,14 @@ __device__ WarpSearch astarWarp(const NavView& nav, const WarpWs<OC>& ws, uint32
         float4* ra = reinterpret_cast<float4*>(&ws.rec[slot]);
         ra[0] = make_float4(npos[0], npos[1], npos[2], cost);
         reinterpret_cast<uint4*>(ra)[1] =
-            make_uint4(__float_as_uint(total), nlnk, l0 + static_cast<uint32_t>(lane), bslot + 1u);
+            make_uint4(__float_as_uint(heuristic), nlnk, l0 + static_cast<uint32_t>(lane), bslot + 1u);
         ws.tab[slot] = kEntValid | key | kNodeOpen;
       }
       const uint32_t accMask = __ballot_sync(kFullMask, acc);
       __syncwarp();
       // heap updates replayed in link order (DQ.cpp:1140-1152)
       const uint32_t openMask = __ballot_sync(kFullMask, acc && wasOpen);
-      const HeapEnt myEnt{total, slot, nlnk, 0u};
+      const HeapEnt myEnt{total, slot, nlnk, bslot + 1u};
       uint32_t m = accMask;
       while (m) {
         const int b = __ffs(m) - 1;

@@ -73,7 +73,7 @@ struct hbn_navmesh {
   int64_t launches = 0;
   std::recursive_mutex mu;
   // scratch (device)
-  DevBuf sG, eG, e2G, sPt, ePt, epPt, lastPoly, lists, counters, wsL, wsFp, io, work;
+  DevBuf sG, eG, e2G, sPt, ePt, epPt, lastPoly, lists, counters, wsL, wsFp, io, work, mgDist, mgBounds, mgOrder, mgEnd;
   // pinned staging for the host-buffer entry points
   void* pinned = nullptr;
   size_t pinnedCap = 0;
@@ -278,7 +278,8 @@ void hbn_navmesh_destroy(hbn_navmesh_t nm) {
   DeviceGuard g(nm->device);
   for (void* d : nm->devArrays) cudaFree(d);
   for (DevBuf* b : {&nm->sG, &nm->eG, &nm->e2G, &nm->sPt, &nm->ePt, &nm->epPt, &nm->lastPoly,
-                    &nm->lists, &nm->counters, &nm->wsL, &nm->wsFp, &nm->io, &nm->work})
+                    &nm->lists, &nm->counters, &nm->wsL, &nm->wsFp, &nm->io, &nm->work, &nm->mgDist,
+                    &nm->mgBounds, &nm->mgOrder, &nm->mgEnd})
     b->release();
   if (nm->pinned) cudaFreeHost(nm->pinned);
   if (nm->faultHost) cudaFreeHost(nm->faultHost);
@@ -406,12 +407,16 @@ int hbn_is_navigable_dev(hbn_navmesh_t nm, const float* pts, int64_t n, float ma
                     static_cast<cudaStream_t>(stream));
 }
 
-int hbn_find_path_dev(hbn_navmesh_t nm, const float* starts, const float* ends, int64_t n,
-                      float* out_dist, int32_t* out_npts, float* out_pts, int max_pts,
-                      uint32_t* out_corridor, int32_t* out_ncorridor, uint32_t* out_status,
-                      int flags, void* stream) {
+}  // extern "C"
+
+// n (start, end) pairs; startDiv > 1: pair q uses start q / startDiv (multi-goal layout)
+static int findPathLaunch(hbn_navmesh_t nm, const float* starts, const float* ends, int64_t n,
+                          int startDiv, float* out_dist, int32_t* out_npts, float* out_pts, int max_pts,
+                          uint32_t* out_corridor, int32_t* out_ncorridor, uint32_t* out_status,
+                          int flags, void* stream) {
   if (!nm || (n > 0 && (!starts || !ends || !out_dist))) return fail(HBN_ERR_INVALID, "null argument");
   if (n <= 0) return HBN_OK;
+  const int64_t nStarts = startDiv > 1 ? n / startDiv : n;
   if (n >= (1ll << 31)) return fail(HBN_ERR_INVALID, "batch too large");
   if (out_pts && max_pts <= 0) return fail(HBN_ERR_INVALID, "max_pts must be positive");
   DeviceGuard g(nm->device);
@@ -419,7 +424,7 @@ int hbn_find_path_dev(hbn_navmesh_t nm, const float* starts, const float* ends, 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc;
   if ((rc = checkFault(nm))) return rc;  // reported by an earlier launch
-  if ((rc = nm->sG.ensure(n * 4)) || (rc = nm->eG.ensure(n * 4)) || (rc = nm->sPt.ensure(n * 12)) ||
+  if ((rc = nm->sG.ensure(nStarts * 4)) || (rc = nm->eG.ensure(n * 4)) || (rc = nm->sPt.ensure(nStarts * 12)) ||
       (rc = nm->ePt.ensure(n * 12)) || (rc = nm->lists.ensure(n * 4)))
     return rc;
   uint32_t* cnt = static_cast<uint32_t*>(nm->counters.p);
@@ -429,7 +434,7 @@ int hbn_find_path_dev(hbn_navmesh_t nm, const float* starts, const float* ends, 
     for (auto& e : pe.e) CK(cudaEventCreate(&e));
     CK(cudaEventRecord(pe.e[0], st));
   }
-  if ((rc = snapLaunch(nm, starts, nullptr, n, static_cast<float*>(nm->sPt.p),
+  if ((rc = snapLaunch(nm, starts, nullptr, nStarts, static_cast<float*>(nm->sPt.p),
                        static_cast<uint32_t*>(nm->sG.p), nullptr, nullptr, nullptr, 0.f, st)))
     return rc;
   if ((rc = snapLaunch(nm, ends, nullptr, n, static_cast<float*>(nm->ePt.p),
@@ -449,6 +454,7 @@ int hbn_find_path_dev(hbn_navmesh_t nm, const float* starts, const float* ends, 
   a.out_corridor = out_corridor; a.out_ncorridor = out_ncorridor; a.out_status = out_status;
   a.scratch = static_cast<char*>(nm->wsFp.p);
   a.fault = nm->faultDev;
+  a.startDiv = startDiv;
   a.fastFail = (flags & HBN_FP_EXACT_STATUS) ? 0 : 1;
   a.workCtr = (flags & HBN_FP_COUNT_WORK) ? static_cast<unsigned long long*>(nm->work.p) : nullptr;
   {
@@ -475,9 +481,54 @@ int hbn_find_path_dev(hbn_navmesh_t nm, const float* starts, const float* ends, 
   return HBN_OK;
 }
 
-int hbn_find_path_multigoal_dev(hbn_navmesh_t, const float*, const float*, int64_t, int, float*,
-                                int32_t*, int32_t*, float*, int, void*) {
-  return fail(HBN_ERR_INVALID, "hbn_find_path_multigoal_dev: not implemented yet");
+
+extern "C" int hbn_find_path_dev(hbn_navmesh_t nm, const float* starts, const float* ends, int64_t n,
+                                 float* out_dist, int32_t* out_npts, float* out_pts, int max_pts,
+                                 uint32_t* out_corridor, int32_t* out_ncorridor, uint32_t* out_status,
+                                 int flags, void* stream) {
+  return findPathLaunch(nm, starts, ends, n, 1, out_dist, out_npts, out_pts, max_pts, out_corridor,
+                        out_ncorridor, out_status, flags, stream);
+}
+
+extern "C" {
+
+int hbn_find_path_multigoal_dev(hbn_navmesh_t nm, const float* starts, const float* ends, int64_t n,
+                                int g, float* out_dist, int32_t* out_index, int32_t* out_npts,
+                                float* out_pts, int max_pts, void* stream) {
+  if (!nm || (n > 0 && (!starts || !ends || !out_dist || !out_index)))
+    return fail(HBN_ERR_INVALID, "null argument");
+  if (g <= 0) return fail(HBN_ERR_INVALID, "g must be positive");
+  if (n <= 0) return HBN_OK;
+  const int64_t pairs = n * g;
+  if (pairs >= (1ll << 31)) return fail(HBN_ERR_INVALID, "batch too large");
+  DeviceGuard gd(nm->device);
+  std::lock_guard<std::recursive_mutex> lk(nm->mu);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc;
+  const bool wantPts = out_npts || out_pts;
+  if ((rc = nm->mgDist.ensure(pairs * 4)) || (rc = nm->mgBounds.ensure(pairs * 4)) ||
+      (rc = nm->mgOrder.ensure(pairs * 4)) || (wantPts && (rc = nm->mgEnd.ensure(n * 12))))
+    return rc;
+  // every (start, goal) pair's findPathInternal, in parallel ...
+  if ((rc = findPathLaunch(nm, starts, ends, pairs, g, static_cast<float*>(nm->mgDist.p), nullptr, nullptr, 0,
+                           nullptr, nullptr, nullptr, 0, stream)))
+    return rc;
+  // ... then the reference's sequential goal loop per start (sG / eG are still in the scratch)
+  k_multigoal_select<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(
+      starts, ends, static_cast<uint32_t*>(nm->sG.p), static_cast<uint32_t*>(nm->eG.p),
+      static_cast<float*>(nm->mgDist.p), n, g, static_cast<float*>(nm->mgBounds.p),
+      static_cast<int32_t*>(nm->mgOrder.p), out_dist, out_index,
+      wantPts ? static_cast<float*>(nm->mgEnd.p) : nullptr);
+  nm->launches++;
+  CK(cudaGetLastError());
+  if (wantPts) {  // the chosen goal's path points: one more find_path per start
+    if ((rc = nm->mgDist.ensure(std::max<int64_t>(pairs, n) * 4))) return rc;
+    if ((rc = findPathLaunch(nm, starts, static_cast<float*>(nm->mgEnd.p), n, 1,
+                             static_cast<float*>(nm->mgDist.p), out_npts, out_pts, max_pts, nullptr, nullptr,
+                             nullptr, 0, stream)))
+      return rc;
+  }
+  return HBN_OK;
 }
 
 int hbn_try_step_dev(hbn_navmesh_t nm, const float* starts, const float* ends, int64_t n,

@@ -126,6 +126,7 @@ struct FindPathArgs {
   // [2] their non-null neighbours, [3] corridor polys, [4] corridor links, [5] path points,
   // [6] queries that ran A*, [7] queries
   unsigned long long* workCtr;
+  int startDiv;           // > 1: query q starts at point q / startDiv (multi-goal: [n, g] pairs)
   // mapped host memory: [0] number of watchdog trips (kernel bugs), [1] a query index, [2] where
   unsigned int* fault;
 };
@@ -155,10 +156,11 @@ __global__ void __launch_bounds__(32 * WPB) k_findpath_w(NavView nav, FindPathAr
     if (wi >= total) break;
     const int64_t q = a.work ? a.work[wi] : wi;
     const long long tq0 = clock64();
-    const uint32_t sG = a.sG[q], eG = a.eG[q];
-    const float rs[3] = {a.starts[3 * q], a.starts[3 * q + 1], a.starts[3 * q + 2]};
+    const int64_t qs = a.startDiv > 1 ? q / a.startDiv : q;
+    const uint32_t sG = a.sG[qs], eG = a.eG[q];
+    const float rs[3] = {a.starts[3 * qs], a.starts[3 * qs + 1], a.starts[3 * qs + 2]};
     const float re[3] = {a.ends[3 * q], a.ends[3 * q + 1], a.ends[3 * q + 2]};
-    const float sp[3] = {a.sPt[3 * q], a.sPt[3 * q + 1], a.sPt[3 * q + 2]};
+    const float sp[3] = {a.sPt[3 * qs], a.sPt[3 * qs + 1], a.sPt[3 * qs + 2]};
     const float ep[3] = {a.ePt[3 * q], a.ePt[3 * q + 1], a.ePt[3 * q + 2]};
     float* outPts = a.out_pts ? a.out_pts + static_cast<size_t>(q) * a.max_pts * 3 : nullptr;
     uint32_t* outCorr = a.out_corridor ? a.out_corridor + static_cast<size_t>(q) * kMaxPathPolys : nullptr;
@@ -281,6 +283,34 @@ __global__ void __launch_bounds__(32 * WPB) k_findpath_w(NavView nav, FindPathAr
       }
     }
     __syncwarp();
+  }
+}
+
+// findPath(MultiGoalShortestPath&) goal loop (PF.cpp:1541-1569) over precomputed pair distances:
+// one thread per start.  bounds / order: [n, g] scratch.  chosenEnd (nullable): the chosen
+// goal's requested point (NaN if none) for the second find_path pass that produces the points.
+__global__ void __launch_bounds__(128) k_multigoal_select(const float* __restrict__ starts,
+                                                          const float* __restrict__ ends,
+                                                          const uint32_t* __restrict__ sG,
+                                                          const uint32_t* __restrict__ eG,
+                                                          const float* __restrict__ pairDist, int64_t n,
+                                                          int g, float* __restrict__ bounds,
+                                                          int32_t* __restrict__ order,
+                                                          float* __restrict__ out_dist,
+                                                          int32_t* __restrict__ out_index,
+                                                          float* __restrict__ chosenEnd) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float st[3] = {starts[3 * i], starts[3 * i + 1], starts[3 * i + 2]};
+  float d;
+  int32_t idx;
+  multiGoalSelect(g, st, sG[i] != kNoPoly, ends + i * g * 3, eG + i * g, pairDist + i * g,
+                  bounds + i * g, order + i * g, &d, &idx);
+  out_dist[i] = d;
+  out_index[i] = idx;
+  if (chosenEnd) {
+    for (int k = 0; k < 3; ++k)
+      chosenEnd[3 * i + k] = idx >= 0 ? ends[(i * g + idx) * 3 + k] : nanF();
   }
 }
 

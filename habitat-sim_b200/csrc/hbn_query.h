@@ -1317,6 +1317,191 @@ HBN_HD PathResult findPathInternal(const NavView& nav, const AStarWs& w, const f
   return r;
 }
 
+// ---------------------------------------------------------------------------------------
+// findPath(MultiGoalShortestPath&), PF.cpp:1515-1572, for a freshly constructed path object.
+// The goals are visited in the order std::sort leaves them in (PF.cpp:1542-1548, keys =
+// minTheoreticalDist); std::sort is not stable, so goals with EQUAL bounds (e.g. one goal
+// listed twice) come out in an order that is a property of libstdc++'s introsort.  That
+// order decides closestEndPointIndex between equally distant goals, hence the sort is
+// restated here operation for operation (bits/stl_algo.h: __introsort_loop, _S_threshold 16,
+// __move_median_to_first, __unguarded_partition, __final_insertion_sort; heapsort fallback
+// __partial_sort = __heap_select + __sort_heap over bits/stl_heap.h).
+// ---------------------------------------------------------------------------------------
+struct SortCtx {
+  int32_t* v;        // the permutation being sorted
+  const float* key;  // comp(a, b) = key[a] < key[b]
+};
+HBN_HD bool sortLess(const SortCtx& c, int32_t a, int32_t b) { return c.key[a] < c.key[b]; }
+HBN_HD void sortSwap(const SortCtx& c, int i, int j) {
+  const int32_t t = c.v[i];
+  c.v[i] = c.v[j];
+  c.v[j] = t;
+}
+// std::__adjust_heap + __push_heap (stl_heap.h) on v[first..), value semantics
+HBN_HD void sortAdjustHeap(const SortCtx& c, int first, int holeIndex, int len, int32_t value) {
+  const int topIndex = holeIndex;
+  int secondChild = holeIndex;
+  while (secondChild < (len - 1) / 2) {
+    secondChild = 2 * (secondChild + 1);
+    if (sortLess(c, c.v[first + secondChild], c.v[first + (secondChild - 1)])) secondChild--;
+    c.v[first + holeIndex] = c.v[first + secondChild];
+    holeIndex = secondChild;
+  }
+  if ((len & 1) == 0 && secondChild == (len - 2) / 2) {
+    secondChild = 2 * (secondChild + 1);
+    c.v[first + holeIndex] = c.v[first + (secondChild - 1)];
+    holeIndex = secondChild - 1;
+  }
+  int parent = (holeIndex - 1) / 2;
+  while (holeIndex > topIndex && sortLess(c, c.v[first + parent], value)) {
+    c.v[first + holeIndex] = c.v[first + parent];
+    holeIndex = parent;
+    parent = (holeIndex - 1) / 2;
+  }
+  c.v[first + holeIndex] = value;
+}
+// std::__partial_sort(first, last, last): heapsort of v[first, last)
+HBN_HD void sortHeapSort(const SortCtx& c, int first, int last) {
+  const int len = last - first;
+  if (len >= 2) {  // __make_heap
+    int parent = (len - 2) / 2;
+    for (;;) {
+      const int32_t value = c.v[first + parent];
+      sortAdjustHeap(c, first, parent, len, value);
+      if (parent == 0) break;
+      parent--;
+    }
+  }
+  // __heap_select's loop over [middle, last) is empty (middle == last); __sort_heap:
+  for (int l = last; l - first > 1;) {
+    --l;
+    const int32_t value = c.v[l];  // __pop_heap(first, l, l)
+    c.v[l] = c.v[first];
+    sortAdjustHeap(c, first, 0, l - first, value);
+  }
+}
+HBN_HD void sortUnguardedLinearInsert(const SortCtx& c, int last) {
+  const int32_t val = c.v[last];
+  int next = last - 1;
+  while (sortLess(c, val, c.v[next])) {
+    c.v[last] = c.v[next];
+    last = next;
+    --next;
+  }
+  c.v[last] = val;
+}
+HBN_HD void sortInsertion(const SortCtx& c, int first, int last) {
+  if (first == last) return;
+  for (int i = first + 1; i != last; ++i) {
+    if (sortLess(c, c.v[i], c.v[first])) {
+      const int32_t val = c.v[i];
+      for (int k = i; k > first; --k) c.v[k] = c.v[k - 1];  // move_backward
+      c.v[first] = val;
+    } else {
+      sortUnguardedLinearInsert(c, i);
+    }
+  }
+}
+// std::sort(v, v + n, comp)
+HBN_HD void stdSortOrder(int32_t* v, const float* key, int n) {
+  if (n <= 0) return;
+  const SortCtx c{v, key};
+  // __introsort_loop, with its tail recursion on [cut, last) turned into an explicit stack
+  int depth0 = 0;
+  for (int t = n; t > 1; t >>= 1) depth0++;  // std::__lg(n)
+  depth0 *= 2;
+  int stFirst[64], stLast[64], stDepth[64];
+  int sp = 0;
+  stFirst[0] = 0; stLast[0] = n; stDepth[0] = depth0;
+  sp = 1;
+  while (sp > 0) {
+    --sp;
+    const int first = stFirst[sp];
+    int last = stLast[sp];
+    int depth = stDepth[sp];
+    // the recursive calls of one frame are issued inside its while loop, in order; each
+    // only touches [cut, last), disjoint from what the frame does next, so running them
+    // after the frame (LIFO) gives the same array
+    while (last - first > 16) {
+      if (depth == 0) {
+        sortHeapSort(c, first, last);
+        break;
+      }
+      --depth;
+      const int mid = first + (last - first) / 2;
+      {  // __move_median_to_first(first, first + 1, mid, last - 1)
+        const int a = first + 1, b = mid, cc = last - 1;
+        if (sortLess(c, c.v[a], c.v[b])) {
+          if (sortLess(c, c.v[b], c.v[cc])) sortSwap(c, first, b);
+          else if (sortLess(c, c.v[a], c.v[cc])) sortSwap(c, first, cc);
+          else sortSwap(c, first, a);
+        } else if (sortLess(c, c.v[a], c.v[cc])) {
+          sortSwap(c, first, a);
+        } else if (sortLess(c, c.v[b], c.v[cc])) {
+          sortSwap(c, first, cc);
+        } else {
+          sortSwap(c, first, b);
+        }
+      }
+      int lo = first + 1, hi = last;  // __unguarded_partition(first + 1, last, first)
+      for (;;) {
+        while (sortLess(c, c.v[lo], c.v[first])) ++lo;
+        --hi;
+        while (sortLess(c, c.v[first], c.v[hi])) --hi;
+        if (!(lo < hi)) break;
+        sortSwap(c, lo, hi);
+        ++lo;
+      }
+      if (sp < 64) {
+        stFirst[sp] = lo; stLast[sp] = last; stDepth[sp] = depth;
+        ++sp;
+      }
+      last = lo;
+    }
+  }
+  // __final_insertion_sort
+  if (n > 16) {
+    sortInsertion(c, 0, 16);
+    for (int i = 16; i != n; ++i) sortUnguardedLinearInsert(c, i);
+  } else {
+    sortInsertion(c, 0, n);
+  }
+}
+
+// The goal loop of PF.cpp:1515-1572 given every goal's findPathInternal result dist[i]
+// (+inf = no path), evaluated for a fresh MultiGoalShortestPath: bounds are the L2 distances
+// requestedEnd - requestedStart when there are several goals (max(0 - movedAmount, L2) with
+// movedAmount >= 0 or +inf), zero for a single goal.  bounds / order: scratch of n entries.
+HBN_HD void multiGoalSelect(int n, const float* start, bool startValid, const float* ends,
+                            const uint32_t* endG, const float* dist, float* bounds,
+                            int32_t* order, float* outDist, int32_t* outIndex) {
+  *outDist = infF();
+  *outIndex = -1;
+  if (!startValid || n <= 0) return;  // findPathSetup, PF.cpp:1483-1485
+  bool anyValid = false;
+  for (int i = 0; i < n; ++i) anyValid = anyValid || endG[i] != kNoPoly;
+  if (!anyValid) return;  // PF.cpp:1507-1510
+  for (int i = 0; i < n; ++i) {
+    bounds[i] = n > 1 ? mnDist(&ends[3 * i], start) : 0.0f;
+    order[i] = i;
+  }
+  stdSortOrder(order, bounds, n);
+  float best = infF();
+  int32_t bestIdx = -1;
+  for (int k = 0; k < n; ++k) {
+    const int i = order[k];
+    if (endG[i] == kNoPoly) continue;
+    if (bounds[i] > best) continue;
+    const float d = dist[i];
+    if (d < infF() && d < best) {  // findResult && distance < geodesicDistance
+      best = d;
+      bestIdx = i;
+    }
+  }
+  *outDist = best;
+  *outIndex = bestIdx;
+}
+
 // PathFinder::Impl::tryStep, PF.cpp:1575-1722, phase A: everything up to and including
 // getPolyHeight (:1687).  Inputs are the projectToPoly results of start and end.
 // Returns false if tryStep returns `start` (PF.cpp:1587-1604); else endPoint/lastPoly/startG

@@ -405,10 +405,10 @@ class PathFinder:
             n, g = e.shape[0], e.shape[1]
             dist = torch.empty(n, dtype=torch.float32, device=dev)
             idx = torch.empty(n, dtype=torch.int32, device=dev)
-            npts = torch.empty(n, dtype=torch.int32, device=dev)
+            npts = torch.empty(n, dtype=torch.int32, device=dev) if max_points else None
             pts = torch.full((n, max_points, 3), float("nan"), dtype=torch.float32, device=dev) if max_points else None
             check(L.hbn_find_path_multigoal_dev(h, s.data_ptr(), e.data_ptr(), n, g, dist.data_ptr(),
-                                                idx.data_ptr(), npts.data_ptr(),
+                                                idx.data_ptr(), npts.data_ptr() if npts is not None else None,
                                                 pts.data_ptr() if pts is not None else None, max_points, st))
             return dict(geodesic_distance=dist, closest_end_point_index=idx, num_points=npts, points=pts)
         s = np.ascontiguousarray(np.asarray(starts, np.float32).reshape(-1, 3))
@@ -416,10 +416,10 @@ class PathFinder:
         n, g = e.shape[0], e.shape[1]
         dist = np.empty(n, np.float32)
         idx = np.empty(n, np.int32)
-        npts = np.empty(n, np.int32)
+        npts = np.empty(n, np.int32) if max_points else None
         pts = np.empty((n, max_points, 3), np.float32) if max_points else None
         check(L.hbn_find_path_multigoal(h, s.ctypes.data, e.ctypes.data, n, g, dist.ctypes.data,
-                                        idx.ctypes.data, npts.ctypes.data,
+                                        idx.ctypes.data, npts.ctypes.data if npts is not None else None,
                                         pts.ctypes.data if pts is not None else None, max_points))
         return dict(geodesic_distance=dist, closest_end_point_index=idx, num_points=npts, points=pts)
 

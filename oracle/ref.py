@@ -353,3 +353,11 @@ def random_point_in_convex_poly(pts, s: float, t: float):
     lib().ref_random_point_in_convex_poly(_p(p, f32p), C.c_int(len(p)), C.c_float(s), C.c_float(t),
                                           _p(out, f32p))
     return out
+
+
+def std_sort_order(keys):
+    """libstdc++ std::sort order of indices by float key (the goal ordering of PF.cpp:1542-1548)."""
+    k = np.ascontiguousarray(keys, dtype=np.float32)
+    out = np.zeros(len(k), np.int32)
+    lib().ref_std_sort_order(_p(k, f32p), C.c_int(len(k)), _p(out, i32p))
+    return out

@@ -1611,6 +1611,15 @@ int ref_random_points_near(ref_pf_t h, int64_t n, const float* centers, float ra
   return 1;
 }
 
+// The goal ordering of PF.cpp:1542-1548 on its own: std::sort of 0..n-1 by key (unstable).
+void ref_std_sort_order(const float* key, int n, int32_t* order) {
+  std::vector<size_t> ordering(n);
+  std::iota(ordering.begin(), ordering.end(), 0);
+  std::sort(ordering.begin(), ordering.end(),
+            [key](const size_t a, const size_t b) -> bool { return key[a] < key[b]; });
+  for (int i = 0; i < n; ++i) order[i] = static_cast<int32_t>(ordering[i]);
+}
+
 float ref_uniform(uint64_t seed, uint64_t query, uint32_t draw) {
   return hbnUniform(seed, query, draw);
 }

@@ -123,6 +123,41 @@ void emu_find_path(void* h, const float* starts, const float* ends, long n, int 
   }
 }
 
+// find_path(MultiGoalShortestPath), fresh object per start: ends [n, g, 3]
+void emu_find_path_multigoal(void* h, const float* starts, const float* ends, long n, int g,
+                             float* out_dist, int* out_idx) {
+  Emu* e = static_cast<Emu*>(h);
+  HostGroup grp;
+  uint32_t q[2];
+  const int cap = kMaxNodes;
+  std::vector<char> buf(astarWsBytes(cap) + 64);
+  void* aligned = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(buf.data()) + 15) & ~uintptr_t(15));
+  AStarWs w = astarWsCarve(aligned, cap);
+  std::vector<uint32_t> eG(g);
+  std::vector<float> dist(g), bounds(g);
+  std::vector<int32_t> order(g);
+  for (long i = 0; i < n; ++i) {
+    const float* st = starts + 3 * i;
+    const Nearest s = findNearestPoly(e->nav, grp, st, kExt, -1, q);
+    for (int k = 0; k < g; ++k) {
+      const float* en = ends + (i * g + k) * 3;
+      const Nearest t = findNearestPoly(e->nav, grp, en, kExt, -1, q);
+      eG[k] = t.g;
+      memset(w.hash, 0, sizeof(uint32_t) * 2 * cap);
+      const PathResult r = findPathInternal(e->nav, w, st, en, s.g, s.pt, t.g, t.pt, true, nullptr, 0, nullptr);
+      dist[k] = r.dist;
+    }
+    multiGoalSelect(g, st, s.g != kNoPoly, ends + i * g * 3, eG.data(), dist.data(), bounds.data(),
+                    order.data(), &out_dist[i], &out_idx[i]);
+  }
+}
+
+// the restated std::sort on its own: order[n] <- argsort of key[n] as libstdc++ leaves it
+void emu_std_sort_order(const float* key, int n, int* order) {
+  for (int i = 0; i < n; ++i) order[i] = i;
+  stdSortOrder(order, key, n);
+}
+
 void emu_try_step(void* h, const float* starts, const float* ends, long n, int allowSliding,
                   float* out) {
   Emu* e = static_cast<Emu*>(h);

@@ -112,6 +112,68 @@ def test_find_path(scene):
     assert beq(got2["geodesic_distance"], want["dist"]).all()
 
 
+def test_find_path_multigoal(scene):
+    """findPath(MultiGoalShortestPath&), PathFinder.cpp:1515-1572: distance, closest goal index and
+    path points against the oracle, with duplicate goals (equal sort keys), unprojectable goals /
+    starts and goals far above the mesh (bound > geodesic, so the pruning shows)."""
+    name, pf, ref = scene
+    rng = np.random.default_rng(10)
+    n, g = 400, 12
+    starts = query_points(name, n, 51)
+    ends = query_points(name, n * g, 52).reshape(n, g, 3)
+    ends[:, 4] = ends[:, 2]
+    ends[:, 7, 1] += 3.0
+    lo, hi = ref.get_bounds()
+    ends[::6, 1] = (hi + 50).astype(np.float32)
+    starts[3] = (hi + 50).astype(np.float32)
+    ends[8] = (hi + 50).astype(np.float32)
+    ends[::4, 9] = starts[::4] + rng.normal(0, 0.2, (len(starts[::4]), 3)).astype(np.float32)
+    for gg in (g, 1):
+        e = np.ascontiguousarray(ends[:, :gg])
+        wd, wi, wn, wp = ref.find_path_multigoal_batch(starts, e, max_pts=32, nthreads=8)
+        got = pf.find_paths_multigoal(starts, e, max_points=32)
+        assert (got["closest_end_point_index"] == wi).all(), "closest goal index must be exact"
+        assert close(got["geodesic_distance"], wd).all() and beq(got["geodesic_distance"], wd).all()
+        assert (got["num_points"] == wn).all()
+        for i in np.nonzero(wi >= 0)[0]:
+            m = min(wn[i], 32)
+            assert beq(got["points"][i, :m], wp[i, :m]).all()
+        assert (wi >= 0).mean() > 0.3
+    # multi-goal == min over the single-goal queries (src/tests/PathFinderTest.cpp:102-134) for
+    # goals on the mesh, where the L2 bound cannot exceed the geodesic distance
+    st = query_points(name, 200, 53, jitter=0.0)
+    en = query_points(name, 200 * 6, 54, jitter=0.0).reshape(200, 6, 3)
+    multi = pf.find_paths_multigoal(st, en)["geodesic_distance"]
+    single = pf.find_paths(np.repeat(st, 6, axis=0), en.reshape(-1, 3))["geodesic_distance"].reshape(200, 6)
+    assert beq(multi, single.min(axis=1)).all()
+
+
+def test_multigoal_device_and_scalar_api():
+    import torch
+    from habitat_sim_b200.nav import MultiGoalShortestPath
+    pf = gpu_pathfinder("c3_multiroom")
+    ref = ref_pathfinder("c3_multiroom")
+    starts = query_points("c3_multiroom", 300, 55)
+    ends = query_points("c3_multiroom", 300 * 16, 56).reshape(300, 16, 3)
+    host = pf.find_paths_multigoal(starts, ends, max_points=8)
+    dev = pf.find_paths_multigoal(torch.from_numpy(starts).cuda(), torch.from_numpy(ends).cuda(), max_points=8)
+    torch.cuda.synchronize()
+    assert beq(dev["geodesic_distance"].cpu().numpy(), host["geodesic_distance"]).all()
+    assert (dev["closest_end_point_index"].cpu().numpy() == host["closest_end_point_index"]).all()
+    assert (dev["num_points"].cpu().numpy() == host["num_points"]).all()
+    wd, wi, wn, wp = ref.find_path_multigoal_batch(starts[:5], ends[:5], max_pts=256)
+    for i in range(5):
+        p = MultiGoalShortestPath()
+        p.requested_start = starts[i]
+        p.requested_ends = ends[i]
+        ok = pf.find_path(p)
+        assert ok == bool(np.isfinite(wd[i]))
+        assert p.closest_end_point_index == wi[i] and len(p.points) == wn[i]
+        assert np.float32(p.geodesic_distance) == wd[i] or (np.isinf(wd[i]) and np.isinf(p.geodesic_distance))
+        for k in range(wn[i]):
+            assert beq(p.points[k], wp[i, k]).all()
+
+
 def test_try_step(scene):
     name, pf, ref = scene
     from workloads.scenes import step_targets

@@ -159,3 +159,68 @@ def test_uniform_stream_definition_matches_oracle():
     emu = hostemu()  # noqa: F841  (forces the build; the stream itself is checked via random points)
     assert 0.0 <= ref.uniform(1, 2, 3) <= 1.0
     assert ref.uniform(1, 2, 3) != ref.uniform(1, 2, 4)
+
+
+def test_restated_std_sort_matches_libstdcxx():
+    """stdSortOrder (hbn_query.h) against the oracle's real std::sort, same comparator as
+    PathFinder.cpp:1544-1548: tie-heavy, sorted, reversed, organ-pipe and random keys at sizes on
+    both sides of the insertion-sort threshold (16) and deep enough to hit the heapsort fallback."""
+    from oracle.ref import std_sort_order
+    emu = hostemu()
+    rng = np.random.default_rng(8)
+    cases = []
+    for n in [1, 2, 3, 15, 16, 17, 31, 32, 33, 64, 100, 257, 1000]:
+        cases.append(rng.random(n).astype(np.float32))
+        cases.append(rng.integers(0, 3, n).astype(np.float32))          # many ties
+        cases.append(np.sort(rng.random(n)).astype(np.float32))
+        cases.append(np.sort(rng.random(n))[::-1].astype(np.float32).copy())
+        cases.append(np.zeros(n, np.float32))
+        k = np.arange(n, dtype=np.float32)
+        cases.append(np.minimum(k, n - 1 - k))                              # organ pipe
+        cases.append(np.where(np.arange(n) % 2 == 0, k, n - k).astype(np.float32))
+    # median-of-3 killer sequence: drives introsort to its depth limit (heapsort fallback)
+    for n in [64, 256, 1024]:
+        k = n // 2
+        a = np.zeros(n, np.float32)
+        for i in range(k):
+            if i % 2 == 0:
+                a[i] = i + 1
+            else:
+                a[i] = k + i + (k % 2)
+            a[k + i] = 2 * (i + 1)
+        cases.append(a)
+    for keys in cases:
+        want = std_sort_order(keys)
+        got = np.zeros(len(keys), np.int32)
+        emu.emu_std_sort_order(P(np.ascontiguousarray(keys), f32p), C.c_int(len(keys)), P(got, i32p))
+        assert (got == want).all(), (len(keys), keys[:8])
+
+
+@pytest.mark.parametrize("name", ["c2_apartment", "t_building"])
+def test_hostemu_multigoal_matches_oracle(name):
+    """multiGoalSelect + restated sort vs the oracle's findPath(MultiGoalShortestPath&): duplicate
+    goals (equal bounds), invalid goals, goals above the mesh (geodesic < L2 bound, so pruning
+    is observable), invalid starts, a single goal."""
+    emu, h = _emu_handle(name)
+    pf = ref_pathfinder(name)
+    rng = np.random.default_rng(9)
+    n, g = 120, 9
+    starts = query_points(name, n, 41)
+    ends = query_points(name, n * g, 42).reshape(n, g, 3)
+    ends[:, 3] = ends[:, 1]                       # duplicate goal -> equal bounds
+    ends[:, 5, 1] += 3.0                          # far above: L2 bound exceeds the geodesic distance
+    lo, hi = pf.get_bounds()
+    ends[::7, 2] = (hi + 50).astype(np.float32)   # cannot be projected
+    starts[5] = (hi + 50).astype(np.float32)
+    ends[9] = (hi + 50).astype(np.float32)        # no valid goal at all
+    ends[::5, 6] = starts[::5] + rng.normal(0, 0.3, (len(starts[::5]), 3)).astype(np.float32)
+    for gg in (g, 1):
+        e = np.ascontiguousarray(ends[:, :gg])
+        wd, wi, _, _ = pf.find_path_multigoal_batch(starts, e)
+        gd = np.zeros(n, np.float32)
+        gi = np.zeros(n, np.int32)
+        emu.emu_find_path_multigoal(h, P(starts, f32p), P(e, f32p), C.c_long(n), C.c_int(gg), P(gd, f32p), P(gi, i32p))
+        assert (gi == wi).all()
+        assert beq(gd, wd).all()
+        assert (wi >= 0).mean() > 0.5
+    emu.emu_destroy(h)

@@ -1,4 +1,5 @@
 set -x
-timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/r1c_pytest_gpu.log; cat gpurun_out/r1c_pytest_gpu.log
-timeout 300 python bench.py --steps 3 > gpurun_out/r1c_bench.json 2> gpurun_out/r1c_bench.err; tail -3 gpurun_out/r1c_bench.err; cat gpurun_out/r1c_bench.json
-timeout 200 compute-sanitizer --tool racecheck python tools/small_fp.py t_building 1000 2>&1 | grep -v "^=========     at\|^=========     by\|Host Frame" | tail -12
+timeout 400 python -m pytest tests -m gpu -x -q 2>&1 | tail -12 > gpurun_out/r1d_pytest_gpu.log; cat gpurun_out/r1d_pytest_gpu.log
+timeout 300 python bench.py --steps 3 > gpurun_out/r1d_bench.json 2> gpurun_out/r1d_bench.err; tail -3 gpurun_out/r1d_bench.err; cat gpurun_out/r1d_bench.json
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_findpath_w -s 6 -c 1 -o gpurun_out/r1d_findpath -f python bench.py --steps 1 --warmup 3 --queries 100000 --no-cpu-baseline > gpurun_out/r1d_ncu_full.log 2>&1
+tail -2 gpurun_out/r1d_ncu_full.log | cut -c1-300
