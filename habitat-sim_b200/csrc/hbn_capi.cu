@@ -11,6 +11,7 @@
 #include "../../include/hbn.h"
 #include "hbn_host.h"
 #include "hbn_kernels.cuh"
+#include "hbn_astar_group.cuh"
 
 using namespace hbn;
 
@@ -74,6 +75,10 @@ struct hbn_navmesh {
   std::recursive_mutex mu;
   // scratch (device)
   DevBuf sG, eG, e2G, sPt, ePt, epPt, lastPoly, lists, counters, wsL, wsFp, io, work, mgDist, mgBounds, mgOrder, mgEnd;
+  // lock-step find_path (hbn_astar_group.cuh): class, search list, status, corridor rings, node records
+  DevBuf fpCls, fpWork, fpStat, fpLen, fpCorr, wsFpG;
+  int fpG = 8;          // lanes per query of k_astar_g; 0 = one query per warp (k_findpath_w tiers only)
+  int blocksFpG = 0;
   // pinned staging for the host-buffer entry points
   void* pinned = nullptr;
   size_t pinnedCap = 0;
@@ -98,6 +103,15 @@ int upload(hbn_navmesh* nm, const std::vector<T>& v, const T** out) {
   if (!v.empty()) CK(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
   *out = static_cast<const T*>(d);
   return HBN_OK;
+}
+
+const void* groupKernel(int g) {
+  switch (g) {
+    case 4: return reinterpret_cast<const void*>(&k_astar_g<4, kOpenS>);
+    case 16: return reinterpret_cast<const void*>(&k_astar_g<16, kOpenS>);
+    case 32: return reinterpret_cast<const void*>(&k_astar_g<32, kOpenS>);
+    default: return reinterpret_cast<const void*>(&k_astar_g<8, kOpenS>);
+  }
 }
 
 int finishCreate(HostNavMesh& mesh, const int32_t* islands, int device, hbn_navmesh_t* out) {
@@ -164,6 +178,18 @@ int finishCreate(HostNavMesh& mesh, const int32_t* islands, int device, hbn_navm
   if (const char* e = getenv("HBN_FP_BLOCKS_PER_SM")) nm->blocksFpS = std::max(1, std::min(occ, atoi(e))) * nm->smCount;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_findpath_w<kOpenL, kFpWpb>, 32 * kFpWpb, smFpL));
   nm->blocksFpL = std::max(1, occ) * nm->smCount;
+  // lock-step search: group width from HBN_FP_G (4, 8, 16, 32; "warp" = the one-query-per-warp tiers)
+  if (const char* e = getenv("HBN_FP_G")) nm->fpG = (strcmp(e, "warp") == 0) ? 0 : atoi(e);
+  if (nm->fpG != 0 && nm->fpG != 4 && nm->fpG != 8 && nm->fpG != 16 && nm->fpG != 32) nm->fpG = 8;
+  if (nm->fpG) {
+    const size_t smG = (32 / nm->fpG) * gGroupSharedBytes<kOpenS>();
+    const void* fn = groupKernel(nm->fpG);
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smG)));
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32, smG));
+    nm->blocksFpG = std::max(1, occ) * nm->smCount;
+    if (const char* e = getenv("HBN_FP_BLOCKS_PER_SM")) nm->blocksFpG = std::max(1, std::min(occ, atoi(e))) * nm->smCount;
+  }
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wall<kWallCapS, kWsShared>, threads, smW));
   nm->blocksWallS = std::max(1, occ) * nm->smCount;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wall<kCapL, kWsHybrid>, threads, smL));
@@ -173,6 +199,8 @@ int finishCreate(HostNavMesh& mesh, const int32_t* islands, int device, hbn_navm
   if (rc == HBN_OK)
     rc = nm->wsFp.ensure(static_cast<size_t>(std::max(nm->blocksFpS, nm->blocksFpL)) * kFpWpb *
                          WarpWs<kOpenS>::globalBytes());
+  if (rc == HBN_OK && nm->fpG)
+    rc = nm->wsFpG.ensure(static_cast<size_t>(nm->blocksFpG) * (32 / nm->fpG) * gGroupGlobalBytes());
   if (rc == HBN_OK) rc = nm->counters.ensure(64);
   if (rc == HBN_OK) rc = nm->work.ensure(64);
   if (rc == HBN_OK) {
@@ -279,7 +307,8 @@ void hbn_navmesh_destroy(hbn_navmesh_t nm) {
   for (void* d : nm->devArrays) cudaFree(d);
   for (DevBuf* b : {&nm->sG, &nm->eG, &nm->e2G, &nm->sPt, &nm->ePt, &nm->epPt, &nm->lastPoly,
                     &nm->lists, &nm->counters, &nm->wsL, &nm->wsFp, &nm->io, &nm->work, &nm->mgDist,
-                    &nm->mgBounds, &nm->mgOrder, &nm->mgEnd})
+                    &nm->mgBounds, &nm->mgOrder, &nm->mgEnd, &nm->fpCls, &nm->fpWork, &nm->fpStat,
+                    &nm->fpLen, &nm->fpCorr, &nm->wsFpG})
     b->release();
   if (nm->pinned) cudaFreeHost(nm->pinned);
   if (nm->faultHost) cudaFreeHost(nm->faultHost);
@@ -409,6 +438,33 @@ int hbn_is_navigable_dev(hbn_navmesh_t nm, const float* pts, int64_t n, float ma
 
 }  // extern "C"
 
+// one-query-per-warp tiers (hbn_astar_warp.cuh) over `work` (nullptr: all n queries): search +
+// funnel + outputs in one kernel.  cnt: 4 zeroed counters.
+static int warpTierLaunch(hbn_navmesh_t nm, FindPathArgs a, bool smallTier, uint32_t* cnt, cudaStream_t st) {
+  a.counter = cnt + 0;
+  a.overflow = static_cast<uint32_t*>(nm->lists.p);
+  a.overflowCount = cnt + 1;
+  a.scratch = static_cast<char*>(nm->wsFp.p);
+  if (smallTier) {
+    int64_t blocks = std::min<int64_t>(nm->blocksFpS, (a.n + kFpWpb - 1) / kFpWpb);
+    k_findpath_w<kOpenS, kFpWpb><<<static_cast<unsigned>(blocks), 32 * kFpWpb,
+                                   kFpWpb * WarpWs<kOpenS>::sharedBytes(), st>>>(nm->view, a);
+    nm->launches++;
+    CK(cudaGetLastError());
+    // large tier over the overflow list (its length stays on the device)
+    a.work = a.overflow;
+    a.workCount = a.overflowCount;
+    a.counter = cnt + 2;
+    a.overflowCount = cnt + 3;  // cannot overflow: open list <= kMaxNodes
+  }
+  k_findpath_w<kOpenL, kFpWpb><<<nm->blocksFpL, 32 * kFpWpb, kFpWpb * WarpWs<kOpenL>::sharedBytes(), st>>>(nm->view, a);
+  nm->launches++;
+  CK(cudaGetLastError());
+  return HBN_OK;
+}
+
+constexpr int64_t kFpChunk = 1 << 20;  // queries per pass of the lock-step pipeline (1 KB corridor ring each)
+
 // n (start, end) pairs; startDiv > 1: pair q uses start q / startDiv (multi-goal layout)
 static int findPathLaunch(hbn_navmesh_t nm, const float* starts, const float* ends, int64_t n,
                           int startDiv, float* out_dist, int32_t* out_npts, float* out_pts, int max_pts,
@@ -424,11 +480,18 @@ static int findPathLaunch(hbn_navmesh_t nm, const float* starts, const float* en
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc;
   if ((rc = checkFault(nm))) return rc;  // reported by an earlier launch
+  const int64_t chunk = startDiv > 1 ? std::max<int64_t>(1, kFpChunk / startDiv) * startDiv : kFpChunk;
+  const int64_t nChunks = nm->fpG ? (n + chunk - 1) / chunk : 1;
+  const int64_t cmax = std::min(n, chunk);
   if ((rc = nm->sG.ensure(nStarts * 4)) || (rc = nm->eG.ensure(n * 4)) || (rc = nm->sPt.ensure(nStarts * 12)) ||
-      (rc = nm->ePt.ensure(n * 12)) || (rc = nm->lists.ensure(n * 4)))
+      (rc = nm->ePt.ensure(n * 12)) || (rc = nm->lists.ensure(cmax * 4)) ||
+      (rc = nm->counters.ensure(static_cast<size_t>(nChunks) * 64)))
     return rc;
-  uint32_t* cnt = static_cast<uint32_t*>(nm->counters.p);
-  CK(cudaMemsetAsync(cnt, 0, 64, st));
+  if (nm->fpG &&
+      ((rc = nm->fpCls.ensure(cmax)) || (rc = nm->fpWork.ensure(cmax * 4)) || (rc = nm->fpStat.ensure(cmax * 4)) ||
+       (rc = nm->fpLen.ensure(cmax * 4)) || (rc = nm->fpCorr.ensure(static_cast<size_t>(cmax) * kMaxPathPolys * 4))))
+    return rc;
+  CK(cudaMemsetAsync(nm->counters.p, 0, static_cast<size_t>(nChunks) * 64, st));
   hbn_navmesh::PhaseEv pe{};
   if (nm->profile) {
     for (auto& e : pe.e) CK(cudaEventCreate(&e));
@@ -441,39 +504,84 @@ static int findPathLaunch(hbn_navmesh_t nm, const float* starts, const float* en
                        static_cast<uint32_t*>(nm->eG.p), nullptr, nullptr, nullptr, 0.f, st)))
     return rc;
   if (nm->profile) CK(cudaEventRecord(pe.e[1], st));
-  FindPathArgs a{};
-  a.starts = starts; a.ends = ends;
-  a.sG = static_cast<uint32_t*>(nm->sG.p); a.sPt = static_cast<float*>(nm->sPt.p);
-  a.eG = static_cast<uint32_t*>(nm->eG.p); a.ePt = static_cast<float*>(nm->ePt.p);
-  a.n = n;
-  a.work = nullptr; a.workCount = nullptr;
-  a.counter = cnt + 0;
-  a.overflow = static_cast<uint32_t*>(nm->lists.p);
-  a.overflowCount = cnt + 1;
-  a.out_dist = out_dist; a.out_npts = out_npts; a.out_pts = out_pts; a.max_pts = max_pts;
-  a.out_corridor = out_corridor; a.out_ncorridor = out_ncorridor; a.out_status = out_status;
-  a.scratch = static_cast<char*>(nm->wsFp.p);
-  a.fault = nm->faultDev;
-  a.startDiv = startDiv;
-  a.fastFail = (flags & HBN_FP_EXACT_STATUS) ? 0 : 1;
-  a.workCtr = (flags & HBN_FP_COUNT_WORK) ? static_cast<unsigned long long*>(nm->work.p) : nullptr;
-  {
-    int64_t blocks = std::min<int64_t>(nm->blocksFpS, (n + kFpWpb - 1) / kFpWpb);
-    k_findpath_w<kOpenS, kFpWpb><<<static_cast<unsigned>(blocks), 32 * kFpWpb,
-                                   kFpWpb * WarpWs<kOpenS>::sharedBytes(), st>>>(nm->view, a);
+  unsigned long long* workCtr = (flags & HBN_FP_COUNT_WORK) ? static_cast<unsigned long long*>(nm->work.p) : nullptr;
+  for (int64_t ci = 0; ci < nChunks; ++ci) {
+    const int64_t c0 = nm->fpG ? ci * chunk : 0;
+    const int64_t cn = nm->fpG ? std::min(chunk, n - c0) : n;
+    const int64_t s0 = startDiv > 1 ? c0 / startDiv : c0;
+    uint32_t* cnt = static_cast<uint32_t*>(nm->counters.p) + ci * 16;
+    FindPathArgs a{};
+    a.starts = starts + 3 * s0; a.ends = ends + 3 * c0;
+    a.sG = static_cast<uint32_t*>(nm->sG.p) + s0; a.sPt = static_cast<float*>(nm->sPt.p) + 3 * s0;
+    a.eG = static_cast<uint32_t*>(nm->eG.p) + c0; a.ePt = static_cast<float*>(nm->ePt.p) + 3 * c0;
+    a.n = cn;
+    a.work = nullptr; a.workCount = nullptr;
+    a.out_dist = out_dist + c0;
+    a.out_npts = out_npts ? out_npts + c0 : nullptr;
+    a.out_pts = out_pts ? out_pts + static_cast<size_t>(c0) * max_pts * 3 : nullptr;
+    a.max_pts = max_pts;
+    a.out_corridor = out_corridor ? out_corridor + static_cast<size_t>(c0) * kMaxPathPolys : nullptr;
+    a.out_ncorridor = out_ncorridor ? out_ncorridor + c0 : nullptr;
+    a.out_status = out_status ? out_status + 2 * c0 : nullptr;
+    a.fault = nm->faultDev;
+    a.startDiv = startDiv;
+    a.fastFail = (flags & HBN_FP_EXACT_STATUS) ? 0 : 1;
+    a.workCtr = workCtr;
+    if (!nm->fpG) {
+      if ((rc = warpTierLaunch(nm, a, true, cnt, st))) return rc;
+      continue;
+    }
+    // lock-step pipeline: classify -> search -> funnel (+ the 2048-entry tier for overflows)
+    uint8_t* cls = static_cast<uint8_t*>(nm->fpCls.p);
+    uint32_t* work = static_cast<uint32_t*>(nm->fpWork.p);
+    k_fp_classify<<<static_cast<unsigned>((cn + 255) / 256), 256, 0, st>>>(nm->view, a.sG, a.sPt, a.eG, a.ePt, cn,
+                                                                          startDiv, cls, work, cnt + 4);
     nm->launches++;
     CK(cudaGetLastError());
+    AStarGArgs ga{};
+    ga.sG = a.sG; ga.sPt = a.sPt; ga.eG = a.eG; ga.ePt = a.ePt;
+    ga.work = work; ga.workCount = cnt + 4;
+    ga.counter = cnt + 5;
+    ga.overflow = static_cast<uint32_t*>(nm->lists.p);
+    ga.overflowCount = cnt + 6;
+    ga.astat = static_cast<uint32_t*>(nm->fpStat.p);
+    ga.fullLen = static_cast<int32_t*>(nm->fpLen.p);
+    ga.corrVia = static_cast<uint32_t*>(nm->fpCorr.p);
+    ga.scratch = static_cast<char*>(nm->wsFpG.p);
+    ga.startDiv = startDiv;
+    ga.fastFail = a.fastFail;
+    ga.allCorridors = (out_corridor || out_ncorridor) ? 1 : 0;
+    ga.workCtr = workCtr;
+    ga.fault = nm->faultDev;
+    {
+      const int qpw = 32 / nm->fpG;
+      const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(nm->blocksFpG, (cn + qpw - 1) / qpw));
+      const size_t sm = qpw * gGroupSharedBytes<kOpenS>();
+      switch (nm->fpG) {
+        case 4: k_astar_g<4, kOpenS><<<blocks, 32, sm, st>>>(nm->view, ga); break;
+        case 16: k_astar_g<16, kOpenS><<<blocks, 32, sm, st>>>(nm->view, ga); break;
+        case 32: k_astar_g<32, kOpenS><<<blocks, 32, sm, st>>>(nm->view, ga); break;
+        default: k_astar_g<8, kOpenS><<<blocks, 32, sm, st>>>(nm->view, ga); break;
+      }
+      nm->launches++;
+      CK(cudaGetLastError());
+    }
+    FpFunnelArgs fa{};
+    fa.starts = a.starts; fa.ends = a.ends;
+    fa.sG = a.sG; fa.sPt = a.sPt; fa.eG = a.eG; fa.ePt = a.ePt;
+    fa.cls = cls; fa.astat = ga.astat; fa.fullLen = ga.fullLen; fa.corrVia = ga.corrVia;
+    fa.n = cn; fa.startDiv = startDiv;
+    fa.out_dist = a.out_dist; fa.out_npts = a.out_npts; fa.out_pts = a.out_pts; fa.max_pts = max_pts;
+    fa.out_corridor = a.out_corridor; fa.out_ncorridor = a.out_ncorridor; fa.out_status = a.out_status;
+    fa.workCtr = workCtr;
+    k_fp_funnel<<<static_cast<unsigned>((cn + 127) / 128), 128, 0, st>>>(nm->view, fa);
+    nm->launches++;
+    CK(cudaGetLastError());
+    // queries whose open list outgrew kOpenS: one query per warp with a 2048-entry heap
+    a.work = ga.overflow;
+    a.workCount = ga.overflowCount;
+    if ((rc = warpTierLaunch(nm, a, false, cnt, st))) return rc;
   }
-  // large tier over the overflow list (its length stays on the device)
-  FindPathArgs b = a;
-  b.work = a.overflow;
-  b.workCount = a.overflowCount;
-  b.counter = cnt + 2;
-  b.overflow = static_cast<uint32_t*>(nm->lists.p);  // cannot overflow: open list <= kMaxNodes
-  b.overflowCount = cnt + 3;
-  k_findpath_w<kOpenL, kFpWpb><<<nm->blocksFpL, 32 * kFpWpb, kFpWpb * WarpWs<kOpenL>::sharedBytes(), st>>>(nm->view, b);
-  nm->launches++;
-  CK(cudaGetLastError());
   if (nm->profile) {
     CK(cudaEventRecord(pe.e[2], st));
     nm->phaseEvents.push_back(pe);

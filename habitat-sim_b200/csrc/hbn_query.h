@@ -723,16 +723,32 @@ HBN_HD uint32_t funnelAppend(Funnel& f, const float* pos, bool isEnd) {
   return 0;
 }
 
+// Corridor accessors of the funnel: poly(i) = global poly index, link(i) = LinkRec index of the
+// portal poly(i) -> poly(i+1) (kNoPoly: none), portal(i, li, l, r) = its left / right points.
 // staged (nullable): the corridor's portals already gathered, staged[i] == nav.portals[pathLink[i]].
-HBN_HD uint32_t funnelStraightPath(const NavView& nav, const float* startPos, const float* endPos,
-                                   const uint32_t* path, const uint32_t* pathLink, int pathSize,
-                                   Funnel& f, const PortalRec* staged = nullptr) {
+struct ArrayCorridor {
+  const NavView& nav;
+  const uint32_t* path;
+  const uint32_t* pathLink;
+  const PortalRec* staged;
+  HBN_HD uint32_t poly(int i) const { return path[i]; }
+  HBN_HD uint32_t link(int i) const { return pathLink[i]; }
+  HBN_HD void portal(int i, uint32_t li, float* l, float* r) const {
+    const PortalRec& po = staged ? staged[i] : nav.portals[li];
+    vcopy(l, po.l);
+    vcopy(r, po.r);
+  }
+};
+
+template <class C>
+HBN_HD uint32_t funnelStraightPathT(const NavView& nav, const float* startPos, const float* endPos,
+                                    const C& cor, int pathSize, Funnel& f) {
   f.count = 0;
   f.length = 0.0f;
   if (!vfinite(startPos) || !vfinite(endPos) || pathSize <= 0) return kDtFailure | kDtInvalidParam;
   float closestStartPos[3], closestEndPos[3];
-  closestPointOnPolyBoundary(&nav.polys[path[0]], startPos, closestStartPos);
-  closestPointOnPolyBoundary(&nav.polys[path[pathSize - 1]], endPos, closestEndPos);
+  closestPointOnPolyBoundary(&nav.polys[cor.poly(0)], startPos, closestStartPos);
+  closestPointOnPolyBoundary(&nav.polys[cor.poly(pathSize - 1)], endPos, closestEndPos);
   uint32_t stat = funnelAppend(f, closestStartPos, false);
   if (stat) return stat;
   if (pathSize > 1) {
@@ -745,17 +761,15 @@ HBN_HD uint32_t funnelStraightPath(const NavView& nav, const float* startPos, co
     for (int i = 0; i < pathSize; ++i) {
       float left[3], right[3];
       if (i + 1 < pathSize) {
-        const uint32_t li = pathLink[i];
+        const uint32_t li = cor.link(i);
         if (li == kNoPoly) {
           // getPortalPoints failed (DQ.cpp:1853-1878): clamp end to path[i], partial result
-          closestPointOnPolyBoundary(&nav.polys[path[i]], endPos, closestEndPos);
+          closestPointOnPolyBoundary(&nav.polys[cor.poly(i)], endPos, closestEndPos);
           funnelAppend(f, closestEndPos, false);
           return kDtSuccess | kDtPartialResult |
                  ((f.count >= kMaxPathPolys) ? kDtBufferTooSmall : 0u);
         }
-        const PortalRec& po = staged ? staged[i] : nav.portals[li];
-        vcopy(left, po.l);
-        vcopy(right, po.r);
+        cor.portal(i, li, left, right);
         if (i == 0) {
           float t;
           if (distPtSegSqr2D(portalApex, left, right, t) < sqr(0.001f)) continue;
@@ -806,6 +820,13 @@ HBN_HD uint32_t funnelStraightPath(const NavView& nav, const float* startPos, co
   }
   funnelAppend(f, closestEndPos, true);
   return kDtSuccess | ((f.count >= kMaxPathPolys) ? kDtBufferTooSmall : 0u);
+}
+
+HBN_HD uint32_t funnelStraightPath(const NavView& nav, const float* startPos, const float* endPos,
+                                   const uint32_t* path, const uint32_t* pathLink, int pathSize,
+                                   Funnel& f, const PortalRec* staged = nullptr) {
+  const ArrayCorridor cor{nav, path, pathLink, staged};
+  return funnelStraightPathT(nav, startPos, endPos, cor, pathSize, f);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -15,7 +15,9 @@ import numpy as np
 from .. import _lib
 from .._lib import HbnError, check
 
-__all__ = ["PathFinder", "ShortestPath", "MultiGoalShortestPath", "HitRecord", "NavMeshSettings",
+from .sharding import gather as gather_shards, shard_slice, shard_slices  # noqa: E402,F401
+
+__all__ = ["shard_slices", "shard_slice", "gather_shards", "PathFinder", "ShortestPath", "MultiGoalShortestPath", "HitRecord", "NavMeshSettings",
            "GreedyFollowerCodes", "GreedyGeodesicFollowerImpl", "GreedyGeodesicFollower", "HbnError"]
 
 MAX_PATH_POINTS = 256  # MAX_POLYS, PathFinder.cpp:1443

@@ -239,10 +239,10 @@ class RefPathFinder:
         expanded, links, neighbours, corridor, corridor_links, points."""
         s = _f32(starts).reshape(-1, 3)
         e = _f32(ends).reshape(-1, 3)
-        out = np.zeros((len(s), 6), np.uint32)
+        out = np.zeros((len(s), 8), np.uint32)
         self._l.ref_find_path_stats_batch(self._h, _p(s, f32p), _p(e, f32p), C.c_int64(len(s)),
                                           _p(out, u32p), C.c_int(nthreads))
-        keys = ["expanded", "links", "neighbours", "corridor", "corridor_links", "points"]
+        keys = ["expanded", "links", "neighbours", "corridor", "corridor_links", "points", "nodes", "open_at_end"]
         return {k: out[:, i].astype(np.int64) for i, k in enumerate(keys)}
 
     def find_path_multigoal_batch(self, starts, ends, max_pts: int = 0, nthreads: int = 1):

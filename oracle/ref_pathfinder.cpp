@@ -1457,8 +1457,8 @@ void ref_find_path_stats_batch(ref_pf_t h, const float* starts, const float* end
   auto* pf = static_cast<RefPathFinder*>(h);
   const dtNavMesh* nav = pf->nav();
   parallelFor(pf, n, nthreads, [&](dtNavMeshQuery* q, int64_t i) {
-    uint32_t* st6 = out_stats + i * 6;
-    memset(st6, 0, 24);
+    uint32_t* st6 = out_stats + i * 8;  // [6] nodes allocated, [7] nodes still open at the end
+    memset(st6, 0, 32);
     dtStatus s0, s1;
     dtPolyRef startRef = 0, endRef = 0;
     V3 pathStart, pathEnd;
@@ -1484,8 +1484,10 @@ void ref_find_path_stats_batch(ref_pf_t h, const float* starts, const float* end
     if (raw.connected && startRef != endRef) {
       dtNodePool* pool = q->getNodePool();
       const int cnt = pool->getNodeCount();
+      st6[6] = static_cast<uint32_t>(cnt);
       for (int k = 0; k < cnt; ++k) {
         const dtNode* node = pool->getNodeAtIdx(k + 1);
+        if (node && (node->flags & DT_NODE_OPEN)) st6[7]++;
         if (!node || !(node->flags & DT_NODE_CLOSED)) continue;
         st6[0]++;
         linkStats(node->id, st6[1], st6[2]);

@@ -332,3 +332,35 @@ def test_full_size_properties():
     m = 4000
     want = ref.find_path_batch(st[:m], en[:m], 0, 8)[0]
     assert beq(d[:m], want).all()
+
+
+@pytest.mark.parametrize("width", ["4", "8", "16", "32", "warp"])
+def test_find_path_search_variants(width, monkeypatch):
+    """Every mapping of the search onto the machine (HBN_FP_G lanes per query in lock step, or the
+    one-query-per-warp tiers) must give the reference's corridors, status words and distances."""
+    from workloads.scenes import NavMeshGeom, pointnav_pairs
+    monkeypatch.setenv("HBN_FP_G", width)
+    for name, n in (("t_building", 3000), ("c4_building", 6000)):
+        pf = gpu_pathfinder(name)
+        ref = ref_pathfinder(name)
+        if name == "c4_building":
+            st, en = pointnav_pairs(NavMeshGeom(navmesh_image(name)), n, 11)
+        else:
+            pts = query_points(name, 2 * n, 5)
+            st, en = pts[:n].copy(), pts[n:].copy()
+        want = ref.find_path_raw_batch(st, en, max_pts=32, nthreads=8)
+        got = pf.find_paths(st, en, max_points=32, corridors=True, exact_status=True)
+        assert beq(got["geodesic_distance"], want["dist"]).all()
+        astar_ran = (want["flags"] & 2) != 0
+        assert (got["status"][astar_ran, 0] == want["astar_status"][astar_ran]).all()
+        assert (got["num_corridor"][astar_ran] == want["num_polys"][astar_ran]).all()
+        for i in np.nonzero(astar_ran)[0]:
+            k = want["num_polys"][i]
+            assert (got["corridor"][i, :k] == want["corridor"][i, :k]).all()
+        found = (want["flags"] & 4) != 0
+        assert (got["num_points"][found] == want["num_points"][found]).all()
+        for i in np.nonzero(found)[0]:
+            m = min(want["num_points"][i], 32)
+            assert beq(got["points"][i, :m], want["pts"][i, :m]).all()
+        fast = pf.find_paths(st, en)  # default mode: stop at pool exhaustion
+        assert beq(fast["geodesic_distance"], want["dist"]).all()

@@ -224,3 +224,37 @@ def test_hostemu_multigoal_matches_oracle(name):
         assert beq(gd, wd).all()
         assert (wi >= 0).mean() > 0.5
     emu.emu_destroy(h)
+
+
+def test_shard_slices_cover_and_balance():
+    import habitat_sim_b200  # noqa: F401
+    from habitat_sim_b200.nav import shard_slices
+    for n, world, g in ((0, 4, 1), (7, 8, 1), (1_000_000, 8, 1), (4096 * 64, 8, 64), (1024, 3, 1), (10, 1, 5)):
+        sl = shard_slices(n, world, g)
+        assert len(sl) == world and sl[0][0] == 0 and sl[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(sl, sl[1:]))
+        sizes = [e - b for b, e in sl]
+        assert all(s % g == 0 for s in sizes) and max(sizes) - min(sizes) <= g
+    with pytest.raises(ValueError):
+        shard_slices(10, 2, 4)
+
+
+def test_sharding_gloo_world2():
+    """The N > 1 path on CPU: two gloo ranks, each answering its slice (tests/_shard_worker.py)."""
+    import socket
+    import subprocess
+    import sys
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    hostemu()  # build once, not concurrently
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(os.path.dirname(__file__), "_shard_worker.py")],
+                                      env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for rank, p in enumerate(procs):
+        out, _ = p.communicate(timeout=240)
+        assert p.returncode == 0, out[-2000:]
+        assert f"rank {rank} ok" in out

@@ -1,0 +1,18 @@
+"""GPU throughput sweep of the find_path search variants (HBN_FP_G) on the C4 workload.
+usage: python tools/sweep_fp.py [queries]"""
+import json, os, subprocess, sys
+n = sys.argv[1] if len(sys.argv) > 1 else "400000"
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for g, bps in (("warp", None), ("8", None), ("16", None), ("32", None), ("4", None), ("8", "4"), ("8", "5")):
+    env = dict(os.environ, HBN_FP_G=g)
+    if bps:
+        env["HBN_FP_BLOCKS_PER_SM"] = bps
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "2", "--warmup", "3",
+                          "--queries", n, "--no-cpu-baseline"], env=env, capture_output=True, text=True)
+    try:
+        j = json.loads(out.stdout.strip().splitlines()[-1])
+        print(f"G={g} blocks/SM={bps}: value={j['value']:.0f} q/s e2e={j['e2e']['value']:.0f} "
+              f"path_ms={j['roofline']['kernel_ms_per_step']:.2f} snap_ms={j['roofline']['snap_ms_per_step']:.2f} "
+              f"launches={j['gpu_launches']}", flush=True)
+    except Exception as ex:
+        print(f"G={g}: failed {ex}: {out.stdout[-300:]} {out.stderr[-600:]}", flush=True)
