@@ -1,0 +1,108 @@
+// k_astar_lane: 32 find_path searches per warp in lock step, one query per lane (the state
+// machine is hbn_astar_lane.h).  Persistent one-warp blocks pull queries from the search list
+// of k_fp_classify with a warp-aggregated atomic; a lane whose query ends takes the next one
+// in the same iteration, so the lanes of a warp stay busy until the list is empty.
+// Outputs are the ones of k_astar_g: status word, corridor ring, overflow list; the funnel
+// runs in k_fp_funnel.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "hbn_astar_group.cuh"  // AStarGArgs, kSearchOverflow
+#include "hbn_astar_lane.h"
+
+namespace hbn {
+
+struct LaneScratch {
+  char* base;           // one laneScratchBytes(numKeys) slot per lane of the grid
+  uint32_t* gen;        // table generation of every lane slot (persists across launches)
+  size_t bytesPerLane;
+  size_t tabBytes;
+};
+
+template <int OC>
+__host__ __device__ constexpr size_t laneSharedBytes() { return static_cast<size_t>(OC) * 32 * 6; }
+
+template <int OC>
+__global__ void __launch_bounds__(32) k_astar_lane(NavView nav, AStarGArgs a, LaneScratch sc) {
+  constexpr uint32_t FULL = 0xffffffffu;
+  extern __shared__ __align__(16) char smem[];
+  const int lane = threadIdx.x;
+  const uint32_t ltMask = (1u << lane) - 1u;
+  const size_t slotId = static_cast<size_t>(blockIdx.x) * 32 + lane;
+  LaneSearch<32, OC> s;
+  s.K = reinterpret_cast<float*>(smem) + lane;
+  s.S = reinterpret_cast<uint16_t*>(smem + static_cast<size_t>(OC) * 32 * 4) + lane;
+  s.tab = reinterpret_cast<uint16_t*>(sc.base + slotId * sc.bytesPerLane);
+  s.rec = sc.base + slotId * sc.bytesPerLane + sc.tabBytes;
+  s.cv = nullptr;
+  s.gen = sc.gen[slotId];
+  s.mode = kLIdle;
+  s.q = 0; s.endG = 0; s.size = 0; s.nodeCount = 0; s.status = 0; s.xk = 0; s.xcur = 0;
+  s.expanded = s.nLinks = s.nNeigh = 0;
+  const uint32_t nWork = *a.workCount;
+  const bool fastFail = a.fastFail != 0, allCorridors = a.allCorridors != 0;
+  const uint32_t tabVec = static_cast<uint32_t>(sc.tabBytes / 16);
+
+  for (;;) {
+    // ---- idle lanes take the next queries -------------------------------------------------
+    const uint32_t idle = __ballot_sync(FULL, s.mode == kLIdle);
+    if (idle) {
+      const int leader = __ffs(idle) - 1;
+      uint32_t wi = 0;
+      if (lane == leader) wi = atomicAdd(a.counter, static_cast<uint32_t>(__popc(idle)));
+      wi = __shfl_sync(FULL, wi, leader) + static_cast<uint32_t>(__popc(idle & ltMask));
+      const bool mine = s.mode == kLIdle;
+      const bool take = mine && wi < nWork;
+      if (mine && !take) s.mode = kLDone;
+      // generations used up: the whole warp wipes the tables of those lanes
+      uint32_t wipe = __ballot_sync(FULL, take && s.gen >= kLaneGenMax);
+      while (wipe) {
+        const int l = __ffs(wipe) - 1;
+        wipe &= wipe - 1;
+        uint4* t = reinterpret_cast<uint4*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(s.tab), l));
+        for (uint32_t i = lane; i < tabVec; i += 32) t[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (lane == l) s.gen = 0;
+      }
+      __syncwarp();
+      if (take) {
+        const uint32_t q = a.work[wi];
+        const uint32_t qs = a.startDiv > 1 ? q / static_cast<uint32_t>(a.startDiv) : q;
+        const float sp[3] = {a.sPt[3 * static_cast<size_t>(qs)], a.sPt[3 * static_cast<size_t>(qs) + 1],
+                             a.sPt[3 * static_cast<size_t>(qs) + 2]};
+        const float ep[3] = {a.ePt[3 * static_cast<size_t>(q)], a.ePt[3 * static_cast<size_t>(q) + 1],
+                             a.ePt[3 * static_cast<size_t>(q) + 2]};
+        s.begin(nav, q, a.sG[qs], sp, a.eG[q], ep, a.corrVia + static_cast<size_t>(q) * kMaxPathPolys);
+      }
+    }
+    if (__all_sync(FULL, s.mode == kLDone)) break;
+
+    const int ev = s.step(nav, fastFail, allCorridors);
+    if (ev != kLEvNone) {
+      const uint32_t q = s.q;
+      if (ev == kLEvFault) {
+        atomicAdd(a.fault, 1u);
+        a.fault[1] = q;
+        a.fault[2] = 5u | (OC << 8);
+        a.astat[q] = kDtFailure;
+        a.fullLen[q] = 0;
+      } else if (ev == kLEvOverflow) {
+        const uint32_t o = atomicAdd(a.overflowCount, 1u);
+        a.overflow[o] = q;
+        a.astat[q] = kSearchOverflow;
+        a.fullLen[q] = 0;
+      } else {
+        a.astat[q] = s.status;
+        a.fullLen[q] = s.xk;
+      }
+      if (a.workCtr && ev != kLEvOverflow) {
+        atomicAdd(a.workCtr + 0, static_cast<unsigned long long>(s.expanded));
+        atomicAdd(a.workCtr + 1, static_cast<unsigned long long>(s.nLinks));
+        atomicAdd(a.workCtr + 2, static_cast<unsigned long long>(s.nNeigh));
+        atomicAdd(a.workCtr + 6, 1ull);
+      }
+    }
+  }
+  sc.gen[slotId] = s.gen;
+}
+
+}  // namespace hbn

@@ -1,0 +1,385 @@
+// Lane-per-query find_path search: the state machine of ONE query, host + device code.
+//
+// dtNavMeshQuery::findPath (DQ.cpp:973-1165) is a serial algorithm; its result depends on the
+// exact order of its heap operations (DNode.cpp:156-200) and of node allocation against the
+// 2048-node pool (PF.cpp:937).  Splitting one query over lanes (hbn_astar_warp.cuh,
+// hbn_astar_group.cuh) leaves most issue slots on warp-uniform bookkeeping: ~500 warp
+// instructions per poly expansion, and shared memory caps an SM at ~25 queries in flight.
+// Here a query belongs to ONE lane and a warp advances 32 queries in lock step (k_astar_lane,
+// hbn_astar_lane.cuh): one warp instruction now serves 32 expansions, and the per-query state
+// that does not fit on chip lives in HBM, sized for 180 GB:
+//
+//   shared  : only the binary heap, 6 B per entry {f32 total, u16 node}, interleaved over the
+//             lanes of the warp (entry i of lane l at word i*32 + l: never a bank conflict);
+//   global  : per lane (a) a DIRECT-MAPPED node table, one u16 per node key (poly, crossSide)
+//             -- the keys are enumerated by the flattener (LinkRec::neiKey, PolyRec::key0) --
+//             holding generation << 11 | node, so a lookup is one load, never a probe loop,
+//             and a new query just bumps the generation (the table is wiped every 31 queries);
+//             (b) 2048 node records of 32 B in ALLOCATION order (dtNodePool's index order):
+//             {pos, cost | poly+flags, parent poly + entering link, link window, parent node +
+//             heap position}.
+//   The heap position of every open node is kept in its record (one byte store per heap
+//   move), so dtNodeQueue::modify (DNode.h:132-142) needs no scan.  A node's total is not
+//   stored: it is cost + heuristic(pos), recomputed with the same operations.
+//
+// One step() = one iteration of the reference's while loop: pop, then the popped poly's links
+// in chunks of kLaneChunk: all link records, then all table entries, then all found records
+// are loaded before the serial part, so a lane has up to 6 independent loads in flight per
+// stage instead of a chain of 3 dependent loads per neighbour.
+// Corridor extraction (getPathToNode, DQ.cpp:1167-1205) is a pointer chase; it runs as a mode
+// of the same state machine, a few hops per step, so it never stalls the other 31 queries.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#include "hbn_query.h"
+
+namespace hbn {
+
+constexpr uint32_t kLaneSlotBits = 11;  // node index < 2048
+constexpr uint32_t kLaneSlotMask = (1u << kLaneSlotBits) - 1u;
+constexpr uint32_t kLaneGenMax = 31;    // generations 1..31, then the table is wiped
+constexpr uint32_t kLaneNoParent = 0x00ffffffu;
+constexpr int kLaneChunk = 6;           // links handled per load stage
+constexpr int kLaneHops = 2;            // corridor hops per step
+constexpr uint32_t kLaneFlagOpen = 1u, kLaneFlagClosed = 2u;
+constexpr uint32_t kLaneMaxExpansions = 1u << 18;  // >> any legal search (2048 nodes, re-opens)
+static_assert(kMaxNodes <= (1 << kLaneSlotBits), "node index must fit the table entry");
+
+struct HBN_ALIGN(16) LaneRecA {
+  float px, py, pz, cost;
+};
+struct HBN_ALIGN(16) LaneRecB {
+  uint32_t w0;   // poly (24 bits) | flags << 24
+  uint32_t w1;   // parent poly (24 bits, kLaneNoParent = none) | entering link's offset in the parent's window << 24
+  uint32_t lnk;  // link window of the poly: start (27 bits) | count << 27
+  uint32_t w3;   // parent node (12 bits) | has-parent << 12 | heap position << 24
+};
+struct HBN_ALIGN(16) LaneLinkLo {
+  float mx, my, mz;
+  uint32_t nei;
+};
+struct HBN_ALIGN(16) LaneLinkHi {
+  uint32_t neiLinkStart, meta, neiRef, neiKey;
+};
+constexpr size_t kLaneRecBytes = static_cast<size_t>(kMaxNodes) * 32;
+HBN_HD size_t laneTabBytes(uint32_t numKeys) { return (static_cast<size_t>(numKeys) * 2 + 15) & ~static_cast<size_t>(15); }
+HBN_HD size_t laneScratchBytes(uint32_t numKeys) { return laneTabBytes(numKeys) + kLaneRecBytes; }
+
+enum { kLIdle = 0, kLSearch = 1, kLExtract = 2, kLDone = 3 };
+enum { kLEvNone = 0, kLEvFinished = 1, kLEvOverflow = 2, kLEvFault = 3, kLEvPoolExhausted = 4 /* internal */ };
+
+HBN_HD void laneLoadLink(const LinkRec* p, LaneLinkLo& lo, LaneLinkHi& hi) {
+#if defined(__CUDA_ARCH__)
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const uint4 b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+  lo.mx = a.x; lo.my = a.y; lo.mz = a.z; lo.nei = __float_as_uint(a.w);
+  hi.neiLinkStart = b.x; hi.meta = b.y; hi.neiRef = b.z; hi.neiKey = b.w;
+#else
+  memcpy(&lo, p, 16);
+  memcpy(&hi, reinterpret_cast<const char*>(p) + 16, 16);
+#endif
+}
+
+// HS: distance (in elements) between consecutive heap entries of this lane (32 on the device,
+// 1 in the host build); OC: open-list capacity.
+template <int HS, int OC>
+struct LaneSearch {
+  // memory of this lane
+  float* K;       // heap keys
+  uint16_t* S;    // heap nodes
+  uint16_t* tab;  // node table
+  char* rec;      // node records
+  uint32_t* cv;   // corridor ring of the current query (entering links, see ViaCorridor)
+  // query
+  uint32_t q, endG;
+  float ep[3];
+  // search state
+  int mode, size, nodeCount;
+  uint32_t gen;
+  uint32_t lastBest, lastBestG;
+  float lastBestCost;
+  bool outOfNodes;
+  uint32_t expanded, nLinks, nNeigh;
+  // result / extraction state
+  uint32_t status;
+  int xk;
+  uint32_t xcur;
+  LaneRecB xB;
+
+  HBN_HD LaneRecA* recA(uint32_t s) const { return reinterpret_cast<LaneRecA*>(rec + static_cast<size_t>(s) * 32); }
+  HBN_HD LaneRecB* recB(uint32_t s) const { return reinterpret_cast<LaneRecB*>(rec + static_cast<size_t>(s) * 32 + 16); }
+  HBN_HD void setHpos(uint32_t s, int i) const { reinterpret_cast<uint8_t*>(rec)[static_cast<size_t>(s) * 32 + 31] = static_cast<uint8_t>(i); }
+  HBN_HD void setFlags(uint32_t s, uint32_t f) const { reinterpret_cast<uint8_t*>(rec)[static_cast<size_t>(s) * 32 + 19] = static_cast<uint8_t>(f); }
+
+  // dtNodeQueue::bubbleUp, DNode.cpp:156-167
+  HBN_HD void heapUp(int i, const float key, const uint32_t slot) const {
+    while (i > 0) {
+      const int parent = (i - 1) >> 1;
+      const float pk = K[parent * HS];
+      if (!(pk > key)) break;
+      const uint16_t ps = S[parent * HS];
+      K[i * HS] = pk;
+      S[i * HS] = ps;
+      setHpos(ps, i);
+      i = parent;
+    }
+    K[i * HS] = key;
+    S[i * HS] = static_cast<uint16_t>(slot);
+    setHpos(slot, i);
+  }
+  // dtNodeQueue::pop's trickleDown (DNode.cpp:169-184) for a heap that has `n` entries left
+  HBN_HD void heapPopSift(const int n) const {
+    const float lk = K[n * HS];
+    const uint16_t ls = S[n * HS];
+    int i = 0, child = 1;
+    while (child < n) {
+      float c0 = K[child * HS];
+      const float c1 = K[(child + 1) * HS];  // child + 1 <= n: inside the array
+      if ((child + 1) < n && c0 > c1) {
+        c0 = c1;
+        child++;
+      }
+      const uint16_t cs = S[child * HS];
+      K[i * HS] = c0;
+      S[i * HS] = cs;
+      setHpos(cs, i);
+      i = child;
+      child = 2 * i + 1;
+    }
+    heapUp(i, lk, ls);
+  }
+
+  // DQ.cpp:1003-1021.  The caller has made sure gen < kLaneGenMax (table wiped otherwise).
+  HBN_HD void begin(const NavView& nav, uint32_t query, uint32_t startG, const float* sp, uint32_t endPoly,
+                    const float* endPos, uint32_t* corridorRing) {
+    q = query;
+    endG = endPoly;
+    ep[0] = endPos[0]; ep[1] = endPos[1]; ep[2] = endPos[2];
+    cv = corridorRing;
+    gen++;
+    const PolyRec* spoly = &nav.polys[startG];
+    const uint32_t slnk = spoly->linkStart | (static_cast<uint32_t>(spoly->linkCount) << 27);
+    const float stotal = vdist(sp, ep) * kHScale;
+    *recA(0) = LaneRecA{sp[0], sp[1], sp[2], 0.f};
+    *recB(0) = LaneRecB{startG | (kLaneFlagOpen << 24), kLaneNoParent, slnk, 0u};
+    tab[spoly->key0] = static_cast<uint16_t>(gen << kLaneSlotBits);
+    K[0] = stotal;
+    S[0] = 0;
+    size = 1;
+    nodeCount = 1;
+    lastBest = 0;
+    lastBestG = startG;
+    lastBestCost = stotal;
+    outOfNodes = false;
+    expanded = nLinks = nNeigh = 0;
+    status = 0;
+    xk = 0;
+    mode = kLSearch;
+  }
+
+  // DQ.cpp:1156-1164: status; the corridor is extracted when somebody will read it
+  HBN_HD int finishSearch(bool allCorridors) {
+    status = kDtSuccess;
+    if (lastBestG != endG) status |= kDtPartialResult;
+    if (outOfNodes) status |= kDtOutOfNodes;
+    xk = 0;
+    if (status == kDtSuccess || allCorridors) {
+      mode = kLExtract;
+      xcur = lastBest;
+      xB = *recB(lastBest);
+      return kLEvNone;
+    }
+    mode = kLIdle;
+    return kLEvFinished;
+  }
+
+  // One neighbour (DQ.cpp:1056-1153).  Returns false when the expansion must stop.
+  HBN_HD bool visit(const uint32_t bslot, const uint32_t bestG, const float* bpos, const float bcost,
+                    const uint32_t viaJ, const LaneLinkLo& lo, const LaneLinkHi& hi, uint32_t te, LaneRecA ra,
+                    uint32_t rw0, uint32_t rw3, const bool fastFail, bool* heapMoved, int* ev) {
+    const uint32_t nei = lo.nei;
+    if ((hi.meta & kLinkDupBit) != 0) {  // an earlier link of this poly may just have created the node
+      te = tab[hi.neiKey];
+      if ((te >> kLaneSlotBits) == gen) {
+        const uint32_t s2 = te & kLaneSlotMask;
+        ra = *recA(s2);
+        const LaneRecB b2 = *recB(s2);
+        rw0 = b2.w0;
+        rw3 = b2.w3;
+      }
+    }
+    const bool found = (te >> kLaneSlotBits) == gen;
+    uint32_t slot;
+    float npos[3];
+    if (!found) {  // dtNodePool::getNode, DNode.cpp:121-152: allocation against the pool limit
+      if (nodeCount >= kMaxNodes) {
+        outOfNodes = true;
+        if (fastFail) {  // PF.cpp:1450 has decided "no path" already
+          *ev = kLEvPoolExhausted;
+          return false;
+        }
+        return true;
+      }
+      slot = static_cast<uint32_t>(nodeCount++);
+      npos[0] = lo.mx; npos[1] = lo.my; npos[2] = lo.mz;
+    } else {
+      slot = te & kLaneSlotMask;
+      npos[0] = ra.px; npos[1] = ra.py; npos[2] = ra.pz;
+    }
+    // DQ.cpp:1088-1121
+    const float curCost = vdist(bpos, npos);
+    const float toEnd = vdist(npos, ep);
+    float cost, heuristic;
+    if (nei == endG) {
+      cost = bcost + curCost + toEnd;
+      heuristic = 0.f;
+    } else {
+      cost = bcost + curCost;
+      heuristic = toEnd * kHScale;
+    }
+    const float total = cost + heuristic;
+    const uint32_t flags = found ? (rw0 >> 24) : 0u;
+    // DQ.cpp:1124-1130; the node's total was formed as its cost + the same heuristic
+    if ((flags & (kLaneFlagOpen | kLaneFlagClosed)) != 0 && total >= ra.cost + heuristic) return true;
+    const bool wasOpen = (flags & kLaneFlagOpen) != 0;
+    if (!wasOpen && size >= OC) {  // this tier's open list is full: the query is re-run in the next tier
+      *ev = kLEvOverflow;
+      return false;
+    }
+    // dtNodeQueue::modify needs the entry's heap position: a heap operation of an earlier link
+    // of this expansion may have moved it after its record was loaded
+    uint32_t hpos = rw3 >> 24;
+    if (wasOpen && *heapMoved) hpos = reinterpret_cast<const uint8_t*>(rec)[static_cast<size_t>(slot) * 32 + 31];
+    *recA(slot) = LaneRecA{npos[0], npos[1], npos[2], cost};
+    *recB(slot) = LaneRecB{nei | (kLaneFlagOpen << 24), bestG | (viaJ << 24),
+                           hi.neiLinkStart | ((hi.meta >> kLinkNeiCountShift) << 27), bslot | (1u << 12)};
+    if (!found) tab[hi.neiKey] = static_cast<uint16_t>((gen << kLaneSlotBits) | slot);
+    if (wasOpen) {
+      heapUp(static_cast<int>(hpos), total, slot);
+    } else {
+      heapUp(size, total, slot);
+      size++;
+    }
+    *heapMoved = true;
+    if (heuristic < lastBestCost) {  // DQ.cpp:1154-1159
+      lastBestCost = heuristic;
+      lastBest = slot;
+      lastBestG = nei;
+    }
+    return true;
+  }
+
+  // One iteration of the state machine.  Returns an event; after kLEvFinished `status` and `xk`
+  // (corridor length, 0 = not extracted) are the query's result and the lane is idle.
+  HBN_HD int step(const NavView& nav, const bool fastFail, const bool allCorridors) {
+    if (mode == kLExtract) {  // getPathToNode, DQ.cpp:1167-1205, from the end backwards
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+      for (int h = 0; h < kLaneHops; ++h) {
+        const bool hasParent = ((xB.w3 >> 12) & 1u) != 0;
+        uint32_t via = kNoPoly;
+        if (hasParent) {
+          const uint32_t ps = xB.w3 & 0xfffu;
+          const LaneRecB pb = *recB(ps);
+          via = (pb.lnk & 0x07ffffffu) + ((xB.w1 >> 24) & 31u);
+          xB = pb;
+          xcur = ps;
+        }
+        cv[(kMaxPathPolys - 1 - xk) & (kMaxPathPolys - 1)] = via;
+        xk++;
+        if (!hasParent) {
+          if (xk > kMaxPathPolys) status |= kDtBufferTooSmall;
+          mode = kLIdle;
+          return kLEvFinished;
+        }
+        if (xk > kMaxNodes) {  // a parent cycle would be a bug
+          mode = kLIdle;
+          return kLEvFault;
+        }
+      }
+      return kLEvNone;
+    }
+    if (mode != kLSearch) return kLEvNone;
+    if (size == 0) return finishSearch(allCorridors);  // open list exhausted: partial result
+    // ---- pop (DQ.cpp:1027-1040) ----------------------------------------------------------
+    const uint32_t bslot = S[0];
+    const LaneRecA ba = *recA(bslot);
+    const LaneRecB bb = *recB(bslot);
+    size--;
+    heapPopSift(size);
+    setFlags(bslot, kLaneFlagClosed);
+    const uint32_t bestG = bb.w0 & 0x00ffffffu;
+    if (bestG == endG) {
+      lastBest = bslot;
+      lastBestG = bestG;
+      return finishSearch(allCorridors);
+    }
+    if (expanded >= kLaneMaxExpansions) {
+      mode = kLIdle;
+      return kLEvFault;
+    }
+    const uint32_t parentG = bb.w1 & 0x00ffffffu;
+    const uint32_t l0 = bb.lnk & 0x07ffffffu;
+    const int ln = static_cast<int>(bb.lnk >> 27);
+    expanded++;
+    nLinks += static_cast<uint32_t>(ln);
+    const float bpos[3] = {ba.px, ba.py, ba.pz};
+    const float bcost = ba.cost;
+    // ---- neighbours (DQ.cpp:1042-1153) ---------------------------------------------------
+    int ev = kLEvNone;
+    bool heapMoved = false;
+    for (int base = 0; base < ln && ev == kLEvNone; base += kLaneChunk) {
+      LaneLinkLo lo[kLaneChunk];
+      LaneLinkHi hi[kLaneChunk];
+      uint32_t te[kLaneChunk], rw0[kLaneChunk], rw3[kLaneChunk];
+      LaneRecA ra[kLaneChunk];
+      bool cand[kLaneChunk];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int k = 0; k < kLaneChunk; ++k) {
+        lo[k].nei = kNoPoly;
+        lo[k].mx = lo[k].my = lo[k].mz = 0.f;
+        hi[k] = LaneLinkHi{0u, 0u, 0u, 0u};
+        if (base + k < ln) laneLoadLink(&nav.links[l0 + base + k], lo[k], hi[k]);
+      }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int k = 0; k < kLaneChunk; ++k) {
+        if (lo[k].nei != kNoPoly) nNeigh++;
+        cand[k] = lo[k].nei != kNoPoly && lo[k].nei != parentG && (hi[k].meta & kLinkPassBit) != 0;
+        te[k] = cand[k] ? tab[hi[k].neiKey] : 0u;
+      }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int k = 0; k < kLaneChunk; ++k) {
+        ra[k] = LaneRecA{0.f, 0.f, 0.f, 0.f};
+        rw0[k] = rw3[k] = 0u;
+        if (cand[k] && (te[k] >> kLaneSlotBits) == gen) {
+          const uint32_t s2 = te[k] & kLaneSlotMask;
+          ra[k] = *recA(s2);
+          const LaneRecB b2 = *recB(s2);
+          rw0[k] = b2.w0;
+          rw3[k] = b2.w3;
+        }
+      }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int k = 0; k < kLaneChunk; ++k) {
+        if (cand[k] && ev == kLEvNone)
+          visit(bslot, bestG, bpos, bcost, static_cast<uint32_t>(base + k), lo[k], hi[k], te[k], ra[k], rw0[k],
+                rw3[k], fastFail, &heapMoved, &ev);
+      }
+    }
+    if (ev == kLEvPoolExhausted) return finishSearch(allCorridors);
+    if (ev == kLEvOverflow) mode = kLIdle;
+    return ev;
+  }
+};
+
+}  // namespace hbn

@@ -12,6 +12,7 @@
 #include "hbn_host.h"
 #include "hbn_kernels.cuh"
 #include "hbn_astar_group.cuh"
+#include "hbn_astar_lane.cuh"
 
 using namespace hbn;
 
@@ -37,6 +38,7 @@ constexpr int kFpWarps = 4;   // warps per block of the wall-distance kernels
 constexpr int kOpenS = 256;
 constexpr int kOpenL = 2048;
 constexpr int kFpWpb = 1;
+constexpr int kOpenLane = 192;  // open-list capacity of the lane-per-query search (6 B per entry and lane)
 constexpr int kSnapW = 8;     // lanes per point in k_snap
 constexpr int kRandW = 8;
 
@@ -77,8 +79,12 @@ struct hbn_navmesh {
   DevBuf sG, eG, e2G, sPt, ePt, epPt, lastPoly, lists, counters, wsL, wsFp, io, work, mgDist, mgBounds, mgOrder, mgEnd;
   // lock-step find_path (hbn_astar_group.cuh): class, search list, status, corridor rings, node records
   DevBuf fpCls, fpWork, fpStat, fpLen, fpCorr, wsFpG;
-  int fpG = 8;          // lanes per query of k_astar_g; 0 = one query per warp (k_findpath_w tiers only)
+  int fpG = 8;          // lanes per query of k_astar_g; 0 = one query per warp (k_findpath_w tiers only);
+                        // 1 = one query per LANE (k_astar_lane, hbn_astar_lane.cuh)
   int blocksFpG = 0;
+  // lane-per-query search: per-lane node table + records in HBM, allocated on first use
+  DevBuf wsLane, laneGen;
+  int blocksFpLane = 0;
   // pinned staging for the host-buffer entry points
   void* pinned = nullptr;
   size_t pinnedCap = 0;
@@ -102,6 +108,29 @@ int upload(hbn_navmesh* nm, const std::vector<T>& v, const T** out) {
   nm->deviceBytes += static_cast<int64_t>(bytes);
   if (!v.empty()) CK(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
   *out = static_cast<const T*>(d);
+  return HBN_OK;
+}
+
+// Per-lane node tables + records of k_astar_lane: blocksFpLane * 32 slots, allocated (and zeroed:
+// generation 0, empty tables) on first use.  Shrinks the grid when HBM is short.
+int laneScratch(hbn_navmesh* nm, cudaStream_t st, LaneScratch* out) {
+  const size_t per = laneScratchBytes(nm->view.numKeys);
+  if (!nm->wsLane.p) {
+    size_t freeB = 0, totalB = 0;
+    CK(cudaMemGetInfo(&freeB, &totalB));
+    const size_t maxBlocks = (freeB / 2) / (per * 32);
+    if (maxBlocks < 1) return fail(HBN_ERR_CUDA, "not enough device memory for the find_path node tables");
+    if (static_cast<size_t>(nm->blocksFpLane) > maxBlocks) nm->blocksFpLane = static_cast<int>(maxBlocks);
+    const size_t lanes = static_cast<size_t>(nm->blocksFpLane) * 32;
+    int rc;
+    if ((rc = nm->wsLane.ensure(lanes * per)) || (rc = nm->laneGen.ensure(lanes * 4))) return rc;
+    CK(cudaMemsetAsync(nm->wsLane.p, 0, lanes * per, st));
+    CK(cudaMemsetAsync(nm->laneGen.p, 0, lanes * 4, st));
+  }
+  out->base = static_cast<char*>(nm->wsLane.p);
+  out->gen = static_cast<uint32_t*>(nm->laneGen.p);
+  out->bytesPerLane = per;
+  out->tabBytes = laneTabBytes(nm->view.numKeys);
   return HBN_OK;
 }
 
@@ -179,9 +208,18 @@ int finishCreate(HostNavMesh& mesh, const int32_t* islands, int device, hbn_navm
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_findpath_w<kOpenL, kFpWpb>, 32 * kFpWpb, smFpL));
   nm->blocksFpL = std::max(1, occ) * nm->smCount;
   // lock-step search: group width from HBN_FP_G (4, 8, 16, 32; "warp" = the one-query-per-warp tiers)
-  if (const char* e = getenv("HBN_FP_G")) nm->fpG = (strcmp(e, "warp") == 0) ? 0 : atoi(e);
-  if (nm->fpG != 0 && nm->fpG != 4 && nm->fpG != 8 && nm->fpG != 16 && nm->fpG != 32) nm->fpG = 8;
-  if (nm->fpG) {
+  if (const char* e = getenv("HBN_FP_G"))
+    nm->fpG = (strcmp(e, "warp") == 0) ? 0 : (strcmp(e, "lane") == 0) ? 1 : atoi(e);
+  if (nm->fpG != 0 && nm->fpG != 1 && nm->fpG != 4 && nm->fpG != 8 && nm->fpG != 16 && nm->fpG != 32) nm->fpG = 8;
+  {
+    const size_t smLane = laneSharedBytes<kOpenLane>();
+    CK(cudaFuncSetAttribute(k_astar_lane<kOpenLane>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smLane)));
+    CK(cudaFuncSetAttribute(k_astar_lane<kOpenLane>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_astar_lane<kOpenLane>, 32, smLane));
+    nm->blocksFpLane = std::max(1, occ) * nm->smCount;
+    if (const char* e = getenv("HBN_FP_BLOCKS_PER_SM")) nm->blocksFpLane = std::max(1, std::min(occ, atoi(e))) * nm->smCount;
+  }
+  if (nm->fpG > 1) {
     const size_t smG = (32 / nm->fpG) * gGroupSharedBytes<kOpenS>();
     const void* fn = groupKernel(nm->fpG);
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smG)));
@@ -199,7 +237,7 @@ int finishCreate(HostNavMesh& mesh, const int32_t* islands, int device, hbn_navm
   if (rc == HBN_OK)
     rc = nm->wsFp.ensure(static_cast<size_t>(std::max(nm->blocksFpS, nm->blocksFpL)) * kFpWpb *
                          WarpWs<kOpenS>::globalBytes());
-  if (rc == HBN_OK && nm->fpG)
+  if (rc == HBN_OK && nm->fpG > 1)
     rc = nm->wsFpG.ensure(static_cast<size_t>(nm->blocksFpG) * (32 / nm->fpG) * gGroupGlobalBytes());
   if (rc == HBN_OK) rc = nm->counters.ensure(64);
   if (rc == HBN_OK) rc = nm->work.ensure(64);
@@ -308,7 +346,7 @@ void hbn_navmesh_destroy(hbn_navmesh_t nm) {
   for (DevBuf* b : {&nm->sG, &nm->eG, &nm->e2G, &nm->sPt, &nm->ePt, &nm->epPt, &nm->lastPoly,
                     &nm->lists, &nm->counters, &nm->wsL, &nm->wsFp, &nm->io, &nm->work, &nm->mgDist,
                     &nm->mgBounds, &nm->mgOrder, &nm->mgEnd, &nm->fpCls, &nm->fpWork, &nm->fpStat,
-                    &nm->fpLen, &nm->fpCorr, &nm->wsFpG})
+                    &nm->fpLen, &nm->fpCorr, &nm->wsFpG, &nm->wsLane, &nm->laneGen})
     b->release();
   if (nm->pinned) cudaFreeHost(nm->pinned);
   if (nm->faultHost) cudaFreeHost(nm->faultHost);
@@ -553,7 +591,14 @@ static int findPathLaunch(hbn_navmesh_t nm, const float* starts, const float* en
     ga.allCorridors = (out_corridor || out_ncorridor) ? 1 : 0;
     ga.workCtr = workCtr;
     ga.fault = nm->faultDev;
-    {
+    if (nm->fpG == 1) {
+      LaneScratch sc{};
+      if ((rc = laneScratch(nm, st, &sc))) return rc;
+      const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(nm->blocksFpLane, (cn + 31) / 32));
+      k_astar_lane<kOpenLane><<<blocks, 32, laneSharedBytes<kOpenLane>(), st>>>(nm->view, ga, sc);
+      nm->launches++;
+      CK(cudaGetLastError());
+    } else {
       const int qpw = 32 / nm->fpG;
       const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(nm->blocksFpG, (cn + qpw - 1) / qpw));
       const size_t sm = qpw * gGroupSharedBytes<kOpenS>();

@@ -670,7 +670,18 @@ void HostNavMesh::flatten(FlatNav& out) const {
       pr.linkCount = static_cast<uint8_t>(std::min<uint32_t>(cnt, 255u));
     }
   }
-  // pass 2: neighbour windows + filter bits (needs every poly's link window)
+  // pass 2: neighbour windows + filter bits (needs every poly's link window), and the dense
+  // enumeration of A* node keys (poly, crossSide): crossSide 0 of every poly, plus the sides
+  // through which tile-border links enter it
+  std::vector<uint8_t> sideMask(out.polys.size(), 1);
+  for (const LinkRec& lr : out.links)
+    if (lr.nei != kNoPoly) sideMask[lr.nei] |= static_cast<uint8_t>(1u << ((lr.meta >> kLinkStateShift) & 3u));
+  uint32_t nKeys = 0;
+  for (size_t g = 0; g < out.polys.size(); ++g) {
+    out.polys[g].key0 = nKeys;
+    nKeys += static_cast<uint32_t>(__builtin_popcount(sideMask[g]));
+  }
+  out.numKeys = nKeys;
   for (LinkRec& lr : out.links) {
     if (lr.nei == kNoPoly) continue;
     const PolyRec& q = out.polys[lr.nei];
@@ -678,6 +689,8 @@ void HostNavMesh::flatten(FlatNav& out) const {
     lr.meta |= static_cast<uint32_t>(q.linkCount) << kLinkNeiCountShift;
     if ((q.flags & kFlagWalk) != 0) lr.meta |= kLinkPassBit;
     if ((q.areaType >> 6) == 1) lr.meta |= kLinkOffmeshBit;
+    const uint32_t st = (lr.meta >> kLinkStateShift) & 3u;
+    lr.neiKey = q.key0 + static_cast<uint32_t>(__builtin_popcount(sideMask[lr.nei] & ((1u << st) - 1u)));
   }
   // tile grid in bucket-chain order (dtNavMesh::getTilesAt)
   bool any = false;
@@ -770,6 +783,7 @@ NavView FlatNav::view() const {
   v.numPolys = static_cast<uint32_t>(polys.size());
   v.numTiles = static_cast<uint32_t>(tiles.size());
   v.numLinks = static_cast<uint32_t>(links.size());
+  v.numKeys = numKeys;
   v.polyBits = polyBits; v.tileBits = tileBits; v.saltBits = saltBits;
   v.numIslands = static_cast<int32_t>(islandRadius.size());
   return v;

@@ -51,7 +51,8 @@ struct HBN_ALIGN(16) PolyRec {
   int32_t island;        // 108: IslandSystem id (PathFinder.cpp:167-207)
   uint32_t tile;         // 112: index into TileRec[]
   float area2d;          // 116: sum of dtTriArea2D fan (DetourNavMeshQuery.cpp:270-277)
-  uint32_t pad1[2];      // 120
+  uint32_t key0;         // 120: node-key index of (this poly, crossSide 0), see LinkRec::neiKey
+  uint32_t pad1;         // 124
 };
 static_assert(sizeof(PolyRec) == 128, "PolyRec must be one cache line");
 
@@ -70,7 +71,10 @@ struct HBN_ALIGN(16) LinkRec {
   uint32_t neiLinkStart;  // neighbour's link window start
   uint32_t meta;
   uint32_t neiRef;        // dtLink::ref
-  uint32_t pad;
+  // Index of the A* node key (neighbour poly, crossSide) in the dense enumeration of all keys
+  // that can occur (DQ.cpp:1067-1073: crossSide = side >> 1 for tile-border links): a direct-
+  // mapped per-query node table replaces dtNodePool's hash (hbn_astar_lane.h).
+  uint32_t neiKey;
 };
 static_assert(sizeof(LinkRec) == 32, "LinkRec");
 
@@ -137,7 +141,7 @@ struct NavView {
   int32_t gridMinX, gridMinY, gridW, gridH;
   float orig[3];
   float tileWidth, tileHeight;
-  uint32_t numPolys, numTiles, numLinks, pad0;
+  uint32_t numPolys, numTiles, numLinks, numKeys;
   uint32_t polyBits, tileBits, saltBits;
   int32_t numIslands;
 };

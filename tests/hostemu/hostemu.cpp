@@ -12,6 +12,7 @@
 
 #include "hbn_host.h"
 #include "hbn_query.h"
+#include "hbn_astar_lane.h"
 
 using namespace hbn;
 
@@ -119,6 +120,57 @@ void emu_find_path(void* h, const float* starts, const float* ends, long n, int 
       o[1] = (s.g != kNoPoly && t.g != kNoPoly) ? e->nav.polys[t.g].ref : 0;
       o[2] = r.astarStatus; o[3] = r.straightStatus; o[4] = r.ncorridor; o[5] = r.npts;
       o[6] = r.nodesUsed; o[7] = r.flags;
+    }
+  }
+}
+
+// The lane-per-query search (hbn_astar_lane.h, the state machine k_astar_lane runs in every
+// lane) on ONE lane slot reused by all n queries, so table generations wrap and get wiped.
+// out_info [n,4]: {findPath status (0 = no search), corridor length, nodes allocated, event};
+// out_corridor [n,256] poly refs of the (possibly truncated) corridor.
+void emu_find_path_lane(void* h, const float* starts, const float* ends, long n, int fastFail, int allCorridors,
+                        unsigned* out_corridor, unsigned* out_info) {
+  Emu* e = static_cast<Emu*>(h);
+  HostGroup grp;
+  uint32_t q[2];
+  constexpr int OC = 192;
+  const NavView& nav = e->nav;
+  std::vector<char> scratch(laneScratchBytes(nav.numKeys) + 64, 0);
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(scratch.data()) + 15) & ~uintptr_t(15));
+  std::vector<float> K(OC);
+  std::vector<uint16_t> S(OC);
+  std::vector<uint32_t> ring(kMaxPathPolys);
+  LaneSearch<1, OC> s{};
+  s.K = K.data(); s.S = S.data();
+  s.tab = reinterpret_cast<uint16_t*>(base);
+  s.rec = base + laneTabBytes(nav.numKeys);
+  s.gen = 0;
+  s.mode = kLIdle;
+  for (long i = 0; i < n; ++i) {
+    unsigned* o = out_info + i * 4;
+    o[0] = o[1] = o[2] = o[3] = 0;
+    const Nearest a = findNearestPoly(nav, grp, starts + 3 * i, kExt, -1, q);
+    const Nearest b = findNearestPoly(nav, grp, ends + 3 * i, kExt, -1, q);
+    if (a.g == kNoPoly || b.g == kNoPoly || vfuzzyEq(a.pt, b.pt)) continue;
+    const int32_t si = nav.polys[a.g].island, ei = nav.polys[b.g].island;
+    if (si < 0 || si != ei || a.g == b.g || !vfinite(a.pt) || !vfinite(b.pt)) continue;  // k_fp_classify
+    if (s.gen >= kLaneGenMax) {
+      memset(s.tab, 0, laneTabBytes(nav.numKeys));
+      s.gen = 0;
+    }
+    s.begin(nav, static_cast<uint32_t>(i), a.g, a.pt, b.g, b.pt, ring.data());
+    int ev = kLEvNone;
+    while (ev == kLEvNone) ev = s.step(nav, fastFail != 0, allCorridors != 0);
+    o[3] = static_cast<unsigned>(ev);
+    if (ev != kLEvFinished) continue;
+    o[0] = s.status;
+    o[1] = static_cast<unsigned>(s.xk);
+    o[2] = static_cast<unsigned>(s.nodeCount);
+    const int len = s.xk < kMaxPathPolys ? s.xk : kMaxPathPolys;
+    const uint32_t first = static_cast<uint32_t>((kMaxPathPolys - s.xk) & (kMaxPathPolys - 1));
+    for (int k = 0; k < len; ++k) {
+      const uint32_t via = ring[(first + k) & (kMaxPathPolys - 1)];
+      out_corridor[i * kMaxPathPolys + k] = nav.polys[k == 0 ? a.g : nav.links[via].nei].ref;
     }
   }
 }

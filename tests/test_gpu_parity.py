@@ -334,7 +334,7 @@ def test_full_size_properties():
     assert beq(d[:m], want).all()
 
 
-@pytest.mark.parametrize("width", ["4", "8", "16", "32", "warp"])
+@pytest.mark.parametrize("width", ["lane", "4", "8", "16", "32", "warp"])
 def test_find_path_search_variants(width, monkeypatch):
     """Every mapping of the search onto the machine (HBN_FP_G lanes per query in lock step, or the
     one-query-per-warp tiers) must give the reference's corridors, status words and distances."""

@@ -3,7 +3,10 @@ usage: python tools/sweep_fp.py [queries]"""
 import json, os, subprocess, sys
 n = sys.argv[1] if len(sys.argv) > 1 else "400000"
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for g, bps in (("warp", None), ("8", None), ("16", None), ("32", None), ("4", None), ("8", "4"), ("8", "5")):
+variants = (("lane", None), ("lane", "4"), ("lane", "2"), ("16", None), ("warp", None))
+if os.environ.get("SWEEP_ALL"):
+    variants += (("8", None), ("32", None), ("4", None))
+for g, bps in variants:
     env = dict(os.environ, HBN_FP_G=g)
     if bps:
         env["HBN_FP_BLOCKS_PER_SM"] = bps

@@ -1,5 +1,4 @@
 set -x
-HBN_FP_G=8 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_astar_g -s 3 -c 1 -o gpurun_out/r1f_astar_g8 -f python bench.py --steps 1 --warmup 3 --queries 100000 --no-cpu-baseline > gpurun_out/r1f_ncu_g8.log 2>&1
-tail -2 gpurun_out/r1f_ncu_g8.log | cut -c1-300
-HBN_FP_G=32 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_astar_g -s 3 -c 1 -o gpurun_out/r1f_astar_g32 -f python bench.py --steps 1 --warmup 3 --queries 100000 --no-cpu-baseline > gpurun_out/r1f_ncu_g32.log 2>&1
-tail -2 gpurun_out/r1f_ncu_g32.log | cut -c1-300
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "search_variants and lane" 2>&1 | tail -15 > gpurun_out/r1g_pytest_lane.log; cat gpurun_out/r1g_pytest_lane.log
+HBN_FP_G=lane timeout 600 compute-sanitizer --tool memcheck python tools/small_fp.py > gpurun_out/r1g_memcheck.log 2>&1; tail -8 gpurun_out/r1g_memcheck.log
+timeout 900 python tools/sweep_fp.py 1000000 > gpurun_out/r1g_sweep.log 2>&1; cat gpurun_out/r1g_sweep.log
