@@ -2,8 +2,8 @@
 // machine is hbn_astar_lane.h).  Persistent one-warp blocks pull queries from the search list
 // of k_fp_classify with a warp-aggregated atomic; a lane whose query ends takes the next one
 // in the same iteration, so the lanes of a warp stay busy until the list is empty.
-// Outputs are the ones of k_astar_g: status word, corridor ring, overflow list; the funnel
-// runs in k_fp_funnel.
+// Outputs are the ones of k_astar_g: status word and corridor ring (the heap continues in HBM,
+// so no query overflows to another tier); the funnel runs in k_fp_funnel.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -12,28 +12,33 @@
 
 namespace hbn {
 
-struct LaneScratch {
-  char* base;           // one laneScratchBytes(numKeys) slot per lane of the grid
+struct LaneScratch {  // one slot per lane of the grid in each region
+  char* tab;            // node tables, tabBytes each (zeroed at allocation, wiped every 31 queries)
+  char* rec;            // node records, kLaneRecBytes each
+  char* heap;           // heap entries beyond the shared levels, kLaneHeapBytes each
   uint32_t* gen;        // table generation of every lane slot (persists across launches)
-  size_t bytesPerLane;
   size_t tabBytes;
 };
 
-template <int OC>
-__host__ __device__ constexpr size_t laneSharedBytes() { return static_cast<size_t>(OC) * 32 * 6; }
+template <int TS, int LOGC>
+__host__ __device__ constexpr size_t laneSharedBytes() { return static_cast<size_t>(TS) * 32 * 6 + (static_cast<size_t>(32) << LOGC) * 2; }
 
-template <int OC>
-__global__ void __launch_bounds__(32) k_astar_lane(NavView nav, AStarGArgs a, LaneScratch sc) {
+// TS: heap entries per lane in shared memory; LOGC: log2 of the position cache entries per lane;
+// MINB: resident one-warp blocks per SM the register allocation must allow.
+template <int TS, int LOGC, int MINB>
+__global__ void __launch_bounds__(32, MINB) k_astar_lane(NavView nav, AStarGArgs a, LaneScratch sc) {
   constexpr uint32_t FULL = 0xffffffffu;
   extern __shared__ __align__(16) char smem[];
   const int lane = threadIdx.x;
   const uint32_t ltMask = (1u << lane) - 1u;
   const size_t slotId = static_cast<size_t>(blockIdx.x) * 32 + lane;
-  LaneSearch<32, OC> s;
+  LaneSearch<32, TS, LOGC> s;
   s.K = reinterpret_cast<float*>(smem) + lane;
-  s.S = reinterpret_cast<uint16_t*>(smem + static_cast<size_t>(OC) * 32 * 4) + lane;
-  s.tab = reinterpret_cast<uint16_t*>(sc.base + slotId * sc.bytesPerLane);
-  s.rec = sc.base + slotId * sc.bytesPerLane + sc.tabBytes;
+  s.S = reinterpret_cast<uint16_t*>(smem + static_cast<size_t>(TS) * 32 * 4) + lane;
+  s.PC = reinterpret_cast<uint16_t*>(smem + static_cast<size_t>(TS) * 32 * 6) + lane;
+  s.G = reinterpret_cast<LaneHeapEnt*>(sc.heap + slotId * kLaneHeapBytes);
+  s.tab = reinterpret_cast<uint16_t*>(sc.tab + slotId * sc.tabBytes);
+  s.rec = sc.rec + slotId * kLaneRecBytes;
   s.cv = nullptr;
   s.gen = sc.gen[slotId];
   s.mode = kLIdle;
@@ -82,19 +87,14 @@ __global__ void __launch_bounds__(32) k_astar_lane(NavView nav, AStarGArgs a, La
       if (ev == kLEvFault) {
         atomicAdd(a.fault, 1u);
         a.fault[1] = q;
-        a.fault[2] = 5u | (OC << 8);
+        a.fault[2] = 5u | (TS << 8);
         a.astat[q] = kDtFailure;
-        a.fullLen[q] = 0;
-      } else if (ev == kLEvOverflow) {
-        const uint32_t o = atomicAdd(a.overflowCount, 1u);
-        a.overflow[o] = q;
-        a.astat[q] = kSearchOverflow;
         a.fullLen[q] = 0;
       } else {
         a.astat[q] = s.status;
         a.fullLen[q] = s.xk;
       }
-      if (a.workCtr && ev != kLEvOverflow) {
+      if (a.workCtr) {
         atomicAdd(a.workCtr + 0, static_cast<unsigned long long>(s.expanded));
         atomicAdd(a.workCtr + 1, static_cast<unsigned long long>(s.nLinks));
         atomicAdd(a.workCtr + 2, static_cast<unsigned long long>(s.nNeigh));

@@ -6,25 +6,36 @@
 // hbn_astar_group.cuh) leaves most issue slots on warp-uniform bookkeeping: ~500 warp
 // instructions per poly expansion, and shared memory caps an SM at ~25 queries in flight.
 // Here a query belongs to ONE lane and a warp advances 32 queries in lock step (k_astar_lane,
-// hbn_astar_lane.cuh): one warp instruction now serves 32 expansions, and the per-query state
-// that does not fit on chip lives in HBM, sized for 180 GB:
+// hbn_astar_lane.cuh): one warp instruction serves 32 expansions, and the per-query state that
+// does not fit on chip lives in HBM, sized for 180 GB:
 //
-//   shared  : only the binary heap, 6 B per entry {f32 total, u16 node}, interleaved over the
-//             lanes of the warp (entry i of lane l at word i*32 + l: never a bank conflict);
-//   global  : per lane (a) a DIRECT-MAPPED node table, one u16 per node key (poly, crossSide)
-//             -- the keys are enumerated by the flattener (LinkRec::neiKey, PolyRec::key0) --
-//             holding generation << 11 | node, so a lookup is one load, never a probe loop,
-//             and a new query just bumps the generation (the table is wiped every 31 queries);
-//             (b) 2048 node records of 32 B in ALLOCATION order (dtNodePool's index order):
-//             {pos, cost | poly+flags, parent poly + entering link, link window, parent node +
-//             heap position}.
-//   The heap position of every open node is kept in its record (one byte store per heap
-//   move), so dtNodeQueue::modify (DNode.h:132-142) needs no scan.  A node's total is not
-//   stored: it is cost + heuristic(pos), recomputed with the same operations.
+//   shared  : the top TS entries (6 levels at TS = 63) of the binary heap, 6 B per entry
+//             {f32 total, u16 node}, interleaved over the lanes of the warp (entry i of lane l
+//             at word i*32 + l: never a bank conflict); and a direct-mapped cache
+//             node -> heap position (2^LOGC u16 entries, tag | position), written with every
+//             heap move, so that dtNodeQueue::modify (DNode.h:132-142) finds its entry without
+//             the reference's linear scan.  Positions are NOT kept in HBM: a heap move would
+//             cost a scattered 2 B store each (9 per expansion, measured: 3/4 of all L2
+//             requests of the first version).  A cache hit is verified against the heap entry;
+//             a miss (8 % of the modifies at 256 entries, modifies being 0.06 per expansion on
+//             the C4 workload) falls back to the scan;
+//   global  : per lane
+//             (a) the rest of the heap, 8 B entries; the two children of an entry share one
+//                 aligned 16 B load;
+//             (b) a DIRECT-MAPPED node table, one u16 per node key (poly, crossSide) -- the keys
+//                 are enumerated by the flattener (LinkRec::neiKey, PolyRec::key0) -- holding
+//                 generation << 11 | node: a lookup is one load, never a probe loop, and a new
+//                 query just bumps the generation (the table is wiped every 31 queries);
+//             (c) 2048 node records of 32 B in ALLOCATION order (dtNodePool's index order):
+//                 {pos, cost | poly, parent poly + entering link, link window, parent node}.
+//                 A node is open or closed; "closed" is the sign bit of the stored cost (costs
+//                 are >= +0), so the first 16 B answer everything a revisit asks.
+//   A node's total is not stored: it is cost + heuristic(pos), recomputed with the same
+//   operations.
 //
 // One step() = one iteration of the reference's while loop: pop, then the popped poly's links
 // in chunks of kLaneChunk: all link records, then all table entries, then all found records
-// are loaded before the serial part, so a lane has up to 6 independent loads in flight per
+// are loaded before the serial part, so a lane has several independent loads in flight per
 // stage instead of a chain of 3 dependent loads per neighbour.
 // Corridor extraction (getPathToNode, DQ.cpp:1167-1205) is a pointer chase; it runs as a mode
 // of the same state machine, a few hops per step, so it never stalls the other 31 queries.
@@ -40,20 +51,39 @@ constexpr uint32_t kLaneSlotBits = 11;  // node index < 2048
 constexpr uint32_t kLaneSlotMask = (1u << kLaneSlotBits) - 1u;
 constexpr uint32_t kLaneGenMax = 31;    // generations 1..31, then the table is wiped
 constexpr uint32_t kLaneNoParent = 0x00ffffffu;
-constexpr int kLaneChunk = 6;           // links handled per load stage
+constexpr int kLaneChunk = 4;           // links handled per load stage
 constexpr int kLaneHops = 2;            // corridor hops per step
-constexpr uint32_t kLaneFlagOpen = 1u, kLaneFlagClosed = 2u;
+constexpr uint32_t kLaneClosedBit = 0x80000000u;  // sign bit of LaneRecA::cost
 constexpr uint32_t kLaneMaxExpansions = 1u << 18;  // >> any legal search (2048 nodes, re-opens)
 static_assert(kMaxNodes <= (1 << kLaneSlotBits), "node index must fit the table entry");
 
 struct HBN_ALIGN(16) LaneRecA {
-  float px, py, pz, cost;
+  float px, py, pz, cost;  // cost: sign bit set = closed
 };
+HBN_HD float laneSetClosed(float c) {
+  uint32_t u;
+  memcpy(&u, &c, 4);
+  u |= kLaneClosedBit;
+  memcpy(&c, &u, 4);
+  return c;
+}
+HBN_HD bool laneIsClosed(float c) {
+  uint32_t u;
+  memcpy(&u, &c, 4);
+  return (u & kLaneClosedBit) != 0;
+}
+HBN_HD float laneCost(float c) {
+  uint32_t u;
+  memcpy(&u, &c, 4);
+  u &= ~kLaneClosedBit;
+  memcpy(&c, &u, 4);
+  return c;
+}
 struct HBN_ALIGN(16) LaneRecB {
-  uint32_t w0;   // poly (24 bits) | flags << 24
-  uint32_t w1;   // parent poly (24 bits, kLaneNoParent = none) | entering link's offset in the parent's window << 24
-  uint32_t lnk;  // link window of the poly: start (27 bits) | count << 27
-  uint32_t w3;   // parent node (12 bits) | has-parent << 12 | heap position << 24
+  uint32_t poly;  // global poly index
+  uint32_t w1;    // parent poly (24 bits, kLaneNoParent = none) | entering link's offset in the parent's window << 24
+  uint32_t lnk;   // link window of the poly: start (27 bits) | count << 27
+  uint32_t w3;    // parent node (12 bits) | has-parent << 12
 };
 struct HBN_ALIGN(16) LaneLinkLo {
   float mx, my, mz;
@@ -62,12 +92,24 @@ struct HBN_ALIGN(16) LaneLinkLo {
 struct HBN_ALIGN(16) LaneLinkHi {
   uint32_t neiLinkStart, meta, neiRef, neiKey;
 };
+struct HBN_ALIGN(8) LaneHeapEnt {
+  float key;
+  uint32_t slot;
+};
+struct HBN_ALIGN(16) LaneHeapPair {
+  LaneHeapEnt a, b;
+};
+
+// per-lane global scratch, one region per kind
 constexpr size_t kLaneRecBytes = static_cast<size_t>(kMaxNodes) * 32;
+constexpr size_t kLaneHeapBytes = static_cast<size_t>(kMaxNodes + 2) * sizeof(LaneHeapEnt);
 HBN_HD size_t laneTabBytes(uint32_t numKeys) { return (static_cast<size_t>(numKeys) * 2 + 15) & ~static_cast<size_t>(15); }
-HBN_HD size_t laneScratchBytes(uint32_t numKeys) { return laneTabBytes(numKeys) + kLaneRecBytes; }
+HBN_HD size_t laneScratchBytes(uint32_t numKeys) {
+  return laneTabBytes(numKeys) + kLaneRecBytes + kLaneHeapBytes;
+}
 
 enum { kLIdle = 0, kLSearch = 1, kLExtract = 2, kLDone = 3 };
-enum { kLEvNone = 0, kLEvFinished = 1, kLEvOverflow = 2, kLEvFault = 3, kLEvPoolExhausted = 4 /* internal */ };
+enum { kLEvNone = 0, kLEvFinished = 1, kLEvFault = 3, kLEvPoolExhausted = 4 /* internal */ };
 
 HBN_HD void laneLoadLink(const LinkRec* p, LaneLinkLo& lo, LaneLinkHi& hi) {
 #if defined(__CUDA_ARCH__)
@@ -81,16 +123,22 @@ HBN_HD void laneLoadLink(const LinkRec* p, LaneLinkLo& lo, LaneLinkHi& hi) {
 #endif
 }
 
-// HS: distance (in elements) between consecutive heap entries of this lane (32 on the device,
-// 1 in the host build); OC: open-list capacity.
-template <int HS, int OC>
+// HS: distance (in elements) between consecutive shared heap entries of this lane (32 on the
+// device, 1 in the host build); TS: heap entries kept in shared memory (odd, so that the
+// children 2i+1, 2i+2 of an entry are both on the same side and pair-aligned in global);
+// LOGC: log2 of the position cache's entry count.
+template <int HS, int TS, int LOGC>
 struct LaneSearch {
+  static_assert((TS & 1) == 1, "TS must be odd");
+  static_assert(LOGC >= 5 && LOGC <= 11, "position cache: tag | 11-bit position must fit 16 bits");
   // memory of this lane
-  float* K;       // heap keys
-  uint16_t* S;    // heap nodes
-  uint16_t* tab;  // node table
-  char* rec;      // node records
-  uint32_t* cv;   // corridor ring of the current query (entering links, see ViaCorridor)
+  float* K;        // shared: heap keys
+  uint16_t* S;     // shared: heap nodes
+  uint16_t* PC;    // shared: position cache, entry (node & mask): node >> LOGC << 11 | position
+  LaneHeapEnt* G;  // global: heap entries TS.. (entry j at G[j - TS])
+  uint16_t* tab;   // node table
+  char* rec;       // node records
+  uint32_t* cv;    // corridor ring of the current query (entering links, see ViaCorridor)
   // query
   uint32_t q, endG;
   float ep[3];
@@ -109,41 +157,83 @@ struct LaneSearch {
 
   HBN_HD LaneRecA* recA(uint32_t s) const { return reinterpret_cast<LaneRecA*>(rec + static_cast<size_t>(s) * 32); }
   HBN_HD LaneRecB* recB(uint32_t s) const { return reinterpret_cast<LaneRecB*>(rec + static_cast<size_t>(s) * 32 + 16); }
-  HBN_HD void setHpos(uint32_t s, int i) const { reinterpret_cast<uint8_t*>(rec)[static_cast<size_t>(s) * 32 + 31] = static_cast<uint8_t>(i); }
-  HBN_HD void setFlags(uint32_t s, uint32_t f) const { reinterpret_cast<uint8_t*>(rec)[static_cast<size_t>(s) * 32 + 19] = static_cast<uint8_t>(f); }
+
+  HBN_HD void hget(int i, float& k, uint32_t& s) const {
+    if (i < TS) {
+      k = K[i * HS];
+      s = S[i * HS];
+    } else {
+      const LaneHeapEnt e = G[i - TS];
+      k = e.key;
+      s = e.slot;
+    }
+  }
+  HBN_HD void hset(int i, float k, uint32_t s) const {
+    if (i < TS) {
+      K[i * HS] = k;
+      S[i * HS] = static_cast<uint16_t>(s);
+    } else {
+      G[i - TS] = LaneHeapEnt{k, s};
+    }
+    PC[(s & ((1u << LOGC) - 1u)) * HS] = static_cast<uint16_t>(((s >> LOGC) << 11) | static_cast<uint32_t>(i));
+  }
+  // heap position of an open node (dtNodeQueue::modify's search, DNode.h:134-141)
+  HBN_HD int findPos(const uint32_t s) const {
+    const uint32_t e = PC[(s & ((1u << LOGC) - 1u)) * HS];
+    const int p = static_cast<int>(e & 2047u);
+    if ((e >> 11) == (s >> LOGC) && p < size) {
+      float k;
+      uint32_t hs;
+      hget(p, k, hs);
+      if (hs == s) return p;
+    }
+    for (int i = 0; i < size; ++i) {
+      float k;
+      uint32_t hs;
+      hget(i, k, hs);
+      if (hs == s) return i;
+    }
+    return -1;
+  }
 
   // dtNodeQueue::bubbleUp, DNode.cpp:156-167
   HBN_HD void heapUp(int i, const float key, const uint32_t slot) const {
     while (i > 0) {
       const int parent = (i - 1) >> 1;
-      const float pk = K[parent * HS];
+      float pk;
+      uint32_t ps;
+      hget(parent, pk, ps);
       if (!(pk > key)) break;
-      const uint16_t ps = S[parent * HS];
-      K[i * HS] = pk;
-      S[i * HS] = ps;
-      setHpos(ps, i);
+      hset(i, pk, ps);
       i = parent;
     }
-    K[i * HS] = key;
-    S[i * HS] = static_cast<uint16_t>(slot);
-    setHpos(slot, i);
+    hset(i, key, slot);
   }
   // dtNodeQueue::pop's trickleDown (DNode.cpp:169-184) for a heap that has `n` entries left
   HBN_HD void heapPopSift(const int n) const {
-    const float lk = K[n * HS];
-    const uint16_t ls = S[n * HS];
+    float lk;
+    uint32_t ls;
+    hget(n, lk, ls);
     int i = 0, child = 1;
-    while (child < n) {
-      float c0 = K[child * HS];
-      const float c1 = K[(child + 1) * HS];  // child + 1 <= n: inside the array
+    while (child < n) {  // child is odd; child + 1 <= n is inside the arrays
+      float c0, c1;
+      uint32_t s0, s1;
+      if (child < TS) {
+        c0 = K[child * HS];
+        c1 = K[(child + 1) * HS];
+        s0 = S[child * HS];
+        s1 = S[(child + 1) * HS];
+      } else {
+        const LaneHeapPair p = *reinterpret_cast<const LaneHeapPair*>(&G[child - TS]);
+        c0 = p.a.key; s0 = p.a.slot;
+        c1 = p.b.key; s1 = p.b.slot;
+      }
       if ((child + 1) < n && c0 > c1) {
         c0 = c1;
+        s0 = s1;
         child++;
       }
-      const uint16_t cs = S[child * HS];
-      K[i * HS] = c0;
-      S[i * HS] = cs;
-      setHpos(cs, i);
+      hset(i, c0, s0);
       i = child;
       child = 2 * i + 1;
     }
@@ -162,10 +252,9 @@ struct LaneSearch {
     const uint32_t slnk = spoly->linkStart | (static_cast<uint32_t>(spoly->linkCount) << 27);
     const float stotal = vdist(sp, ep) * kHScale;
     *recA(0) = LaneRecA{sp[0], sp[1], sp[2], 0.f};
-    *recB(0) = LaneRecB{startG | (kLaneFlagOpen << 24), kLaneNoParent, slnk, 0u};
+    *recB(0) = LaneRecB{startG, kLaneNoParent, slnk, 0u};
     tab[spoly->key0] = static_cast<uint16_t>(gen << kLaneSlotBits);
-    K[0] = stotal;
-    S[0] = 0;
+    hset(0, stotal, 0u);
     size = 1;
     nodeCount = 1;
     lastBest = 0;
@@ -194,20 +283,15 @@ struct LaneSearch {
     return kLEvFinished;
   }
 
-  // One neighbour (DQ.cpp:1056-1153).  Returns false when the expansion must stop.
-  HBN_HD bool visit(const uint32_t bslot, const uint32_t bestG, const float* bpos, const float bcost,
+  // One neighbour (DQ.cpp:1056-1153).  `te` and `ra` were loaded before the serial part of this
+  // chunk.
+  HBN_HD void visit(const uint32_t bslot, const uint32_t bestG, const float* bpos, const float bcost,
                     const uint32_t viaJ, const LaneLinkLo& lo, const LaneLinkHi& hi, uint32_t te, LaneRecA ra,
-                    uint32_t rw0, uint32_t rw3, const bool fastFail, bool* heapMoved, int* ev) {
+                    const bool fastFail, int* ev) {
     const uint32_t nei = lo.nei;
     if ((hi.meta & kLinkDupBit) != 0) {  // an earlier link of this poly may just have created the node
       te = tab[hi.neiKey];
-      if ((te >> kLaneSlotBits) == gen) {
-        const uint32_t s2 = te & kLaneSlotMask;
-        ra = *recA(s2);
-        const LaneRecB b2 = *recB(s2);
-        rw0 = b2.w0;
-        rw3 = b2.w3;
-      }
+      if ((te >> kLaneSlotBits) == gen) ra = *recA(te & kLaneSlotMask);
     }
     const bool found = (te >> kLaneSlotBits) == gen;
     uint32_t slot;
@@ -215,11 +299,8 @@ struct LaneSearch {
     if (!found) {  // dtNodePool::getNode, DNode.cpp:121-152: allocation against the pool limit
       if (nodeCount >= kMaxNodes) {
         outOfNodes = true;
-        if (fastFail) {  // PF.cpp:1450 has decided "no path" already
-          *ev = kLEvPoolExhausted;
-          return false;
-        }
-        return true;
+        if (fastFail) *ev = kLEvPoolExhausted;  // PF.cpp:1450 has decided "no path" already
+        return;
       }
       slot = static_cast<uint32_t>(nodeCount++);
       npos[0] = lo.mx; npos[1] = lo.my; npos[2] = lo.mz;
@@ -239,35 +320,30 @@ struct LaneSearch {
       heuristic = toEnd * kHScale;
     }
     const float total = cost + heuristic;
-    const uint32_t flags = found ? (rw0 >> 24) : 0u;
-    // DQ.cpp:1124-1130; the node's total was formed as its cost + the same heuristic
-    if ((flags & (kLaneFlagOpen | kLaneFlagClosed)) != 0 && total >= ra.cost + heuristic) return true;
-    const bool wasOpen = (flags & kLaneFlagOpen) != 0;
-    if (!wasOpen && size >= OC) {  // this tier's open list is full: the query is re-run in the next tier
-      *ev = kLEvOverflow;
-      return false;
-    }
-    // dtNodeQueue::modify needs the entry's heap position: a heap operation of an earlier link
-    // of this expansion may have moved it after its record was loaded
-    uint32_t hpos = rw3 >> 24;
-    if (wasOpen && *heapMoved) hpos = reinterpret_cast<const uint8_t*>(rec)[static_cast<size_t>(slot) * 32 + 31];
+    // DQ.cpp:1124-1130: an allocated node is open or closed, and its total was formed as its
+    // cost + the same heuristic
+    if (found && total >= laneCost(ra.cost) + heuristic) return;
+    const bool wasOpen = found && !laneIsClosed(ra.cost);
     *recA(slot) = LaneRecA{npos[0], npos[1], npos[2], cost};
-    *recB(slot) = LaneRecB{nei | (kLaneFlagOpen << 24), bestG | (viaJ << 24),
-                           hi.neiLinkStart | ((hi.meta >> kLinkNeiCountShift) << 27), bslot | (1u << 12)};
+    *recB(slot) = LaneRecB{nei, bestG | (viaJ << 24), hi.neiLinkStart | ((hi.meta >> kLinkNeiCountShift) << 27),
+                           bslot | (1u << 12)};
     if (!found) tab[hi.neiKey] = static_cast<uint16_t>((gen << kLaneSlotBits) | slot);
     if (wasOpen) {
-      heapUp(static_cast<int>(hpos), total, slot);
+      const int hp = findPos(slot);
+      if (hp < 0) {  // an open node that is not in the heap would be a bug
+        *ev = kLEvFault;
+        return;
+      }
+      heapUp(hp, total, slot);
     } else {
       heapUp(size, total, slot);
       size++;
     }
-    *heapMoved = true;
     if (heuristic < lastBestCost) {  // DQ.cpp:1154-1159
       lastBestCost = heuristic;
       lastBest = slot;
       lastBestG = nei;
     }
-    return true;
   }
 
   // One iteration of the state machine.  Returns an event; after kLEvFinished `status` and `xk`
@@ -309,8 +385,8 @@ struct LaneSearch {
     const LaneRecB bb = *recB(bslot);
     size--;
     heapPopSift(size);
-    setFlags(bslot, kLaneFlagClosed);
-    const uint32_t bestG = bb.w0 & 0x00ffffffu;
+    recA(bslot)->cost = laneSetClosed(ba.cost);
+    const uint32_t bestG = bb.poly;
     if (bestG == endG) {
       lastBest = bslot;
       lastBestG = bestG;
@@ -326,14 +402,13 @@ struct LaneSearch {
     expanded++;
     nLinks += static_cast<uint32_t>(ln);
     const float bpos[3] = {ba.px, ba.py, ba.pz};
-    const float bcost = ba.cost;
+    const float bcost = ba.cost;  // open until this pop: sign bit clear
     // ---- neighbours (DQ.cpp:1042-1153) ---------------------------------------------------
     int ev = kLEvNone;
-    bool heapMoved = false;
     for (int base = 0; base < ln && ev == kLEvNone; base += kLaneChunk) {
       LaneLinkLo lo[kLaneChunk];
       LaneLinkHi hi[kLaneChunk];
-      uint32_t te[kLaneChunk], rw0[kLaneChunk], rw3[kLaneChunk];
+      uint32_t te[kLaneChunk];
       LaneRecA ra[kLaneChunk];
       bool cand[kLaneChunk];
 #if defined(__CUDA_ARCH__)
@@ -358,26 +433,18 @@ struct LaneSearch {
 #endif
       for (int k = 0; k < kLaneChunk; ++k) {
         ra[k] = LaneRecA{0.f, 0.f, 0.f, 0.f};
-        rw0[k] = rw3[k] = 0u;
-        if (cand[k] && (te[k] >> kLaneSlotBits) == gen) {
-          const uint32_t s2 = te[k] & kLaneSlotMask;
-          ra[k] = *recA(s2);
-          const LaneRecB b2 = *recB(s2);
-          rw0[k] = b2.w0;
-          rw3[k] = b2.w3;
-        }
+        if (cand[k] && (te[k] >> kLaneSlotBits) == gen) ra[k] = *recA(te[k] & kLaneSlotMask);
       }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
       for (int k = 0; k < kLaneChunk; ++k) {
         if (cand[k] && ev == kLEvNone)
-          visit(bslot, bestG, bpos, bcost, static_cast<uint32_t>(base + k), lo[k], hi[k], te[k], ra[k], rw0[k],
-                rw3[k], fastFail, &heapMoved, &ev);
+          visit(bslot, bestG, bpos, bcost, static_cast<uint32_t>(base + k), lo[k], hi[k], te[k], ra[k], fastFail, &ev);
       }
     }
     if (ev == kLEvPoolExhausted) return finishSearch(allCorridors);
-    if (ev == kLEvOverflow) mode = kLIdle;
+    if (ev == kLEvFault) mode = kLIdle;
     return ev;
   }
 };

@@ -38,7 +38,9 @@ constexpr int kFpWarps = 4;   // warps per block of the wall-distance kernels
 constexpr int kOpenS = 256;
 constexpr int kOpenL = 2048;
 constexpr int kFpWpb = 1;
-constexpr int kOpenLane = 192;  // open-list capacity of the lane-per-query search (6 B per entry and lane)
+constexpr int kLaneTS = 63;    // lane-per-query search: heap entries per lane kept in shared memory (6 levels)
+constexpr int kLaneLogC = 8;   // ... log2 of its node -> heap position cache entries per lane (shared)
+constexpr int kLaneMinB = 7;   // ... and resident warps per SM its register budget must allow
 constexpr int kSnapW = 8;     // lanes per point in k_snap
 constexpr int kRandW = 8;
 
@@ -79,12 +81,13 @@ struct hbn_navmesh {
   DevBuf sG, eG, e2G, sPt, ePt, epPt, lastPoly, lists, counters, wsL, wsFp, io, work, mgDist, mgBounds, mgOrder, mgEnd;
   // lock-step find_path (hbn_astar_group.cuh): class, search list, status, corridor rings, node records
   DevBuf fpCls, fpWork, fpStat, fpLen, fpCorr, wsFpG;
-  int fpG = 8;          // lanes per query of k_astar_g; 0 = one query per warp (k_findpath_w tiers only);
+  int fpG = 1;          // lanes per query of k_astar_g; 0 = one query per warp (k_findpath_w tiers only);
                         // 1 = one query per LANE (k_astar_lane, hbn_astar_lane.cuh)
   int blocksFpG = 0;
   // lane-per-query search: per-lane node table + records in HBM, allocated on first use
   DevBuf wsLane, laneGen;
   int blocksFpLane = 0;
+  int laneCfg = 0;      // HBN_LANE_CFG: shared heap levels / warps per SM variant (tuning)
   // pinned staging for the host-buffer entry points
   void* pinned = nullptr;
   size_t pinnedCap = 0;
@@ -114,6 +117,7 @@ int upload(hbn_navmesh* nm, const std::vector<T>& v, const T** out) {
 // Per-lane node tables + records of k_astar_lane: blocksFpLane * 32 slots, allocated (and zeroed:
 // generation 0, empty tables) on first use.  Shrinks the grid when HBM is short.
 int laneScratch(hbn_navmesh* nm, cudaStream_t st, LaneScratch* out) {
+  const size_t tabB = laneTabBytes(nm->view.numKeys);
   const size_t per = laneScratchBytes(nm->view.numKeys);
   if (!nm->wsLane.p) {
     size_t freeB = 0, totalB = 0;
@@ -124,14 +128,29 @@ int laneScratch(hbn_navmesh* nm, cudaStream_t st, LaneScratch* out) {
     const size_t lanes = static_cast<size_t>(nm->blocksFpLane) * 32;
     int rc;
     if ((rc = nm->wsLane.ensure(lanes * per)) || (rc = nm->laneGen.ensure(lanes * 4))) return rc;
-    CK(cudaMemsetAsync(nm->wsLane.p, 0, lanes * per, st));
+    CK(cudaMemsetAsync(nm->wsLane.p, 0, lanes * tabB, st));  // the tables come first
     CK(cudaMemsetAsync(nm->laneGen.p, 0, lanes * 4, st));
   }
-  out->base = static_cast<char*>(nm->wsLane.p);
+  const size_t lanes = static_cast<size_t>(nm->blocksFpLane) * 32;
+  char* p = static_cast<char*>(nm->wsLane.p);
+  out->tab = p;
+  out->rec = p + lanes * tabB;
+  out->heap = out->rec + lanes * kLaneRecBytes;
   out->gen = static_cast<uint32_t*>(nm->laneGen.p);
-  out->bytesPerLane = per;
-  out->tabBytes = laneTabBytes(nm->view.numKeys);
+  out->tabBytes = tabB;
   return HBN_OK;
+}
+
+// lane-per-query search variants: {heap entries in shared, log2 position cache entries, resident warps per SM}
+const void* laneKernel(int cfg, size_t* shared) {
+  switch (cfg) {
+    case 1: *shared = laneSharedBytes<63, 7>(); return reinterpret_cast<const void*>(&k_astar_lane<63, 7, 11>);
+    case 2: *shared = laneSharedBytes<31, 8>(); return reinterpret_cast<const void*>(&k_astar_lane<31, 8, 10>);
+    case 3: *shared = laneSharedBytes<127, 8>(); return reinterpret_cast<const void*>(&k_astar_lane<127, 8, 5>);
+    case 4: *shared = laneSharedBytes<127, 7>(); return reinterpret_cast<const void*>(&k_astar_lane<127, 7, 7>);
+    case 5: *shared = laneSharedBytes<63, 9>(); return reinterpret_cast<const void*>(&k_astar_lane<63, 9, 5>);
+    default: *shared = laneSharedBytes<kLaneTS, kLaneLogC>(); return reinterpret_cast<const void*>(&k_astar_lane<kLaneTS, kLaneLogC, kLaneMinB>);
+  }
 }
 
 const void* groupKernel(int g) {
@@ -212,10 +231,12 @@ int finishCreate(HostNavMesh& mesh, const int32_t* islands, int device, hbn_navm
     nm->fpG = (strcmp(e, "warp") == 0) ? 0 : (strcmp(e, "lane") == 0) ? 1 : atoi(e);
   if (nm->fpG != 0 && nm->fpG != 1 && nm->fpG != 4 && nm->fpG != 8 && nm->fpG != 16 && nm->fpG != 32) nm->fpG = 8;
   {
-    const size_t smLane = laneSharedBytes<kOpenLane>();
-    CK(cudaFuncSetAttribute(k_astar_lane<kOpenLane>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smLane)));
-    CK(cudaFuncSetAttribute(k_astar_lane<kOpenLane>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_astar_lane<kOpenLane>, 32, smLane));
+    if (const char* e = getenv("HBN_LANE_CFG")) nm->laneCfg = atoi(e);
+    size_t smLane = 0;
+    const void* fn = laneKernel(nm->laneCfg, &smLane);
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smLane)));
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32, smLane));
     nm->blocksFpLane = std::max(1, occ) * nm->smCount;
     if (const char* e = getenv("HBN_FP_BLOCKS_PER_SM")) nm->blocksFpLane = std::max(1, std::min(occ, atoi(e))) * nm->smCount;
   }
@@ -595,7 +616,10 @@ static int findPathLaunch(hbn_navmesh_t nm, const float* starts, const float* en
       LaneScratch sc{};
       if ((rc = laneScratch(nm, st, &sc))) return rc;
       const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(nm->blocksFpLane, (cn + 31) / 32));
-      k_astar_lane<kOpenLane><<<blocks, 32, laneSharedBytes<kOpenLane>(), st>>>(nm->view, ga, sc);
+      size_t smLane = 0;
+      const void* fn = laneKernel(nm->laneCfg, &smLane);
+      void* kargs[] = {&nm->view, &ga, &sc};
+      CK(cudaLaunchKernel(fn, dim3(blocks), dim3(32), kargs, smLane, st));
       nm->launches++;
       CK(cudaGetLastError());
     } else {

@@ -133,17 +133,18 @@ void emu_find_path_lane(void* h, const float* starts, const float* ends, long n,
   Emu* e = static_cast<Emu*>(h);
   HostGroup grp;
   uint32_t q[2];
-  constexpr int OC = 192;
+  constexpr int TS = 63, LOGC = 8;
   const NavView& nav = e->nav;
   std::vector<char> scratch(laneScratchBytes(nav.numKeys) + 64, 0);
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(scratch.data()) + 15) & ~uintptr_t(15));
-  std::vector<float> K(OC);
-  std::vector<uint16_t> S(OC);
+  std::vector<float> K(TS);
+  std::vector<uint16_t> S(TS), PC(1 << LOGC);
   std::vector<uint32_t> ring(kMaxPathPolys);
-  LaneSearch<1, OC> s{};
-  s.K = K.data(); s.S = S.data();
+  LaneSearch<1, TS, LOGC> s{};
+  s.K = K.data(); s.S = S.data(); s.PC = PC.data();
   s.tab = reinterpret_cast<uint16_t*>(base);
   s.rec = base + laneTabBytes(nav.numKeys);
+  s.G = reinterpret_cast<LaneHeapEnt*>(s.rec + kLaneRecBytes);
   s.gen = 0;
   s.mode = kLIdle;
   for (long i = 0; i < n; ++i) {

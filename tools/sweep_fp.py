@@ -3,11 +3,13 @@ usage: python tools/sweep_fp.py [queries]"""
 import json, os, subprocess, sys
 n = sys.argv[1] if len(sys.argv) > 1 else "400000"
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-variants = (("lane", None), ("lane", "4"), ("lane", "2"), ("16", None), ("warp", None))
+variants = (("lane", None), ("lane:1", None), ("lane:2", None), ("lane:3", None), ("lane:4", None), ("lane:5", None), ("lane:1", "8"))
 if os.environ.get("SWEEP_ALL"):
     variants += (("8", None), ("32", None), ("4", None))
 for g, bps in variants:
-    env = dict(os.environ, HBN_FP_G=g)
+    env = dict(os.environ, HBN_FP_G=g.split(":")[0])
+    if ":" in g:
+        env["HBN_LANE_CFG"] = g.split(":")[1]
     if bps:
         env["HBN_FP_BLOCKS_PER_SM"] = bps
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "2", "--warmup", "3",
