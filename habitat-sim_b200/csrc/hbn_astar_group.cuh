@@ -472,35 +472,78 @@ __global__ void __launch_bounds__(32) k_astar_g(NavView nav, AStarGArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
-// findPathInternal's decisions that need no search (PF.cpp:1426-1447), one thread per query;
-// the rest are appended to the search list.
+// findPathInternal's decisions that need no search (PF.cpp:1426-1447), one thread per query.
+// The queries that do need one are put on the search list LONGEST FIRST: a search costs between
+// a handful and ~2000 expansions, the persistent search kernels hand queries out in list order,
+// and a cheap estimate of the cost (the straight-line distance between the snapped points, in
+// kFpBuckets classes) is enough to keep the expensive ones out of the tail of the launch.
+// Two passes: classify + histogram of the classes, then a scatter into per-class ranges.
+constexpr int kFpBuckets = 32;
+constexpr float kFpBucketWidth = 2.0f;  // metres of straight-line distance per class
+constexpr uint8_t kFpNoBucket = 0xff;
+
 __global__ void __launch_bounds__(256) k_fp_classify(NavView nav, const uint32_t* __restrict__ sG,
                                                      const float* __restrict__ sPt,
                                                      const uint32_t* __restrict__ eG,
                                                      const float* __restrict__ ePt, int64_t n, int startDiv,
-                                                     uint8_t* __restrict__ cls, uint32_t* __restrict__ work,
-                                                     uint32_t* __restrict__ workCount) {
+                                                     uint8_t* __restrict__ cls, uint8_t* __restrict__ bucket,
+                                                     uint32_t* __restrict__ hist, uint32_t* __restrict__ workCount) {
+  __shared__ uint32_t histS[kFpBuckets];
+  if (threadIdx.x < kFpBuckets) histS[threadIdx.x] = 0;
+  __syncthreads();
   const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (q >= n) return;
-  const int64_t qs = startDiv > 1 ? q / startDiv : q;
-  const uint32_t s = sG[qs], e = eG[q];
-  uint8_t c = kClsNone;
-  if (s != kNoPoly && e != kNoPoly) {
-    const float sp[3] = {sPt[3 * qs], sPt[3 * qs + 1], sPt[3 * qs + 2]};
-    const float ep[3] = {ePt[3 * q], ePt[3 * q + 1], ePt[3 * q + 2]};
-    if (vfuzzyEq(sp, ep)) {
-      c = kClsTrivial;
-    } else {
-      const int32_t si = nav.polys[s].island, ei = nav.polys[e].island;
-      if (si >= 0 && si == ei) {  // hasConnection, PF.cpp:209-221
-        if (s == e) c = kClsSamePoly;
-        else if (!vfinite(sp) || !vfinite(ep)) c = kClsInvalid;
-        else c = kClsSearch;
+  if (q < n) {
+    const int64_t qs = startDiv > 1 ? q / startDiv : q;
+    const uint32_t s = sG[qs], e = eG[q];
+    uint8_t c = kClsNone, b = kFpNoBucket;
+    if (s != kNoPoly && e != kNoPoly) {
+      const float sp[3] = {sPt[3 * qs], sPt[3 * qs + 1], sPt[3 * qs + 2]};
+      const float ep[3] = {ePt[3 * q], ePt[3 * q + 1], ePt[3 * q + 2]};
+      if (vfuzzyEq(sp, ep)) {
+        c = kClsTrivial;
+      } else {
+        const int32_t si = nav.polys[s].island, ei = nav.polys[e].island;
+        if (si >= 0 && si == ei) {  // hasConnection, PF.cpp:209-221
+          if (s == e) c = kClsSamePoly;
+          else if (!vfinite(sp) || !vfinite(ep)) c = kClsInvalid;
+          else {
+            c = kClsSearch;
+            const float d = vdist(sp, ep) / kFpBucketWidth;
+            b = static_cast<uint8_t>(d < static_cast<float>(kFpBuckets - 1) ? static_cast<int>(d) : kFpBuckets - 1);
+            atomicAdd(&histS[b], 1u);
+          }
+        }
       }
     }
+    cls[q] = c;
+    bucket[q] = b;
   }
-  cls[q] = c;
-  if (c == kClsSearch) work[atomicAdd(workCount, 1u)] = static_cast<uint32_t>(q);
+  __syncthreads();
+  if (threadIdx.x < kFpBuckets && histS[threadIdx.x]) {
+    atomicAdd(&hist[threadIdx.x], histS[threadIdx.x]);
+    atomicAdd(workCount, histS[threadIdx.x]);
+  }
+}
+
+// work[] = the search queries, class kFpBuckets-1 (longest) first.  cursor[]: zeroed.
+__global__ void __launch_bounds__(256) k_fp_scatter(const uint8_t* __restrict__ bucket, int64_t n,
+                                                    const uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor,
+                                                    uint32_t* __restrict__ work) {
+  __shared__ uint32_t cntS[kFpBuckets], baseS[kFpBuckets];
+  if (threadIdx.x < kFpBuckets) cntS[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const uint8_t b = q < n ? bucket[q] : kFpNoBucket;
+  uint32_t r = 0;
+  if (b != kFpNoBucket) r = atomicAdd(&cntS[b], 1u);
+  __syncthreads();
+  if (threadIdx.x < kFpBuckets && cntS[threadIdx.x]) {
+    uint32_t start = 0;
+    for (int j = kFpBuckets - 1; j > static_cast<int>(threadIdx.x); --j) start += hist[j];
+    baseS[threadIdx.x] = start + atomicAdd(&cursor[threadIdx.x], cntS[threadIdx.x]);
+  }
+  __syncthreads();
+  if (b != kFpNoBucket) work[baseS[b] + r] = static_cast<uint32_t>(q);
 }
 
 // Corridor as the search left it: entering links in a 256-entry ring; poly i is the neighbour

@@ -20,22 +20,21 @@ struct LaneScratch {  // one slot per lane of the grid in each region
   size_t tabBytes;
 };
 
-template <int TS, int LOGC>
-__host__ __device__ constexpr size_t laneSharedBytes() { return static_cast<size_t>(TS) * 32 * 6 + (static_cast<size_t>(32) << LOGC) * 2; }
+template <int TS>
+__host__ __device__ constexpr size_t laneSharedBytes() { return static_cast<size_t>(TS) * 32 * 6; }
 
-// TS: heap entries per lane in shared memory; LOGC: log2 of the position cache entries per lane;
-// MINB: resident one-warp blocks per SM the register allocation must allow.
-template <int TS, int LOGC, int MINB>
+// TS: heap entries per lane in shared memory; MINB: resident one-warp blocks per SM the
+// register allocation must allow.
+template <int TS, int MINB>
 __global__ void __launch_bounds__(32, MINB) k_astar_lane(NavView nav, AStarGArgs a, LaneScratch sc) {
   constexpr uint32_t FULL = 0xffffffffu;
   extern __shared__ __align__(16) char smem[];
   const int lane = threadIdx.x;
   const uint32_t ltMask = (1u << lane) - 1u;
   const size_t slotId = static_cast<size_t>(blockIdx.x) * 32 + lane;
-  LaneSearch<32, TS, LOGC> s;
+  LaneSearch<32, TS> s;
   s.K = reinterpret_cast<float*>(smem) + lane;
   s.S = reinterpret_cast<uint16_t*>(smem + static_cast<size_t>(TS) * 32 * 4) + lane;
-  s.PC = reinterpret_cast<uint16_t*>(smem + static_cast<size_t>(TS) * 32 * 6) + lane;
   s.G = reinterpret_cast<LaneHeapEnt*>(sc.heap + slotId * kLaneHeapBytes);
   s.tab = reinterpret_cast<uint16_t*>(sc.tab + slotId * sc.tabBytes);
   s.rec = sc.rec + slotId * kLaneRecBytes;

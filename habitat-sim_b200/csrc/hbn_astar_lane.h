@@ -11,14 +11,13 @@
 //
 //   shared  : the top TS entries (6 levels at TS = 63) of the binary heap, 6 B per entry
 //             {f32 total, u16 node}, interleaved over the lanes of the warp (entry i of lane l
-//             at word i*32 + l: never a bank conflict); and a direct-mapped cache
-//             node -> heap position (2^LOGC u16 entries, tag | position), written with every
-//             heap move, so that dtNodeQueue::modify (DNode.h:132-142) finds its entry without
-//             the reference's linear scan.  Positions are NOT kept in HBM: a heap move would
-//             cost a scattered 2 B store each (9 per expansion, measured: 3/4 of all L2
-//             requests of the first version).  A cache hit is verified against the heap entry;
-//             a miss (8 % of the modifies at 256 entries, modifies being 0.06 per expansion on
-//             the C4 workload) falls back to the scan;
+//             at word i*32 + l: never a bank conflict).  Nothing else: heap positions of the
+//             nodes are NOT tracked (a first version kept them in HBM: one scattered 2 B store
+//             per heap move, 9 per expansion, 3/4 of all L2 requests; a second one in a shared
+//             cache, which cost occupancy and 8 % of the instructions).  dtNodeQueue::modify
+//             (DNode.h:132-142) is rare (0.06 per expansion on the C4 workload), so it does
+//             what the reference does, a linear scan for the node -- but the WHOLE WARP scans
+//             the heap of the lane that needs it (findPosAll), 32 entries per step;
 //   global  : per lane
 //             (a) the rest of the heap, 8 B entries; the two children of an entry share one
 //                 aligned 16 B load;
@@ -36,7 +35,11 @@
 // One step() = one iteration of the reference's while loop: pop, then the popped poly's links
 // in chunks of kLaneChunk: all link records, then all table entries, then all found records
 // are loaded before the serial part, so a lane has several independent loads in flight per
-// stage instead of a chain of 3 dependent loads per neighbour.
+// stage instead of a chain of 3 dependent loads per neighbour.  The serial part is split too:
+// first every link's cost test and record update (visit), which only queues the heap
+// operation; then the queued operations are replayed in link order (they are the only heap
+// operations between two pops, so the heap goes through exactly the reference's states).
+// Replaying by queue position instead of link index keeps more lanes busy per instruction.
 // Corridor extraction (getPathToNode, DQ.cpp:1167-1205) is a pointer chase; it runs as a mode
 // of the same state machine, a few hops per step, so it never stalls the other 31 queries.
 #pragma once
@@ -125,16 +128,15 @@ HBN_HD void laneLoadLink(const LinkRec* p, LaneLinkLo& lo, LaneLinkHi& hi) {
 
 // HS: distance (in elements) between consecutive shared heap entries of this lane (32 on the
 // device, 1 in the host build); TS: heap entries kept in shared memory (odd, so that the
-// children 2i+1, 2i+2 of an entry are both on the same side and pair-aligned in global);
-// LOGC: log2 of the position cache's entry count.
-template <int HS, int TS, int LOGC>
+// children 2i+1, 2i+2 of an entry are both on the same side and pair-aligned in global).
+// step() contains warp collectives on the device: all 32 lanes of the warp must call it
+// together, whatever their mode.
+template <int HS, int TS>
 struct LaneSearch {
   static_assert((TS & 1) == 1, "TS must be odd");
-  static_assert(LOGC >= 5 && LOGC <= 11, "position cache: tag | 11-bit position must fit 16 bits");
   // memory of this lane
   float* K;        // shared: heap keys
   uint16_t* S;     // shared: heap nodes
-  uint16_t* PC;    // shared: position cache, entry (node & mask): node >> LOGC << 11 | position
   LaneHeapEnt* G;  // global: heap entries TS.. (entry j at G[j - TS])
   uint16_t* tab;   // node table
   char* rec;       // node records
@@ -175,18 +177,51 @@ struct LaneSearch {
     } else {
       G[i - TS] = LaneHeapEnt{k, s};
     }
-    PC[(s & ((1u << LOGC) - 1u)) * HS] = static_cast<uint16_t>(((s >> LOGC) << 11) | static_cast<uint32_t>(i));
   }
-  // heap position of an open node (dtNodeQueue::modify's search, DNode.h:134-141)
-  HBN_HD int findPos(const uint32_t s) const {
-    const uint32_t e = PC[(s & ((1u << LOGC) - 1u)) * HS];
-    const int p = static_cast<int>(e & 2047u);
-    if ((e >> 11) == (s >> LOGC) && p < size) {
-      float k;
-      uint32_t hs;
-      hget(p, k, hs);
-      if (hs == s) return p;
+  static HBN_HD bool warpAny(bool p) {
+#if defined(__CUDA_ARCH__)
+    return __any_sync(0xffffffffu, p) != 0;
+#else
+    return p;
+#endif
+  }
+  // Heap position of open node `s` for every lane with `need` (dtNodeQueue::modify's search,
+  // DNode.h:134-141); -1 if absent.  Warp collective.
+  HBN_HD int findPosAll(const bool need, const uint32_t s) const {
+#if defined(__CUDA_ARCH__)
+    static_assert(HS == 32, "device build: one lane per column");
+    const int lane = threadIdx.x & 31;
+    int pos = -1;
+    uint32_t m = __ballot_sync(0xffffffffu, need);
+    while (m) {
+      const int l = __ffs(m) - 1;
+      m &= m - 1;
+      const uint32_t tgt = __shfl_sync(0xffffffffu, s, l);
+      const int n = __shfl_sync(0xffffffffu, size, l);
+      const LaneHeapEnt* g = reinterpret_cast<const LaneHeapEnt*>(
+          __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(G), l));
+      const uint16_t* col = S - lane + l;  // lane l's column of the shared heap
+      int hit = -1;
+      for (int base = lane; base < n; base += 128) {  // 4 independent loads in flight per lane
+        uint32_t hs[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = base + 32 * u;
+          hs[u] = 0xffffffffu;
+          if (i < n) hs[u] = i < TS ? static_cast<uint32_t>(col[i * 32]) : g[i - TS].slot;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (hs[u] == tgt) hit = base + 32 * u;
+      }
+      __syncwarp();
+      const uint32_t hm = __ballot_sync(0xffffffffu, hit >= 0);
+      const int p = __shfl_sync(0xffffffffu, hit, hm ? __ffs(hm) - 1 : 0);
+      if (lane == l) pos = hm ? p : -1;
     }
+    return pos;
+#else
+    if (!need) return -1;
     for (int i = 0; i < size; ++i) {
       float k;
       uint32_t hs;
@@ -194,6 +229,7 @@ struct LaneSearch {
       if (hs == s) return i;
     }
     return -1;
+#endif
   }
 
   // dtNodeQueue::bubbleUp, DNode.cpp:156-167
@@ -283,11 +319,13 @@ struct LaneSearch {
     return kLEvFinished;
   }
 
-  // One neighbour (DQ.cpp:1056-1153).  `te` and `ra` were loaded before the serial part of this
-  // chunk.
-  HBN_HD void visit(const uint32_t bslot, const uint32_t bestG, const float* bpos, const float bcost,
-                    const uint32_t viaJ, const LaneLinkLo& lo, const LaneLinkHi& hi, uint32_t te, LaneRecA ra,
-                    const bool fastFail, int* ev) {
+  // One neighbour (DQ.cpp:1056-1153) up to the heap operation, which is returned: 0 = none,
+  // else kOpPush / kOpModify with the node in *opSlot and its new total in *opKey.  `te` and
+  // `ra` were loaded before the serial part of this chunk.
+  enum { kOpNone = 0, kOpPush = 1, kOpModify = 2 };
+  HBN_HD int visit(const uint32_t bslot, const uint32_t bestG, const float* bpos, const float bcost,
+                   const uint32_t viaJ, const LaneLinkLo& lo, const LaneLinkHi& hi, uint32_t te, LaneRecA ra,
+                   const bool fastFail, int* stop, float* opKey, uint32_t* opSlot) {
     const uint32_t nei = lo.nei;
     if ((hi.meta & kLinkDupBit) != 0) {  // an earlier link of this poly may just have created the node
       te = tab[hi.neiKey];
@@ -299,8 +337,8 @@ struct LaneSearch {
     if (!found) {  // dtNodePool::getNode, DNode.cpp:121-152: allocation against the pool limit
       if (nodeCount >= kMaxNodes) {
         outOfNodes = true;
-        if (fastFail) *ev = kLEvPoolExhausted;  // PF.cpp:1450 has decided "no path" already
-        return;
+        if (fastFail) *stop = kLEvPoolExhausted;  // PF.cpp:1450 has decided "no path" already
+        return kOpNone;
       }
       slot = static_cast<uint32_t>(nodeCount++);
       npos[0] = lo.mx; npos[1] = lo.my; npos[2] = lo.mz;
@@ -322,38 +360,36 @@ struct LaneSearch {
     const float total = cost + heuristic;
     // DQ.cpp:1124-1130: an allocated node is open or closed, and its total was formed as its
     // cost + the same heuristic
-    if (found && total >= laneCost(ra.cost) + heuristic) return;
+    if (found && total >= laneCost(ra.cost) + heuristic) return kOpNone;
     const bool wasOpen = found && !laneIsClosed(ra.cost);
     *recA(slot) = LaneRecA{npos[0], npos[1], npos[2], cost};
     *recB(slot) = LaneRecB{nei, bestG | (viaJ << 24), hi.neiLinkStart | ((hi.meta >> kLinkNeiCountShift) << 27),
                            bslot | (1u << 12)};
     if (!found) tab[hi.neiKey] = static_cast<uint16_t>((gen << kLaneSlotBits) | slot);
-    if (wasOpen) {
-      const int hp = findPos(slot);
-      if (hp < 0) {  // an open node that is not in the heap would be a bug
-        *ev = kLEvFault;
-        return;
-      }
-      heapUp(hp, total, slot);
-    } else {
-      heapUp(size, total, slot);
-      size++;
-    }
     if (heuristic < lastBestCost) {  // DQ.cpp:1154-1159
       lastBestCost = heuristic;
       lastBest = slot;
       lastBestG = nei;
     }
+    *opKey = total;
+    *opSlot = slot;
+    return wasOpen ? kOpModify : kOpPush;
   }
 
   // One iteration of the state machine.  Returns an event; after kLEvFinished `status` and `xk`
   // (corridor length, 0 = not extracted) are the query's result and the lane is idle.
   HBN_HD int step(const NavView& nav, const bool fastFail, const bool allCorridors) {
+    int ev = kLEvNone;
+    bool go = false;  // this lane expands a poly in this step
+    uint32_t bslot = 0, bestG = 0, parentG = 0, l0 = 0;
+    int ln = 0;
+    float bpos[3] = {0.f, 0.f, 0.f};
+    float bcost = 0.f;
     if (mode == kLExtract) {  // getPathToNode, DQ.cpp:1167-1205, from the end backwards
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-      for (int h = 0; h < kLaneHops; ++h) {
+      for (int h = 0; h < kLaneHops && mode == kLExtract; ++h) {
         const bool hasParent = ((xB.w3 >> 12) & 1u) != 0;
         uint32_t via = kNoPoly;
         if (hasParent) {
@@ -368,44 +404,47 @@ struct LaneSearch {
         if (!hasParent) {
           if (xk > kMaxPathPolys) status |= kDtBufferTooSmall;
           mode = kLIdle;
-          return kLEvFinished;
-        }
-        if (xk > kMaxNodes) {  // a parent cycle would be a bug
+          ev = kLEvFinished;
+        } else if (xk > kMaxNodes) {  // a parent cycle would be a bug
           mode = kLIdle;
-          return kLEvFault;
+          ev = kLEvFault;
         }
       }
-      return kLEvNone;
+    } else if (mode == kLSearch) {
+      if (size == 0) {
+        ev = finishSearch(allCorridors);  // open list exhausted: partial result
+      } else {
+        // ---- pop (DQ.cpp:1027-1040) ------------------------------------------------------
+        bslot = S[0];
+        const LaneRecA ba = *recA(bslot);
+        const LaneRecB bb = *recB(bslot);
+        size--;
+        heapPopSift(size);
+        recA(bslot)->cost = laneSetClosed(ba.cost);
+        bestG = bb.poly;
+        if (bestG == endG) {
+          lastBest = bslot;
+          lastBestG = bestG;
+          ev = finishSearch(allCorridors);
+        } else if (expanded >= kLaneMaxExpansions) {
+          mode = kLIdle;
+          ev = kLEvFault;
+        } else {
+          go = true;
+          parentG = bb.w1 & 0x00ffffffu;
+          l0 = bb.lnk & 0x07ffffffu;
+          ln = static_cast<int>(bb.lnk >> 27);
+          expanded++;
+          nLinks += static_cast<uint32_t>(ln);
+          bpos[0] = ba.px; bpos[1] = ba.py; bpos[2] = ba.pz;
+          bcost = ba.cost;  // open until this pop: sign bit clear
+        }
+      }
     }
-    if (mode != kLSearch) return kLEvNone;
-    if (size == 0) return finishSearch(allCorridors);  // open list exhausted: partial result
-    // ---- pop (DQ.cpp:1027-1040) ----------------------------------------------------------
-    const uint32_t bslot = S[0];
-    const LaneRecA ba = *recA(bslot);
-    const LaneRecB bb = *recB(bslot);
-    size--;
-    heapPopSift(size);
-    recA(bslot)->cost = laneSetClosed(ba.cost);
-    const uint32_t bestG = bb.poly;
-    if (bestG == endG) {
-      lastBest = bslot;
-      lastBestG = bestG;
-      return finishSearch(allCorridors);
-    }
-    if (expanded >= kLaneMaxExpansions) {
-      mode = kLIdle;
-      return kLEvFault;
-    }
-    const uint32_t parentG = bb.w1 & 0x00ffffffu;
-    const uint32_t l0 = bb.lnk & 0x07ffffffu;
-    const int ln = static_cast<int>(bb.lnk >> 27);
-    expanded++;
-    nLinks += static_cast<uint32_t>(ln);
-    const float bpos[3] = {ba.px, ba.py, ba.pz};
-    const float bcost = ba.cost;  // open until this pop: sign bit clear
-    // ---- neighbours (DQ.cpp:1042-1153) ---------------------------------------------------
-    int ev = kLEvNone;
-    for (int base = 0; base < ln && ev == kLEvNone; base += kLaneChunk) {
+    // ---- neighbours (DQ.cpp:1042-1153); the loop is warp-uniform (collectives inside) -----
+    int stop = kLEvNone;
+    for (int base = 0; warpAny(go && stop == kLEvNone && base < ln); base += kLaneChunk) {
+      const bool act = go && stop == kLEvNone && base < ln;
       LaneLinkLo lo[kLaneChunk];
       LaneLinkHi hi[kLaneChunk];
       uint32_t te[kLaneChunk];
@@ -418,7 +457,7 @@ struct LaneSearch {
         lo[k].nei = kNoPoly;
         lo[k].mx = lo[k].my = lo[k].mz = 0.f;
         hi[k] = LaneLinkHi{0u, 0u, 0u, 0u};
-        if (base + k < ln) laneLoadLink(&nav.links[l0 + base + k], lo[k], hi[k]);
+        if (act && base + k < ln) laneLoadLink(&nav.links[l0 + base + k], lo[k], hi[k]);
       }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -435,16 +474,67 @@ struct LaneSearch {
         ra[k] = LaneRecA{0.f, 0.f, 0.f, 0.f};
         if (cand[k] && (te[k] >> kLaneSlotBits) == gen) ra[k] = *recA(te[k] & kLaneSlotMask);
       }
+      // cost tests and record updates; the heap operations are queued in link order
+      float qKey[kLaneChunk];
+      uint32_t qSlot[kLaneChunk];  // node | modify << 16
+      int nq = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
       for (int k = 0; k < kLaneChunk; ++k) {
-        if (cand[k] && ev == kLEvNone)
-          visit(bslot, bestG, bpos, bcost, static_cast<uint32_t>(base + k), lo[k], hi[k], te[k], ra[k], fastFail, &ev);
+        qKey[k] = 0.f;
+        qSlot[k] = 0u;
+      }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int k = 0; k < kLaneChunk; ++k) {
+        if (cand[k] && stop == kLEvNone) {
+          float key = 0.f;
+          uint32_t slot = 0u;
+          const int op = visit(bslot, bestG, bpos, bcost, static_cast<uint32_t>(base + k), lo[k], hi[k], te[k],
+                               ra[k], fastFail, &stop, &key, &slot);
+          if (op != kOpNone) {
+            const uint32_t v = slot | (op == kOpModify ? 0x10000u : 0u);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int j = 0; j <= k; ++j)  // qKey[nq] = key with a compile-time register index
+              if (j == nq) {
+                qKey[j] = key;
+                qSlot[j] = v;
+              }
+            nq++;
+          }
+        }
+      }
+      // replay: push = bubbleUp from the end, modify = locate + bubbleUp (DNode.h:118-142)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int j = 0; j < kLaneChunk; ++j) {
+        if (!warpAny(j < nq)) break;
+        const bool mine = j < nq;
+        const bool isModify = mine && (qSlot[j] & 0x10000u) != 0;
+        const uint32_t slot = qSlot[j] & 0xffffu;
+        const int hp = findPosAll(isModify, slot);
+        if (mine) {
+          if (isModify) {
+            if (hp < 0) stop = kLEvFault;  // an open node that is not in the heap would be a bug
+            else heapUp(hp, qKey[j], slot);
+          } else {
+            heapUp(size, qKey[j], slot);
+            size++;
+          }
+        }
       }
     }
-    if (ev == kLEvPoolExhausted) return finishSearch(allCorridors);
-    if (ev == kLEvFault) mode = kLIdle;
+    if (stop == kLEvPoolExhausted) {
+      ev = finishSearch(allCorridors);
+    } else if (stop == kLEvFault) {
+      mode = kLIdle;
+      ev = kLEvFault;
+    }
     return ev;
   }
 };

@@ -13,6 +13,8 @@
 #include "hbn_kernels.cuh"
 #include "hbn_astar_group.cuh"
 #include "hbn_astar_lane.cuh"
+#include "hbn_snap.cuh"
+#include <cub/device/device_scan.cuh>
 
 using namespace hbn;
 
@@ -38,9 +40,10 @@ constexpr int kFpWarps = 4;   // warps per block of the wall-distance kernels
 constexpr int kOpenS = 256;
 constexpr int kOpenL = 2048;
 constexpr int kFpWpb = 1;
+// per chunk of a find_path call: 16 counters, then the class histogram and the scatter cursors (k_fp_classify)
+constexpr size_t kFpCounterBytes = (16 + 2 * 32) * 4;
 constexpr int kLaneTS = 63;    // lane-per-query search: heap entries per lane kept in shared memory (6 levels)
-constexpr int kLaneLogC = 8;   // ... log2 of its node -> heap position cache entries per lane (shared)
-constexpr int kLaneMinB = 7;   // ... and resident warps per SM its register budget must allow
+constexpr int kLaneMinB = 16;  // ... and resident warps per SM its register budget must allow
 constexpr int kSnapW = 8;     // lanes per point in k_snap
 constexpr int kRandW = 8;
 
@@ -80,11 +83,12 @@ struct hbn_navmesh {
   // scratch (device)
   DevBuf sG, eG, e2G, sPt, ePt, epPt, lastPoly, lists, counters, wsL, wsFp, io, work, mgDist, mgBounds, mgOrder, mgEnd;
   // lock-step find_path (hbn_astar_group.cuh): class, search list, status, corridor rings, node records
-  DevBuf fpCls, fpWork, fpStat, fpLen, fpCorr, wsFpG;
+  DevBuf fpCls, fpBucket, fpWork, fpStat, fpLen, fpCorr, wsFpG;
   int fpG = 1;          // lanes per query of k_astar_g; 0 = one query per warp (k_findpath_w tiers only);
                         // 1 = one query per LANE (k_astar_lane, hbn_astar_lane.cuh)
   int blocksFpG = 0;
   // lane-per-query search: per-lane node table + records in HBM, allocated on first use
+  DevBuf snapCnt, snapOff, snapG, snapQ, snapD, snapOut, snapTmp, snapTodo;  // candidate-list snap (hbn_snap.cuh)
   DevBuf wsLane, laneGen;
   int blocksFpLane = 0;
   int laneCfg = 0;      // HBN_LANE_CFG: shared heap levels / warps per SM variant (tuning)
@@ -141,15 +145,14 @@ int laneScratch(hbn_navmesh* nm, cudaStream_t st, LaneScratch* out) {
   return HBN_OK;
 }
 
-// lane-per-query search variants: {heap entries in shared, log2 position cache entries, resident warps per SM}
+// lane-per-query search variants: {heap entries in shared, resident warps per SM}
 const void* laneKernel(int cfg, size_t* shared) {
   switch (cfg) {
-    case 1: *shared = laneSharedBytes<63, 7>(); return reinterpret_cast<const void*>(&k_astar_lane<63, 7, 11>);
-    case 2: *shared = laneSharedBytes<31, 8>(); return reinterpret_cast<const void*>(&k_astar_lane<31, 8, 10>);
-    case 3: *shared = laneSharedBytes<127, 8>(); return reinterpret_cast<const void*>(&k_astar_lane<127, 8, 5>);
-    case 4: *shared = laneSharedBytes<127, 7>(); return reinterpret_cast<const void*>(&k_astar_lane<127, 7, 7>);
-    case 5: *shared = laneSharedBytes<63, 9>(); return reinterpret_cast<const void*>(&k_astar_lane<63, 9, 5>);
-    default: *shared = laneSharedBytes<kLaneTS, kLaneLogC>(); return reinterpret_cast<const void*>(&k_astar_lane<kLaneTS, kLaneLogC, kLaneMinB>);
+    case 1: *shared = laneSharedBytes<63>(); return reinterpret_cast<const void*>(&k_astar_lane<63, 12>);
+    case 2: *shared = laneSharedBytes<31>(); return reinterpret_cast<const void*>(&k_astar_lane<31, 16>);
+    case 3: *shared = laneSharedBytes<127>(); return reinterpret_cast<const void*>(&k_astar_lane<127, 9>);
+    case 4: *shared = laneSharedBytes<255>(); return reinterpret_cast<const void*>(&k_astar_lane<255, 4>);
+    default: *shared = laneSharedBytes<kLaneTS>(); return reinterpret_cast<const void*>(&k_astar_lane<kLaneTS, kLaneMinB>);
   }
 }
 
@@ -301,18 +304,68 @@ struct DeviceGuard {
   ~DeviceGuard() { cudaSetDevice(prev); }
 };
 
+constexpr int64_t kSnapChunk = 1 << 19;   // points per pass of the candidate-list pipeline
+constexpr int64_t kSnapSmall = 4096;      // below this one k_snap<8> launch is cheaper than five kernels + a scan
+
+// projectToPoly for n points.  Large batches: count -> scan -> fill -> eval -> select
+// (hbn_snap.cuh), nothing read back by the host; small ones: the lane-group kernel.
 int snapLaunch(hbn_navmesh* nm, const float* pts, const int32_t* islands, int64_t n, float* out_pts,
                uint32_t* out_g, uint32_t* out_refs, int32_t* out_isl, uint8_t* out_nav,
                float maxYDelta, cudaStream_t st) {
   if (n <= 0) return HBN_OK;
   const int groupsPerBlock = 256 / kSnapW;
-  int64_t blocks = (n + groupsPerBlock - 1) / groupsPerBlock;
   const int64_t maxBlocks = static_cast<int64_t>(nm->smCount) * 64;
-  if (blocks > maxBlocks) blocks = maxBlocks;
-  k_snap<kSnapW><<<static_cast<unsigned>(blocks), 256, 0, st>>>(nm->view, pts, islands, n, out_pts, out_g,
-                                                                out_refs, out_isl, out_nav, maxYDelta);
-  nm->launches++;
-  CK(cudaGetLastError());
+  static const bool forceGroup = getenv("HBN_SNAP_GROUP") != nullptr;
+  if (n < kSnapSmall || forceGroup) {
+    const int64_t blocks = std::min(maxBlocks, (n + groupsPerBlock - 1) / groupsPerBlock);
+    k_snap<kSnapW><<<static_cast<unsigned>(blocks), 256, 0, st>>>(nm->view, pts, islands, n, out_pts, out_g,
+                                                                  out_refs, out_isl, out_nav, maxYDelta, nullptr);
+    nm->launches++;
+    CK(cudaGetLastError());
+    return HBN_OK;
+  }
+  const int64_t cmax = std::min(n, kSnapChunk);
+  const size_t cap = static_cast<size_t>(cmax) * kSnapAvgCap;
+  size_t tmpBytes = 0;
+  CK(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr),
+                                   static_cast<int>(cmax + 1), st));
+  int rc;
+  if ((rc = nm->snapCnt.ensure((cmax + 1) * 4)) || (rc = nm->snapOff.ensure((cmax + 1) * 4)) ||
+      (rc = nm->snapG.ensure(cap * 4)) || (rc = nm->snapQ.ensure(cap * 4)) || (rc = nm->snapD.ensure(cap * 4)) ||
+      (rc = nm->snapOut.ensure(cap * sizeof(SnapCandOut))) || (rc = nm->snapTmp.ensure(tmpBytes)) ||
+      (rc = nm->snapTodo.ensure(16)))
+    return rc;
+  uint32_t* cnt = static_cast<uint32_t*>(nm->snapCnt.p);
+  uint32_t* off = static_cast<uint32_t*>(nm->snapOff.p);
+  uint32_t* cg = static_cast<uint32_t*>(nm->snapG.p);
+  uint32_t* cq = static_cast<uint32_t*>(nm->snapQ.p);
+  float* cd = static_cast<float*>(nm->snapD.p);
+  SnapCandOut* co = static_cast<SnapCandOut*>(nm->snapOut.p);
+  uint32_t* todo = static_cast<uint32_t*>(nm->snapTodo.p);
+  for (int64_t c0 = 0; c0 < n; c0 += kSnapChunk) {
+    const int64_t cn = std::min(kSnapChunk, n - c0);
+    const float* p = pts + 3 * c0;
+    const int32_t* isl = islands ? islands + c0 : nullptr;
+    const unsigned pb = static_cast<unsigned>((cn + 255) / 256);
+    CK(cudaMemsetAsync(cnt + cn, 0, 4, st));
+    k_snap_count<<<pb, 256, 0, st>>>(nm->view, p, cn, cnt);
+    CK(cub::DeviceScan::ExclusiveSum(nm->snapTmp.p, tmpBytes, cnt, off, static_cast<int>(cn + 1), st));
+    k_snap_fill<<<pb, 256, 0, st>>>(nm->view, p, cn, off, static_cast<uint32_t>(cap), cg, cq);
+    k_snap_eval<<<static_cast<unsigned>(nm->smCount * 16), 256, 0, st>>>(nm->view, p, isl, cn, off,
+                                                                        static_cast<uint32_t>(cap), cg, cq, cd, co);
+    k_snap_select<<<pb, 256, 0, st>>>(nm->view, p, cn, off, static_cast<uint32_t>(cap), cg, cd, co,
+                                      out_pts ? out_pts + 3 * c0 : nullptr, out_g ? out_g + c0 : nullptr,
+                                      out_refs ? out_refs + c0 : nullptr, out_isl ? out_isl + c0 : nullptr,
+                                      out_nav ? out_nav + c0 : nullptr, maxYDelta, todo);
+    // redone here only if the chunk's candidates did not fit the scratch (decided on the device)
+    const int64_t blocks = std::min(maxBlocks, (cn + groupsPerBlock - 1) / groupsPerBlock);
+    k_snap<kSnapW><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+        nm->view, p, isl, cn, out_pts ? out_pts + 3 * c0 : nullptr, out_g ? out_g + c0 : nullptr,
+        out_refs ? out_refs + c0 : nullptr, out_isl ? out_isl + c0 : nullptr, out_nav ? out_nav + c0 : nullptr,
+        maxYDelta, todo);
+    nm->launches += 7;  // 5 kernels here + cub's scan (2 kernels)
+    CK(cudaGetLastError());
+  }
   return HBN_OK;
 }
 
@@ -367,7 +420,8 @@ void hbn_navmesh_destroy(hbn_navmesh_t nm) {
   for (DevBuf* b : {&nm->sG, &nm->eG, &nm->e2G, &nm->sPt, &nm->ePt, &nm->epPt, &nm->lastPoly,
                     &nm->lists, &nm->counters, &nm->wsL, &nm->wsFp, &nm->io, &nm->work, &nm->mgDist,
                     &nm->mgBounds, &nm->mgOrder, &nm->mgEnd, &nm->fpCls, &nm->fpWork, &nm->fpStat,
-                    &nm->fpLen, &nm->fpCorr, &nm->wsFpG, &nm->wsLane, &nm->laneGen})
+                    &nm->fpLen, &nm->fpCorr, &nm->fpBucket, &nm->wsFpG, &nm->wsLane, &nm->laneGen, &nm->snapCnt, &nm->snapOff,
+                    &nm->snapG, &nm->snapQ, &nm->snapD, &nm->snapOut, &nm->snapTmp, &nm->snapTodo})
     b->release();
   if (nm->pinned) cudaFreeHost(nm->pinned);
   if (nm->faultHost) cudaFreeHost(nm->faultHost);
@@ -544,13 +598,13 @@ static int findPathLaunch(hbn_navmesh_t nm, const float* starts, const float* en
   const int64_t cmax = std::min(n, chunk);
   if ((rc = nm->sG.ensure(nStarts * 4)) || (rc = nm->eG.ensure(n * 4)) || (rc = nm->sPt.ensure(nStarts * 12)) ||
       (rc = nm->ePt.ensure(n * 12)) || (rc = nm->lists.ensure(cmax * 4)) ||
-      (rc = nm->counters.ensure(static_cast<size_t>(nChunks) * 64)))
+      (rc = nm->counters.ensure(static_cast<size_t>(nChunks) * kFpCounterBytes)))
     return rc;
   if (nm->fpG &&
-      ((rc = nm->fpCls.ensure(cmax)) || (rc = nm->fpWork.ensure(cmax * 4)) || (rc = nm->fpStat.ensure(cmax * 4)) ||
+      ((rc = nm->fpCls.ensure(cmax)) || (rc = nm->fpBucket.ensure(cmax)) || (rc = nm->fpWork.ensure(cmax * 4)) || (rc = nm->fpStat.ensure(cmax * 4)) ||
        (rc = nm->fpLen.ensure(cmax * 4)) || (rc = nm->fpCorr.ensure(static_cast<size_t>(cmax) * kMaxPathPolys * 4))))
     return rc;
-  CK(cudaMemsetAsync(nm->counters.p, 0, static_cast<size_t>(nChunks) * 64, st));
+  CK(cudaMemsetAsync(nm->counters.p, 0, static_cast<size_t>(nChunks) * kFpCounterBytes, st));
   hbn_navmesh::PhaseEv pe{};
   if (nm->profile) {
     for (auto& e : pe.e) CK(cudaEventCreate(&e));
@@ -568,7 +622,7 @@ static int findPathLaunch(hbn_navmesh_t nm, const float* starts, const float* en
     const int64_t c0 = nm->fpG ? ci * chunk : 0;
     const int64_t cn = nm->fpG ? std::min(chunk, n - c0) : n;
     const int64_t s0 = startDiv > 1 ? c0 / startDiv : c0;
-    uint32_t* cnt = static_cast<uint32_t*>(nm->counters.p) + ci * 16;
+    uint32_t* cnt = static_cast<uint32_t*>(nm->counters.p) + ci * (kFpCounterBytes / 4);
     FindPathArgs a{};
     a.starts = starts + 3 * s0; a.ends = ends + 3 * c0;
     a.sG = static_cast<uint32_t*>(nm->sG.p) + s0; a.sPt = static_cast<float*>(nm->sPt.p) + 3 * s0;
@@ -593,9 +647,12 @@ static int findPathLaunch(hbn_navmesh_t nm, const float* starts, const float* en
     // lock-step pipeline: classify -> search -> funnel (+ the 2048-entry tier for overflows)
     uint8_t* cls = static_cast<uint8_t*>(nm->fpCls.p);
     uint32_t* work = static_cast<uint32_t*>(nm->fpWork.p);
+    uint8_t* bucket = static_cast<uint8_t*>(nm->fpBucket.p);
     k_fp_classify<<<static_cast<unsigned>((cn + 255) / 256), 256, 0, st>>>(nm->view, a.sG, a.sPt, a.eG, a.ePt, cn,
-                                                                          startDiv, cls, work, cnt + 4);
-    nm->launches++;
+                                                                          startDiv, cls, bucket, cnt + 16, cnt + 4);
+    k_fp_scatter<<<static_cast<unsigned>((cn + 255) / 256), 256, 0, st>>>(bucket, cn, cnt + 16, cnt + 16 + kFpBuckets,
+                                                                         work);
+    nm->launches += 2;
     CK(cudaGetLastError());
     AStarGArgs ga{};
     ga.sG = a.sG; ga.sPt = a.sPt; ga.eG = a.eG; ga.ePt = a.ePt;

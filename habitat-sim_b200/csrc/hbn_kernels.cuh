@@ -29,8 +29,10 @@ __global__ void __launch_bounds__(256) k_snap(NavView nav, const float* __restri
                                               uint32_t* __restrict__ out_g,
                                               uint32_t* __restrict__ out_refs,
                                               int32_t* __restrict__ out_isl,
-                                              uint8_t* __restrict__ out_nav, float maxYDelta) {
+                                              uint8_t* __restrict__ out_nav, float maxYDelta,
+                                              const uint32_t* __restrict__ todo) {
   __shared__ uint32_t queue[256 / W][2 * W];
+  if (todo && *todo == 0u) return;  // fallback launch of the candidate-list pipeline (hbn_snap.cuh): not needed
   WarpGroup<W> grp;
   const int gInBlock = threadIdx.x / W;
   const int64_t groupsPerGrid = static_cast<int64_t>(gridDim.x) * (blockDim.x / W);

@@ -90,7 +90,7 @@ def hostemu():
         src = [os.path.join(ROOT, "tests", "hostemu", "hostemu.cpp"),
                os.path.join(ROOT, "habitat-sim_b200", "csrc", "hbn_host.cpp")]
         deps = src + [os.path.join(ROOT, "habitat-sim_b200", "csrc", f)
-                      for f in ("hbn_query.h", "hbn_math.h", "hbn_types.h", "hbn_host.h", "hbn_astar_lane.h")]
+                      for f in ("hbn_query.h", "hbn_math.h", "hbn_types.h", "hbn_host.h", "hbn_astar_lane.h", "hbn_snap.h")]
         if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
             os.makedirs(out, exist_ok=True)
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared",

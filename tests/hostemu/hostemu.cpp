@@ -13,6 +13,7 @@
 #include "hbn_host.h"
 #include "hbn_query.h"
 #include "hbn_astar_lane.h"
+#include "hbn_snap.h"
 
 using namespace hbn;
 
@@ -94,6 +95,31 @@ void emu_snap(void* h, const float* pts, const int* islands, long n, float* out_
   }
 }
 
+// The candidate-list findNearestPoly (hbn_snap.h: walk -> eval -> select), serially.
+void emu_snap_list(void* h, const float* pts, const int* islands, long n, float* out_pts,
+                   unsigned* out_refs, int* out_isl, long* out_ncand) {
+  Emu* e = static_cast<Emu*>(h);
+  std::vector<uint32_t> cand;
+  std::vector<float> d;
+  std::vector<SnapCandOut> co;
+  long total = 0;
+  for (long i = 0; i < n; ++i) {
+    cand.clear();
+    snapWalk(e->nav, pts + 3 * i, kExt, [&](uint32_t g) { cand.push_back(g); });
+    total += static_cast<long>(cand.size());
+    d.resize(cand.size());
+    co.resize(cand.size());
+    for (size_t c = 0; c < cand.size(); ++c)
+      d[c] = snapEval(e->nav, pts + 3 * i, islands ? islands[i] : -1, cand[c], &co[c]);
+    const uint32_t w = snapSelect(d.data(), 0, static_cast<uint32_t>(cand.size()));
+    const bool ok = w < cand.size();
+    for (int k = 0; k < 3; ++k) out_pts[3 * i + k] = ok ? co[w].cp[k] : NAN;
+    if (out_refs) out_refs[i] = ok ? e->nav.polys[cand[w]].ref : 0u;
+    if (out_isl) out_isl[i] = ok ? e->nav.polys[cand[w]].island : -1;
+  }
+  if (out_ncand) *out_ncand = total;
+}
+
 // out_info [n,8] like the oracle's ref_find_path_raw_batch
 void emu_find_path(void* h, const float* starts, const float* ends, long n, int cap, int fastFail,
                    float* out_dist, int* out_npts, float* out_pts, int max_pts,
@@ -133,15 +159,15 @@ void emu_find_path_lane(void* h, const float* starts, const float* ends, long n,
   Emu* e = static_cast<Emu*>(h);
   HostGroup grp;
   uint32_t q[2];
-  constexpr int TS = 63, LOGC = 8;
+  constexpr int TS = 63;
   const NavView& nav = e->nav;
   std::vector<char> scratch(laneScratchBytes(nav.numKeys) + 64, 0);
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(scratch.data()) + 15) & ~uintptr_t(15));
   std::vector<float> K(TS);
-  std::vector<uint16_t> S(TS), PC(1 << LOGC);
+  std::vector<uint16_t> S(TS);
   std::vector<uint32_t> ring(kMaxPathPolys);
-  LaneSearch<1, TS, LOGC> s{};
-  s.K = K.data(); s.S = S.data(); s.PC = PC.data();
+  LaneSearch<1, TS> s{};
+  s.K = K.data(); s.S = S.data();
   s.tab = reinterpret_cast<uint16_t*>(base);
   s.rec = base + laneTabBytes(nav.numKeys);
   s.G = reinterpret_cast<LaneHeapEnt*>(s.rec + kLaneRecBytes);

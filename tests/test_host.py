@@ -94,6 +94,15 @@ def test_hostemu_queries_match_oracle(name):
     oi_pts, oi_refs = pf.snap_island_batch(pts[:300], isl)
     emu.emu_snap(h, P(pts, f32p), P(isl, i32p), C.c_long(300), P(e_pts, f32p), P(e_refs, u32p), P(e_isl, i32p))
     assert (oi_refs == e_refs[:300]).all() and beq(oi_pts, e_pts[:300]).all()
+    # the candidate-list pipeline (hbn_snap.h) gives the same answers
+    ncand = C.c_long(0)
+    emu.emu_snap_list(h, P(pts, f32p), None, C.c_long(len(pts)), P(e_pts, f32p), P(e_refs, u32p), P(e_isl, i32p),
+                      C.byref(ncand))
+    assert (o_refs == e_refs).all() and (o_isl == e_isl).all() and beq(o_pts, e_pts).all()
+    assert ncand.value > len(pts) // 2
+    emu.emu_snap_list(h, P(pts, f32p), P(isl, i32p), C.c_long(300), P(e_pts, f32p), P(e_refs, u32p), P(e_isl, i32p),
+                      None)
+    assert (oi_refs == e_refs[:300]).all() and beq(oi_pts, e_pts[:300]).all()
     # find_path, exact status mode and the small tier with fast fail
     st, en = pts[:n].copy(), pts[n:].copy()
     en[200:300] = st[200:300] + rng.normal(0, 0.01, (100, 3)).astype(np.float32)
