@@ -24,15 +24,15 @@ template <int TS>
 __host__ __device__ constexpr size_t laneSharedBytes() { return static_cast<size_t>(TS) * 32 * 6; }
 
 // TS: heap entries per lane in shared memory; MINB: resident one-warp blocks per SM the
-// register allocation must allow.
-template <int TS, int MINB>
+// register allocation must allow; CH: links per load stage.
+template <int TS, int MINB, int CH>
 __global__ void __launch_bounds__(32, MINB) k_astar_lane(NavView nav, AStarGArgs a, LaneScratch sc) {
   constexpr uint32_t FULL = 0xffffffffu;
   extern __shared__ __align__(16) char smem[];
   const int lane = threadIdx.x;
   const uint32_t ltMask = (1u << lane) - 1u;
   const size_t slotId = static_cast<size_t>(blockIdx.x) * 32 + lane;
-  LaneSearch<32, TS> s;
+  LaneSearch<32, TS, CH> s;
   s.K = reinterpret_cast<float*>(smem) + lane;
   s.S = reinterpret_cast<uint16_t*>(smem + static_cast<size_t>(TS) * 32 * 4) + lane;
   s.G = reinterpret_cast<LaneHeapEnt*>(sc.heap + slotId * kLaneHeapBytes);

@@ -54,7 +54,6 @@ constexpr uint32_t kLaneSlotBits = 11;  // node index < 2048
 constexpr uint32_t kLaneSlotMask = (1u << kLaneSlotBits) - 1u;
 constexpr uint32_t kLaneGenMax = 31;    // generations 1..31, then the table is wiped
 constexpr uint32_t kLaneNoParent = 0x00ffffffu;
-constexpr int kLaneChunk = 4;           // links handled per load stage
 constexpr int kLaneHops = 2;            // corridor hops per step
 constexpr uint32_t kLaneClosedBit = 0x80000000u;  // sign bit of LaneRecA::cost
 constexpr uint32_t kLaneMaxExpansions = 1u << 18;  // >> any legal search (2048 nodes, re-opens)
@@ -128,11 +127,13 @@ HBN_HD void laneLoadLink(const LinkRec* p, LaneLinkLo& lo, LaneLinkHi& hi) {
 
 // HS: distance (in elements) between consecutive shared heap entries of this lane (32 on the
 // device, 1 in the host build); TS: heap entries kept in shared memory (odd, so that the
-// children 2i+1, 2i+2 of an entry are both on the same side and pair-aligned in global).
+// children 2i+1, 2i+2 of an entry are both on the same side and pair-aligned in global);
+// CH: links per load stage (registers vs. rounds).
 // step() contains warp collectives on the device: all 32 lanes of the warp must call it
 // together, whatever their mode.
-template <int HS, int TS>
+template <int HS, int TS, int CH>
 struct LaneSearch {
+  static constexpr int kLaneChunk = CH;  // links handled per load stage
   static_assert((TS & 1) == 1, "TS must be odd");
   // memory of this lane
   float* K;        // shared: heap keys
@@ -421,6 +422,11 @@ struct LaneSearch {
         size--;
         heapPopSift(size);
         recA(bslot)->cost = laneSetClosed(ba.cost);
+#if defined(__CUDA_ARCH__)
+        // The next pop takes the new top unless one of this poly's neighbours (whose records are
+        // written below, so they are in L2) overtakes it: pull its record into L2 meanwhile.
+        if (size > 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + static_cast<size_t>(S[0]) * 32));
+#endif
         bestG = bb.poly;
         if (bestG == endG) {
           lastBest = bslot;

@@ -88,7 +88,7 @@ struct hbn_navmesh {
                         // 1 = one query per LANE (k_astar_lane, hbn_astar_lane.cuh)
   int blocksFpG = 0;
   // lane-per-query search: per-lane node table + records in HBM, allocated on first use
-  DevBuf snapCnt, snapOff, snapG, snapQ, snapD, snapOut, snapTmp, snapTodo;  // candidate-list snap (hbn_snap.cuh)
+  DevBuf snapCnt, snapOff, snapG, snapQ, snapD, snapOut, snapBest, snapTmp, snapTodo;  // candidate-list snap (hbn_snap.cuh)
   DevBuf wsLane, laneGen;
   int blocksFpLane = 0;
   int laneCfg = 0;      // HBN_LANE_CFG: shared heap levels / warps per SM variant (tuning)
@@ -145,14 +145,14 @@ int laneScratch(hbn_navmesh* nm, cudaStream_t st, LaneScratch* out) {
   return HBN_OK;
 }
 
-// lane-per-query search variants: {heap entries in shared, resident warps per SM}
+// lane-per-query search variants: {heap entries in shared, resident warps per SM, links per load stage}
 const void* laneKernel(int cfg, size_t* shared) {
   switch (cfg) {
-    case 1: *shared = laneSharedBytes<63>(); return reinterpret_cast<const void*>(&k_astar_lane<63, 12>);
-    case 2: *shared = laneSharedBytes<31>(); return reinterpret_cast<const void*>(&k_astar_lane<31, 16>);
-    case 3: *shared = laneSharedBytes<127>(); return reinterpret_cast<const void*>(&k_astar_lane<127, 9>);
-    case 4: *shared = laneSharedBytes<255>(); return reinterpret_cast<const void*>(&k_astar_lane<255, 4>);
-    default: *shared = laneSharedBytes<kLaneTS>(); return reinterpret_cast<const void*>(&k_astar_lane<kLaneTS, kLaneMinB>);
+    case 1: *shared = laneSharedBytes<63>(); return reinterpret_cast<const void*>(&k_astar_lane<63, 17, 3>);
+    case 2: *shared = laneSharedBytes<31>(); return reinterpret_cast<const void*>(&k_astar_lane<31, 20, 2>);
+    case 3: *shared = laneSharedBytes<63>(); return reinterpret_cast<const void*>(&k_astar_lane<63, 18, 2>);
+    case 4: *shared = laneSharedBytes<31>(); return reinterpret_cast<const void*>(&k_astar_lane<31, 17, 3>);
+    default: *shared = laneSharedBytes<kLaneTS>(); return reinterpret_cast<const void*>(&k_astar_lane<kLaneTS, kLaneMinB, 4>);
   }
 }
 
@@ -195,6 +195,7 @@ int finishCreate(HostNavMesh& mesh, const int32_t* islands, int device, hbn_navm
   up(f.tiles, &v.tiles);
   up(f.detTris, &v.detTris);
   up(f.detVerts, &v.detVerts);
+  up(f.polyBox, &v.polyBox);
   up(f.gridStart, &v.gridStart);
   up(f.tileOrder, &v.tileOrder);
   up(f.randEntries, &v.randEntries);
@@ -304,7 +305,7 @@ struct DeviceGuard {
   ~DeviceGuard() { cudaSetDevice(prev); }
 };
 
-constexpr int64_t kSnapChunk = 1 << 19;   // points per pass of the candidate-list pipeline
+constexpr int64_t kSnapChunk = 1 << 18;   // points per pass of the candidate-list pipeline
 constexpr int64_t kSnapSmall = 4096;      // below this one k_snap<8> launch is cheaper than five kernels + a scan
 
 // projectToPoly for n points.  Large batches: count -> scan -> fill -> eval -> select
@@ -332,7 +333,7 @@ int snapLaunch(hbn_navmesh* nm, const float* pts, const int32_t* islands, int64_
   int rc;
   if ((rc = nm->snapCnt.ensure((cmax + 1) * 4)) || (rc = nm->snapOff.ensure((cmax + 1) * 4)) ||
       (rc = nm->snapG.ensure(cap * 4)) || (rc = nm->snapQ.ensure(cap * 4)) || (rc = nm->snapD.ensure(cap * 4)) ||
-      (rc = nm->snapOut.ensure(cap * sizeof(SnapCandOut))) || (rc = nm->snapTmp.ensure(tmpBytes)) ||
+      (rc = nm->snapOut.ensure(cap * 4)) || (rc = nm->snapBest.ensure(cmax * 4)) || (rc = nm->snapTmp.ensure(tmpBytes)) ||
       (rc = nm->snapTodo.ensure(16)))
     return rc;
   uint32_t* cnt = static_cast<uint32_t*>(nm->snapCnt.p);
@@ -340,7 +341,8 @@ int snapLaunch(hbn_navmesh* nm, const float* pts, const int32_t* islands, int64_
   uint32_t* cg = static_cast<uint32_t*>(nm->snapG.p);
   uint32_t* cq = static_cast<uint32_t*>(nm->snapQ.p);
   float* cd = static_cast<float*>(nm->snapD.p);
-  SnapCandOut* co = static_cast<SnapCandOut*>(nm->snapOut.p);
+  float* clb = static_cast<float*>(nm->snapOut.p);
+  uint32_t* best = static_cast<uint32_t*>(nm->snapBest.p);
   uint32_t* todo = static_cast<uint32_t*>(nm->snapTodo.p);
   for (int64_t c0 = 0; c0 < n; c0 += kSnapChunk) {
     const int64_t cn = std::min(kSnapChunk, n - c0);
@@ -348,12 +350,13 @@ int snapLaunch(hbn_navmesh* nm, const float* pts, const int32_t* islands, int64_
     const int32_t* isl = islands ? islands + c0 : nullptr;
     const unsigned pb = static_cast<unsigned>((cn + 255) / 256);
     CK(cudaMemsetAsync(cnt + cn, 0, 4, st));
-    k_snap_count<<<pb, 256, 0, st>>>(nm->view, p, cn, cnt);
+    k_snap_count<<<pb, 256, 0, st>>>(nm->view, p, cn, cnt, best);
     CK(cub::DeviceScan::ExclusiveSum(nm->snapTmp.p, tmpBytes, cnt, off, static_cast<int>(cn + 1), st));
-    k_snap_fill<<<pb, 256, 0, st>>>(nm->view, p, cn, off, static_cast<uint32_t>(cap), cg, cq);
-    k_snap_eval<<<static_cast<unsigned>(nm->smCount * 16), 256, 0, st>>>(nm->view, p, isl, cn, off,
-                                                                        static_cast<uint32_t>(cap), cg, cq, cd, co);
-    k_snap_select<<<pb, 256, 0, st>>>(nm->view, p, cn, off, static_cast<uint32_t>(cap), cg, cd, co,
+    k_snap_fill<<<pb, 256, 0, st>>>(nm->view, p, cn, off, static_cast<uint32_t>(cap), cg, cq, clb);
+    for (int pass = 0; pass < 2; ++pass)
+      k_snap_eval<<<static_cast<unsigned>(nm->smCount * 16), 256, 0, st>>>(
+          nm->view, p, isl, cn, off, static_cast<uint32_t>(cap), cg, cq, clb, pass, cd, best);
+    k_snap_select<<<pb, 256, 0, st>>>(nm->view, p, isl, cn, off, static_cast<uint32_t>(cap), cg, cd,
                                       out_pts ? out_pts + 3 * c0 : nullptr, out_g ? out_g + c0 : nullptr,
                                       out_refs ? out_refs + c0 : nullptr, out_isl ? out_isl + c0 : nullptr,
                                       out_nav ? out_nav + c0 : nullptr, maxYDelta, todo);
@@ -363,7 +366,7 @@ int snapLaunch(hbn_navmesh* nm, const float* pts, const int32_t* islands, int64_
         nm->view, p, isl, cn, out_pts ? out_pts + 3 * c0 : nullptr, out_g ? out_g + c0 : nullptr,
         out_refs ? out_refs + c0 : nullptr, out_isl ? out_isl + c0 : nullptr, out_nav ? out_nav + c0 : nullptr,
         maxYDelta, todo);
-    nm->launches += 7;  // 5 kernels here + cub's scan (2 kernels)
+    nm->launches += 8;  // 6 kernels here + cub's scan (2 kernels)
     CK(cudaGetLastError());
   }
   return HBN_OK;
@@ -421,7 +424,7 @@ void hbn_navmesh_destroy(hbn_navmesh_t nm) {
                     &nm->lists, &nm->counters, &nm->wsL, &nm->wsFp, &nm->io, &nm->work, &nm->mgDist,
                     &nm->mgBounds, &nm->mgOrder, &nm->mgEnd, &nm->fpCls, &nm->fpWork, &nm->fpStat,
                     &nm->fpLen, &nm->fpCorr, &nm->fpBucket, &nm->wsFpG, &nm->wsLane, &nm->laneGen, &nm->snapCnt, &nm->snapOff,
-                    &nm->snapG, &nm->snapQ, &nm->snapD, &nm->snapOut, &nm->snapTmp, &nm->snapTodo})
+                    &nm->snapG, &nm->snapQ, &nm->snapD, &nm->snapOut, &nm->snapBest, &nm->snapTmp, &nm->snapTodo})
     b->release();
   if (nm->pinned) cudaFreeHost(nm->pinned);
   if (nm->faultHost) cudaFreeHost(nm->faultHost);

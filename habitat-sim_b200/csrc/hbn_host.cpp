@@ -670,6 +670,26 @@ void HostNavMesh::flatten(FlatNav& out) const {
       pr.linkCount = static_cast<uint8_t>(std::min<uint32_t>(cnt, 255u));
     }
   }
+  // bounds of each poly's vertices and detail vertices
+  out.polyBox.assign(out.polys.size() * 8, 0.f);
+  for (size_t g = 0; g < out.polys.size(); ++g) {
+    const PolyRec& pr = out.polys[g];
+    float* b = &out.polyBox[g * 8];
+    for (int k = 0; k < 3; ++k) { b[k] = pr.nv ? pr.v[k] : 0.f; b[4 + k] = b[k]; }
+    auto grow = [&](const float* v) {
+      for (int k = 0; k < 3; ++k) {
+        b[k] = std::min(b[k], v[k]);
+        b[4 + k] = std::max(b[4 + k], v[k]);
+      }
+    };
+    for (int j = 1; j < pr.nv; ++j) grow(&pr.v[3 * j]);
+    for (int t = 0; t < pr.detTriCount; ++t) {
+      const unsigned char* tri = &out.detTris[(static_cast<size_t>(pr.detTriBase) + t) * 4];
+      for (int k = 0; k < 3; ++k)
+        if (tri[k] >= pr.nv) grow(&out.detVerts[(static_cast<size_t>(pr.detVertBase) + (tri[k] - pr.nv)) * 3]);
+    }
+    // layout: min xyz at [0..2], max xyz at [4..6]
+  }
   // pass 2: neighbour windows + filter bits (needs every poly's link window), and the dense
   // enumeration of A* node keys (poly, crossSide): crossSide 0 of every poly, plus the sides
   // through which tile-border links enter it
@@ -769,6 +789,7 @@ NavView FlatNav::view() const {
   v.tiles = tiles.data();
   v.detTris = detTris.data();
   v.detVerts = detVerts.data();
+  v.polyBox = polyBox.data();
   v.gridStart = gridStart.data();
   v.tileOrder = tileOrder.data();
   v.randEntries = randEntries.data();

@@ -92,6 +92,7 @@ struct FlatNav {
   std::vector<TileRec> tiles;
   std::vector<uint8_t> detTris;
   std::vector<float> detVerts;
+  std::vector<float> polyBox;  // 8 floats per poly: min xyz, max xyz (poly + detail vertices), 2 pad
   std::vector<uint32_t> gridStart, tileOrder;
   std::vector<RandEntry> randEntries;
   std::vector<uint32_t> tileIslStart, tileIslWin, tileIslCnt;

@@ -9,7 +9,8 @@
 // lanes diverged (measured: 8 of 32 threads active, 9.6 k warp instructions per point).
 // So the work is cut where its shape changes:
 //   1. snapWalk      one thread per POINT: the BV walk, counting / emitting candidates
-//   2. snapEval      one thread per CANDIDATE: closest point + the reference's distance
+//   2. snapEval      one thread per CANDIDATE: closest point + the reference's distance; first
+//                    the candidates whose lower bound is 0, then those that may still win
 //   3. snapSelect    one thread per POINT: first strict minimum in visit order
 // with the candidates of all points in one compact array (offsets from a prefix sum).
 #pragma once
@@ -18,7 +19,35 @@
 namespace hbn {
 
 // The polys findNearestPoly would hand to process(), in the reference's order.
-// emit(g) is called once per candidate; returns the number of candidates.
+// emit(g, lb) is called once per candidate; returns the number of candidates.
+// lb is a LOWER BOUND of the distance process() will compute for the candidate, from the
+// bounds of the poly's vertices and detail vertices (NavView::polyBox; the BV boxes will not do:
+// their y range is not the poly's): 0 if the point can be over the poly within walkableClimb.  It
+// lets snapEval skip candidates that cannot win -- on a multi-storey mesh the +-4 m pick box
+// collects the polys of the storeys above and below, two thirds of all candidates.
+HBN_HD float snapLowerBound(const NavView& nav, const float* c, uint32_t g, float climb) {
+#if defined(__CUDA_ARCH__)
+  const float4 lo = __ldg(reinterpret_cast<const float4*>(nav.polyBox) + 2 * static_cast<size_t>(g));
+  const float4 hi = __ldg(reinterpret_cast<const float4*>(nav.polyBox) + 2 * static_cast<size_t>(g) + 1);
+  const float bmin[3] = {lo.x, lo.y, lo.z}, bmax[3] = {hi.x, hi.y, hi.z};
+#else
+  const float* bmin = nav.polyBox + 8 * static_cast<size_t>(g);
+  const float* bmax = bmin + 4;
+#endif
+  const float pad = 1e-3f, padY = 1e-3f;
+  float dx = 0.f, dz = 0.f, dy = 0.f;
+  if (c[0] < bmin[0] - pad) dx = (bmin[0] - pad) - c[0];
+  else if (c[0] > bmax[0] + pad) dx = c[0] - (bmax[0] + pad);
+  if (c[2] < bmin[2] - pad) dz = (bmin[2] - pad) - c[2];
+  else if (c[2] > bmax[2] + pad) dz = c[2] - (bmax[2] + pad);
+  if (c[1] < bmin[1] - padY) dy = (bmin[1] - padY) - c[1];
+  else if (c[1] > bmax[1] + padY) dy = c[1] - (bmax[1] + padY);
+  const float dxz = dx * dx + dz * dz;
+  if (dxz > 0.f) return dxz + dy * dy;  // outside the poly in xz: plain 3D distance
+  const float e = dy - climb;           // possibly over the poly: (|dy| - climb)^2
+  return e > 0.f ? e * e : 0.f;
+}
+
 template <class F>
 HBN_HD uint32_t snapWalk(const NavView& nav, const float* center, const float* halfExt, F&& emit) {
   if (!vfinite(center) || !vfinite(halfExt)) return 0;  // DQ.cpp:928-933
@@ -67,7 +96,7 @@ HBN_HD uint32_t snapWalk(const NavView& nav, const float* center, const float* h
             const bool ov = overlapQuant(bmin, bmax, n.bmin, n.bmax);
             const bool leaf = n.i >= 0;
             if (leaf && ov && (n.i & kBvFailBit) == 0) {
-              emit(static_cast<uint32_t>(n.i));
+              emit(static_cast<uint32_t>(n.i), snapLowerBound(nav, center, static_cast<uint32_t>(n.i), tr.walkableClimb));
               count++;
             }
             if (ov || leaf) node++;
@@ -90,7 +119,7 @@ HBN_HD uint32_t snapWalk(const NavView& nav, const float* center, const float* h
             bool ov = true;
             for (int k = 0; k < 3; ++k) ov = (qmin[k] > pmax[k] || qmax[k] < pmin[k]) ? false : ov;
             if (ov) {
-              emit(g);
+              emit(g, snapLowerBound(nav, center, g, tr.walkableClimb));
               count++;
             }
           }
@@ -101,10 +130,13 @@ HBN_HD uint32_t snapWalk(const NavView& nav, const float* center, const float* h
   return count;
 }
 
-struct HBN_ALIGN(16) SnapCandOut {
+struct SnapCandOut {
   float cp[3];
   uint32_t over;
 };
+// May a candidate with lower bound lb still win against the best distance seen so far?
+// (margins: the bound and the distances are rounded float results)
+HBN_HD bool snapMayWin(float lb, float best) { return lb * 0.999f - 1e-6f <= best; }
 
 // dtFindNearestPolyQuery::process for one candidate (DQ.cpp:655-676): the distance it would
 // compare, or a negative value if the island filter (PF.cpp:1729-1751) hides the poly.
@@ -127,7 +159,7 @@ HBN_HD float snapEval(const NavView& nav, const float* center, int islandFilter,
 
 // "if (d < m_nearestDistanceSqr)" over the candidates in visit order (DQ.cpp:670).
 // Returns the index of the winner in [begin, end) or end if none.  (A NaN distance never wins,
-// as in the reference.)
+// as in the reference; negative = hidden by the island filter or skipped by its lower bound.)
 HBN_HD uint32_t snapSelect(const float* d, uint32_t begin, uint32_t end) {
   float best = kFltMax;
   uint32_t win = end;

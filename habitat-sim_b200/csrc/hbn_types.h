@@ -126,6 +126,9 @@ struct NavView {
   const TileRec* tiles;
   const unsigned char* detTris;  // 4 bytes per triangle
   const float* detVerts;         // 3 floats per vertex
+  // bounds of everything closestPointOnPoly can return for a poly (poly + detail vertices):
+  // 8 floats per poly, min xyz | max xyz | 2 pad.  Only used to skip hopeless candidates.
+  const float* polyBox;
   // tile grid lookup (dtNavMesh::getTilesAt, DetourNavMesh.cpp:1120-1140): dense grid over
   // [gridMinX, gridMinX+gridW) x [gridMinY, gridMinY+gridH); cell -> window of tileOrder[]
   const uint32_t* gridStart;     // gridW*gridH + 1 entries

@@ -100,24 +100,35 @@ void emu_snap_list(void* h, const float* pts, const int* islands, long n, float*
                    unsigned* out_refs, int* out_isl, long* out_ncand) {
   Emu* e = static_cast<Emu*>(h);
   std::vector<uint32_t> cand;
-  std::vector<float> d;
-  std::vector<SnapCandOut> co;
-  long total = 0;
+  std::vector<float> lb, d;
+  long total = 0, evaluated = 0;
   for (long i = 0; i < n; ++i) {
     cand.clear();
-    snapWalk(e->nav, pts + 3 * i, kExt, [&](uint32_t g) { cand.push_back(g); });
+    lb.clear();
+    snapWalk(e->nav, pts + 3 * i, kExt, [&](uint32_t g, float b) { cand.push_back(g); lb.push_back(b); });
     total += static_cast<long>(cand.size());
-    d.resize(cand.size());
-    co.resize(cand.size());
-    for (size_t c = 0; c < cand.size(); ++c)
-      d[c] = snapEval(e->nav, pts + 3 * i, islands ? islands[i] : -1, cand[c], &co[c]);
+    d.assign(cand.size(), -1.f);
+    const int isl = islands ? islands[i] : -1;
+    SnapCandOut o;
+    float best = kFltMax;
+    for (int pass = 0; pass < 2; ++pass)  // as k_snap_eval
+      for (size_t c = 0; c < cand.size(); ++c) {
+        if ((lb[c] == 0.f) != (pass == 0)) continue;
+        if (pass == 1 && !snapMayWin(lb[c], best)) continue;
+        d[c] = snapEval(e->nav, pts + 3 * i, isl, cand[c], &o);
+        evaluated++;
+        if (pass == 0 && d[c] >= 0.f && d[c] < best) best = d[c];
+        // the bound must never exceed the distance it bounds
+        if (d[c] >= 0.f && lb[c] * 0.999f - 1e-6f > d[c]) { fprintf(stderr, "snap lower bound violated: pt %ld cand %zu g %u lb %g d %g over %u center %g %g %g cp %g %g %g\n", i, c, cand[c], lb[c], d[c], o.over, pts[3*i], pts[3*i+1], pts[3*i+2], o.cp[0], o.cp[1], o.cp[2]); abort(); }
+      }
     const uint32_t w = snapSelect(d.data(), 0, static_cast<uint32_t>(cand.size()));
     const bool ok = w < cand.size();
-    for (int k = 0; k < 3; ++k) out_pts[3 * i + k] = ok ? co[w].cp[k] : NAN;
+    if (ok) snapEval(e->nav, pts + 3 * i, isl, cand[w], &o);
+    for (int k = 0; k < 3; ++k) out_pts[3 * i + k] = ok ? o.cp[k] : NAN;
     if (out_refs) out_refs[i] = ok ? e->nav.polys[cand[w]].ref : 0u;
     if (out_isl) out_isl[i] = ok ? e->nav.polys[cand[w]].island : -1;
   }
-  if (out_ncand) *out_ncand = total;
+  if (out_ncand) { out_ncand[0] = total; out_ncand[1] = evaluated; }
 }
 
 // out_info [n,8] like the oracle's ref_find_path_raw_batch
@@ -166,7 +177,7 @@ void emu_find_path_lane(void* h, const float* starts, const float* ends, long n,
   std::vector<float> K(TS);
   std::vector<uint16_t> S(TS);
   std::vector<uint32_t> ring(kMaxPathPolys);
-  LaneSearch<1, TS> s{};
+  LaneSearch<1, TS, 3> s{};
   s.K = K.data(); s.S = S.data();
   s.tab = reinterpret_cast<uint16_t*>(base);
   s.rec = base + laneTabBytes(nav.numKeys);

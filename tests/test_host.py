@@ -95,11 +95,11 @@ def test_hostemu_queries_match_oracle(name):
     emu.emu_snap(h, P(pts, f32p), P(isl, i32p), C.c_long(300), P(e_pts, f32p), P(e_refs, u32p), P(e_isl, i32p))
     assert (oi_refs == e_refs[:300]).all() and beq(oi_pts, e_pts[:300]).all()
     # the candidate-list pipeline (hbn_snap.h) gives the same answers
-    ncand = C.c_long(0)
+    ncand = (C.c_long * 2)()
     emu.emu_snap_list(h, P(pts, f32p), None, C.c_long(len(pts)), P(e_pts, f32p), P(e_refs, u32p), P(e_isl, i32p),
-                      C.byref(ncand))
+                      ncand)
     assert (o_refs == e_refs).all() and (o_isl == e_isl).all() and beq(o_pts, e_pts).all()
-    assert ncand.value > len(pts) // 2
+    assert ncand[0] > len(pts) // 2 and ncand[1] <= ncand[0]
     emu.emu_snap_list(h, P(pts, f32p), P(isl, i32p), C.c_long(300), P(e_pts, f32p), P(e_refs, u32p), P(e_isl, i32p),
                       None)
     assert (oi_refs == e_refs[:300]).all() and beq(oi_pts, e_pts[:300]).all()

@@ -3,7 +3,7 @@ usage: python tools/sweep_fp.py [queries]"""
 import json, os, subprocess, sys
 n = sys.argv[1] if len(sys.argv) > 1 else "400000"
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-variants = (("lane", None), ("lane:1", None), ("lane:2", None), ("lane:3", None), ("lane:4", None), ("lane", "8"))
+variants = (("lane", None), ("lane:1", None), ("lane:2", None), ("lane:3", None), ("lane:4", None))
 if os.environ.get("SWEEP_ALL"):
     variants += (("8", None), ("32", None), ("4", None))
 for g, bps in variants:
