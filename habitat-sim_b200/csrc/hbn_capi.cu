@@ -333,7 +333,7 @@ int snapLaunch(hbn_navmesh* nm, const float* pts, const int32_t* islands, int64_
   int rc;
   if ((rc = nm->snapCnt.ensure((cmax + 1) * 4)) || (rc = nm->snapOff.ensure((cmax + 1) * 4)) ||
       (rc = nm->snapG.ensure(cap * 4)) || (rc = nm->snapQ.ensure(cap * 4)) || (rc = nm->snapD.ensure(cap * 4)) ||
-      (rc = nm->snapOut.ensure(cap * 4)) || (rc = nm->snapBest.ensure(cmax * 4)) || (rc = nm->snapTmp.ensure(tmpBytes)) ||
+      (rc = nm->snapOut.ensure(cap * 4)) || (rc = nm->snapBest.ensure(cmax * 8)) || (rc = nm->snapTmp.ensure(tmpBytes)) ||
       (rc = nm->snapTodo.ensure(16)))
     return rc;
   uint32_t* cnt = static_cast<uint32_t*>(nm->snapCnt.p);
@@ -343,6 +343,7 @@ int snapLaunch(hbn_navmesh* nm, const float* pts, const int32_t* islands, int64_
   float* cd = static_cast<float*>(nm->snapD.p);
   float* clb = static_cast<float*>(nm->snapOut.p);
   uint32_t* best = static_cast<uint32_t*>(nm->snapBest.p);
+  float* rxz = reinterpret_cast<float*>(best + cmax);
   uint32_t* todo = static_cast<uint32_t*>(nm->snapTodo.p);
   for (int64_t c0 = 0; c0 < n; c0 += kSnapChunk) {
     const int64_t cn = std::min(kSnapChunk, n - c0);
@@ -350,9 +351,9 @@ int snapLaunch(hbn_navmesh* nm, const float* pts, const int32_t* islands, int64_
     const int32_t* isl = islands ? islands + c0 : nullptr;
     const unsigned pb = static_cast<unsigned>((cn + 255) / 256);
     CK(cudaMemsetAsync(cnt + cn, 0, 4, st));
-    k_snap_count<<<pb, 256, 0, st>>>(nm->view, p, cn, cnt, best);
+    k_snap_count<<<pb, 256, 0, st>>>(nm->view, p, isl, cn, cnt, best, rxz);
     CK(cub::DeviceScan::ExclusiveSum(nm->snapTmp.p, tmpBytes, cnt, off, static_cast<int>(cn + 1), st));
-    k_snap_fill<<<pb, 256, 0, st>>>(nm->view, p, cn, off, static_cast<uint32_t>(cap), cg, cq, clb);
+    k_snap_fill<<<pb, 256, 0, st>>>(nm->view, p, cn, off, static_cast<uint32_t>(cap), rxz, cg, cq, clb);
     for (int pass = 0; pass < 2; ++pass)
       k_snap_eval<<<static_cast<unsigned>(nm->smCount * 16), 256, 0, st>>>(
           nm->view, p, isl, cn, off, static_cast<uint32_t>(cap), cg, cq, clb, pass, cd, best);

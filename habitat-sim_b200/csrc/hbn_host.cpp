@@ -690,6 +690,28 @@ void HostNavMesh::flatten(FlatNav& out) const {
     }
     // layout: min xyz at [0..2], max xyz at [4..6]
   }
+  // do the BV leaf boxes cover their polys in xz?  (their y range does not, see hbn_snap.h)
+  // Leaves behind the end of the tree (index >= the root's escape) are marked loose instead.
+  out.bvXzTight = 1;
+  for (const TileRec& tr : out.tiles) {
+    if (!tr.bvCount) continue;
+    const float inv = 1.0f / tr.bvQuantFactor;
+    const int32_t rootI = out.bv[tr.bvStart].i;
+    const uint32_t treeSize = rootI < 0 ? static_cast<uint32_t>(-rootI) : 1u;
+    for (uint32_t b = 0; b < tr.bvCount; ++b) {
+      BvRec& n = out.bv[tr.bvStart + b];
+      if (n.i < 0) continue;
+      if (b >= treeSize) {
+        n.i |= kBvLooseBit;
+        continue;
+      }
+      const float* box = &out.polyBox[static_cast<size_t>(n.i & kBvIndexMask) * 8];
+      for (int k = 0; k < 3; k += 2) {
+        const float lo = tr.bmin[k] + n.bmin[k] * inv, hi = tr.bmin[k] + (n.bmax[k] + 1) * inv;
+        if (box[k] < lo - 1e-3f || box[4 + k] > hi + 1e-3f) out.bvXzTight = 0;
+      }
+    }
+  }
   // pass 2: neighbour windows + filter bits (needs every poly's link window), and the dense
   // enumeration of A* node keys (poly, crossSide): crossSide 0 of every poly, plus the sides
   // through which tile-border links enter it
@@ -805,6 +827,7 @@ NavView FlatNav::view() const {
   v.numTiles = static_cast<uint32_t>(tiles.size());
   v.numLinks = static_cast<uint32_t>(links.size());
   v.numKeys = numKeys;
+  v.bvXzTight = bvXzTight;
   v.polyBits = polyBits; v.tileBits = tileBits; v.saltBits = saltBits;
   v.numIslands = static_cast<int32_t>(islandRadius.size());
   return v;

@@ -100,6 +100,7 @@ struct FlatNav {
   int32_t gridMinX = 0, gridMinY = 0, gridW = 0, gridH = 0;
   DtNavMeshParams params{};
   uint32_t polyBits = 0, tileBits = 0, saltBits = 0;
+  int32_t bvXzTight = 0;  // see NavView::bvXzTight
   uint32_t numKeys = 0;  // A* node keys (poly, crossSide), see LinkRec::neiKey
   // IslandSystem products (PathFinder.cpp:167-207,1045-1085)
   std::vector<float> islandRadius, islandArea;

@@ -338,7 +338,7 @@ HBN_HD Nearest findNearestPoly(const NavView& nav, const G& grp, const float* ce
               isSkip = !ov && !leaf;
               esc = -n.i;
               isCand = ov && leaf && ((n.i & kBvFailBit) == 0);
-              candG = static_cast<uint32_t>(n.i);
+              candG = static_cast<uint32_t>(n.i & kBvIndexMask);
             } else {
               // no BV tree: linear scan with float bounds, DQ.cpp:806-842
               const uint32_t g = tr.polyStart + idx;

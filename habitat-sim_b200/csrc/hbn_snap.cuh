@@ -12,20 +12,26 @@ namespace hbn {
 
 constexpr int kSnapAvgCap = 128;  // candidate scratch: this many entries per point of a chunk
 
-// cnt[q] = number of candidates of point q; best[q] = FLT_MAX
-__global__ void __launch_bounds__(256) k_snap_count(NavView nav, const float* __restrict__ pts, int64_t n,
-                                                    uint32_t* __restrict__ cnt, uint32_t* __restrict__ best) {
+// rxz[q] = xz half-extent of the walk (snapRadius); cnt[q] = number of candidates of point q;
+// best[q] = FLT_MAX
+__global__ void __launch_bounds__(256) k_snap_count(NavView nav, const float* __restrict__ pts,
+                                                    const int32_t* __restrict__ islands, int64_t n,
+                                                    uint32_t* __restrict__ cnt, uint32_t* __restrict__ best,
+                                                    float* __restrict__ rxz) {
   const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (q >= n) return;
   const float c[3] = {pts[3 * q], pts[3 * q + 1], pts[3 * q + 2]};
   const float ext[3] = {2.f, 4.f, 2.f};  // polyPickExt, PF.cpp:134
-  cnt[q] = snapWalk(nav, c, ext, [](uint32_t, float) {});
+  const float r = snapRadius(nav, c, ext, islands ? islands[q] : -1);
+  rxz[q] = r;
+  cnt[q] = snapWalk(nav, c, ext, r, [](uint32_t, float) {});
   best[q] = 0x7f7fffffu;
 }
 
 // off[] = exclusive prefix sum of cnt[] (off[n] = total).  Nothing happens if the total exceeds cap.
 __global__ void __launch_bounds__(256) k_snap_fill(NavView nav, const float* __restrict__ pts, int64_t n,
                                                    const uint32_t* __restrict__ off, uint32_t cap,
+                                                   const float* __restrict__ rxz,
                                                    uint32_t* __restrict__ candG, uint32_t* __restrict__ candQ,
                                                    float* __restrict__ candLb) {
   const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -33,7 +39,7 @@ __global__ void __launch_bounds__(256) k_snap_fill(NavView nav, const float* __r
   const float c[3] = {pts[3 * q], pts[3 * q + 1], pts[3 * q + 2]};
   const float ext[3] = {2.f, 4.f, 2.f};
   uint32_t w = off[q];
-  snapWalk(nav, c, ext, [&](uint32_t g, float lb) {
+  snapWalk(nav, c, ext, rxz[q], [&](uint32_t g, float lb) {
     candG[w] = g;
     candQ[w] = static_cast<uint32_t>(q);
     candLb[w] = lb;

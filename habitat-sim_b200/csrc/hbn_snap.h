@@ -48,13 +48,18 @@ HBN_HD float snapLowerBound(const NavView& nav, const float* c, uint32_t g, floa
   return e > 0.f ? e * e : 0.f;
 }
 
+//
+// rxz <= halfExt[0], halfExt[2] narrows the box in x and z.  The walk then visits a subset of the
+// reference's candidates in the same relative order; snapRadius() picks rxz so that the subset
+// still holds every candidate that can win.
 template <class F>
-HBN_HD uint32_t snapWalk(const NavView& nav, const float* center, const float* halfExt, F&& emit) {
+HBN_HD uint32_t snapWalk(const NavView& nav, const float* center, const float* halfExt, float rxz, F&& emit) {
   if (!vfinite(center) || !vfinite(halfExt)) return 0;  // DQ.cpp:928-933
   float qmin[3], qmax[3];
   for (int k = 0; k < 3; ++k) {
-    qmin[k] = center[k] - halfExt[k];
-    qmax[k] = center[k] + halfExt[k];
+    const float h = (k == 1) ? halfExt[k] : rxz;
+    qmin[k] = center[k] - h;
+    qmax[k] = center[k] + h;
   }
   // calcTileLoc, DN.cpp:1191-1195
   int minx = static_cast<int>(floorf((qmin[0] - nav.orig[0]) / nav.tileWidth));
@@ -73,14 +78,18 @@ HBN_HD uint32_t snapWalk(const NavView& nav, const float* center, const float* h
       for (uint32_t c = c0; c < c1; ++c) {
         const TileRec& tr = nav.tiles[nav.tileOrder[c]];
         if (tr.bvCount) {
-          // quantised query box, DQ.cpp:749-765
-          uint16_t bmin[3], bmax[3];
+          // quantised query box, DQ.cpp:749-765; [0] = the (narrowed) box of this walk, [1] = the
+          // reference's full box, which decides for the loose leaves behind the tree
+          uint16_t bmin[2][3], bmax[2][3];
           const float qfac = tr.bvQuantFactor;
           for (int k = 0; k < 3; ++k) {
-            const float mn = fclamp(qmin[k], tr.bmin[k], tr.bmax[k]) - tr.bmin[k];
-            const float mx = fclamp(qmax[k], tr.bmin[k], tr.bmax[k]) - tr.bmin[k];
-            bmin[k] = static_cast<uint16_t>(static_cast<uint16_t>(static_cast<int>(qfac * mn)) & 0xfffe);
-            bmax[k] = static_cast<uint16_t>(static_cast<uint16_t>(static_cast<int>(qfac * mx + 1)) | 1);
+            const float lo[2] = {qmin[k], center[k] - halfExt[k]}, hi[2] = {qmax[k], center[k] + halfExt[k]};
+            for (int b = 0; b < 2; ++b) {
+              const float mn = fclamp(lo[b], tr.bmin[k], tr.bmax[k]) - tr.bmin[k];
+              const float mx = fclamp(hi[b], tr.bmin[k], tr.bmax[k]) - tr.bmin[k];
+              bmin[b][k] = static_cast<uint16_t>(static_cast<uint16_t>(static_cast<int>(qfac * mn)) & 0xfffe);
+              bmax[b][k] = static_cast<uint16_t>(static_cast<uint16_t>(static_cast<int>(qfac * mx + 1)) | 1);
+            }
           }
           // DQ.cpp:768-800: pre-order array with escape indices
           const BvRec* node = &nav.bv[tr.bvStart];
@@ -93,10 +102,12 @@ HBN_HD uint32_t snapWalk(const NavView& nav, const float* center, const float* h
 #else
             const BvRec n = *node;
 #endif
-            const bool ov = overlapQuant(bmin, bmax, n.bmin, n.bmax);
             const bool leaf = n.i >= 0;
+            const int which = (leaf && (n.i & kBvLooseBit) != 0) ? 1 : 0;
+            const bool ov = overlapQuant(bmin[which], bmax[which], n.bmin, n.bmax);
             if (leaf && ov && (n.i & kBvFailBit) == 0) {
-              emit(static_cast<uint32_t>(n.i), snapLowerBound(nav, center, static_cast<uint32_t>(n.i), tr.walkableClimb));
+              const uint32_t g = static_cast<uint32_t>(n.i & kBvIndexMask);
+              emit(g, snapLowerBound(nav, center, g, tr.walkableClimb));
               count++;
             }
             if (ov || leaf) node++;
@@ -128,6 +139,33 @@ HBN_HD uint32_t snapWalk(const NavView& nav, const float* center, const float* h
     }
   }
   return count;
+}
+
+// xz half-extent that is enough for the walk of a point (<= halfExt[0]).
+// If some poly lies under the point -- found with a walk of a 0.1 m column -- the winner's
+// distance is at most that poly's: d <= ub = (max |dy| over the poly's height range - climb)^2.
+// Every candidate that can win or tie then has its closest point, hence its xz bounds, hence
+// (bvXzTight) its BV leaf box within sqrt(ub) of the point in xz.  On a multi-storey tile the
+// reference's +-2 m x +-4 m box collects ~70 candidates from ~350 BV nodes per point; the narrowed
+// walk of an on-mesh point sees the handful of polys stacked under it.
+HBN_HD float snapRadius(const NavView& nav, const float* center, const float* halfExt, int islandFilter) {
+  const float full = halfExt[0];
+  if (!nav.bvXzTight) return full;
+  float ub = kFltMax;
+  snapWalk(nav, center, halfExt, 0.1f, [&](uint32_t g, float lb) {
+    if (lb >= ub) return;
+    const PolyRec* p = &nav.polys[g];
+    if (islandFilter >= 0 && p->island != islandFilter) return;
+    if ((p->areaType >> 6) == 1 || !pointInPolygon(center, p->v, p->nv)) return;  // getPolyHeight would fail
+    const float* b = nav.polyBox + 8 * static_cast<size_t>(g);
+    const float dlo = fabsf(center[1] - b[1]), dhi = fabsf(center[1] - b[5]);
+    const float e = (dlo > dhi ? dlo : dhi) - nav.tiles[p->tile].walkableClimb;
+    const float u = e > 0.f ? e * e : 0.f;
+    if (u < ub) ub = u;
+  });
+  if (!(ub < kFltMax)) return full;
+  const float r = fsqrt(ub) * 1.001f + 0.11f;  // + two BV quanta (0.05 m cells) and rounding
+  return r < full ? r : full;
 }
 
 struct SnapCandOut {

@@ -87,6 +87,10 @@ struct HBN_ALIGN(16) PortalRec {
 static_assert(sizeof(PortalRec) == 32, "PortalRec");
 
 constexpr int32_t kBvFailBit = 1 << 30;  // leaf poly fails the default filter
+// leaf outside the tree proper (the zeroed spare node at the end of Detour's BV array: it reads as
+// a leaf of poly 0 with an empty box at the tile origin): always visited, box unrelated to its poly
+constexpr int32_t kBvLooseBit = 1 << 29;
+constexpr int32_t kBvIndexMask = (1 << 29) - 1;
 
 struct HBN_ALIGN(16) BvRec {
   uint16_t bmin[3];
@@ -147,6 +151,9 @@ struct NavView {
   uint32_t numPolys, numTiles, numLinks, numKeys;
   uint32_t polyBits, tileBits, saltBits;
   int32_t numIslands;
+  // 1 if every BV leaf box covers its poly's xz bounds (checked by the flattener): the BV walk
+  // may then use a narrower xz box than the reference's without losing the winner (hbn_snap.h)
+  int32_t bvXzTight;
 };
 
 }  // namespace hbn

@@ -105,10 +105,11 @@ void emu_snap_list(void* h, const float* pts, const int* islands, long n, float*
   for (long i = 0; i < n; ++i) {
     cand.clear();
     lb.clear();
-    snapWalk(e->nav, pts + 3 * i, kExt, [&](uint32_t g, float b) { cand.push_back(g); lb.push_back(b); });
+    const int isl = islands ? islands[i] : -1;
+    const float r = snapRadius(e->nav, pts + 3 * i, kExt, isl);
+    snapWalk(e->nav, pts + 3 * i, kExt, r, [&](uint32_t g, float b) { cand.push_back(g); lb.push_back(b); });
     total += static_cast<long>(cand.size());
     d.assign(cand.size(), -1.f);
-    const int isl = islands ? islands[i] : -1;
     SnapCandOut o;
     float best = kFltMax;
     for (int pass = 0; pass < 2; ++pass)  // as k_snap_eval
