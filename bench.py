@@ -14,7 +14,8 @@ of the timings).
 
 Prints ONE JSON line (rank 0).  `value` = device-resident throughput (CUDA events, inputs in
 HBM), `e2e` = the same through the C ABI's host-buffer entry point hbn_find_path (H2D + D2H
-inside the timed region), `roofline` for the dominant kernel (A* + funnel), `cpu_baseline` =
+inside the timed region), `roofline` for the dominant kernel (k_astar_lane, 93 % of a step; timed
+together with the classify / funnel kernels around it), `cpu_baseline` =
 the oracle (reference Detour compiled from /root/reference + restated PathFinder layer) on all
 host cores over a bounded sample of the same queries.
 """
@@ -257,7 +258,7 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            traffic = json.load(open(tpath)).get("dram_bytes_per_query") * n  # ncu capture, scaled to this launch
         except Exception:
             traffic = None
 
@@ -304,7 +305,7 @@ def main():
                     "d2h_bytes_per_step": int(4 * n)},
             "gpu_launches": int(tot_launch),
             "clocks": clocks.summary(),
-            "roofline": {"bound": "hbm", "kernel": "k_findpath (A* + funnel)", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": "k_astar_lane (+ k_fp_classify/scatter/funnel: the find_path phase after the snaps)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes),
                          "kernel_ms_per_step": path_ms,

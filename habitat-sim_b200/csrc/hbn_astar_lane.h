@@ -386,6 +386,9 @@ struct LaneSearch {
     int ln = 0;
     float bpos[3] = {0.f, 0.f, 0.f};
     float bcost = 0.f;
+    float pk0 = 0.f, pk1 = 0.f;  // keys of the parents of heap positions size, size + 1 (see below)
+    bool pkValid = false;
+    int pushed = 0;
     if (mode == kLExtract) {  // getPathToNode, DQ.cpp:1167-1205, from the end backwards
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
@@ -444,6 +447,16 @@ struct LaneSearch {
           nLinks += static_cast<uint32_t>(ln);
           bpos[0] = ba.px; bpos[1] = ba.py; bpos[2] = ba.pz;
           bcost = ba.cost;  // open until this pop: sign bit clear
+          // The first two pushes of this expansion go to positions size and size + 1; their
+          // parents' keys are fetched now (beyond the shared levels that is an HBM access), so
+          // the usual case -- a new node stays at the bottom -- costs no load in the replay.
+          if (size > 0) {
+            uint32_t dummy;
+            hget((size - 1) >> 1, pk0, dummy);
+            pk1 = pk0;
+            if ((size >> 1) != ((size - 1) >> 1)) hget(size >> 1, pk1, dummy);
+            pkValid = true;
+          }
         }
       }
     }
@@ -528,12 +541,22 @@ struct LaneSearch {
           if (isModify) {
             if (hp < 0) stop = kLEvFault;  // an open node that is not in the heap would be a bug
             else heapUp(hp, qKey[j], slot);
+            pkValid = false;
           } else {
-            heapUp(size, qKey[j], slot);
+            // bubbleUp's first comparison against the prefetched parent key: valid as long as
+            // no earlier operation of this expansion has moved an entry
+            if (pkValid && pushed < 2 && !((pushed == 0 ? pk0 : pk1) > qKey[j])) {
+              hset(size, qKey[j], slot);
+            } else {
+              heapUp(size, qKey[j], slot);
+              pkValid = false;
+            }
+            pushed++;
             size++;
           }
         }
       }
+      pkValid = false;  // a further chunk of links starts from other positions
     }
     if (stop == kLEvPoolExhausted) {
       ev = finishSearch(allCorridors);
