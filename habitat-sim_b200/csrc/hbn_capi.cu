@@ -316,7 +316,7 @@ int snapLaunch(hbn_navmesh* nm, const float* pts, const int32_t* islands, int64_
   if (n <= 0) return HBN_OK;
   const int groupsPerBlock = 256 / kSnapW;
   const int64_t maxBlocks = static_cast<int64_t>(nm->smCount) * 64;
-  static const bool forceGroup = getenv("HBN_SNAP_GROUP") != nullptr;
+  const bool forceGroup = getenv("HBN_SNAP_GROUP") != nullptr;  // testing: the lane-group kernel only
   if (n < kSnapSmall || forceGroup) {
     const int64_t blocks = std::min(maxBlocks, (n + groupsPerBlock - 1) / groupsPerBlock);
     k_snap<kSnapW><<<static_cast<unsigned>(blocks), 256, 0, st>>>(nm->view, pts, islands, n, out_pts, out_g,
@@ -326,7 +326,8 @@ int snapLaunch(hbn_navmesh* nm, const float* pts, const int32_t* islands, int64_
     return HBN_OK;
   }
   const int64_t cmax = std::min(n, kSnapChunk);
-  const size_t cap = static_cast<size_t>(cmax) * kSnapAvgCap;
+  size_t cap = static_cast<size_t>(cmax) * kSnapAvgCap;
+  if (const char* e = getenv("HBN_SNAP_CAP")) cap = static_cast<size_t>(std::max(1, atoi(e)));  // testing: force the fallback
   size_t tmpBytes = 0;
   CK(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr),
                                    static_cast<int>(cmax + 1), st));

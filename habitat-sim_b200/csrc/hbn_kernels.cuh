@@ -2,13 +2,13 @@
 // in hbn_query.h; this file decides how queries map onto the machine.
 //
 //  k_snap<W>       W lanes per point: BV nodes are scanned W at a time with coalesced 16 B
-//                  loads, candidate polys evaluated W at a time (findNearestPoly).
-//  k_findpath<..>  one warp per query, pulled from an atomic work counter (query cost varies
-//                  by 1000x).  The A* node pool, open-list heap and hash live in a per-warp
-//                  workspace: shared memory for the small tier, shared heap+hash with
-//                  L2-resident node arrays for the 2048-node tier.  Queries that outgrow the
-//                  small tier are appended to an overflow list and re-run by the large tier
-//                  (the search is deterministic, so the re-run reproduces it).
+//                  loads, candidate polys evaluated W at a time (findNearestPoly).  Used for
+//                  small batches; large ones go through the candidate-list pipeline of
+//                  hbn_snap.cuh (thread per point walk, thread per candidate closest point).
+//  k_findpath_w<..> one warp per query, pulled from an atomic work counter.  The first find_path
+//                  mapping; kept selectable (HBN_FP_G=warp) and as the 2048-entry open-list
+//                  tier of k_astar_g.  The default is k_astar_lane (hbn_astar_lane.cuh): one
+//                  query per lane, search state in HBM.
 //  k_wall<..>      same workspace scheme for findDistanceToWall's Dijkstra.
 //  k_trystep_*     one thread per query (64-node BFS in local memory).
 //  k_random<W>     W lanes per sample; both reservoir scans run lane-parallel.

@@ -334,6 +334,53 @@ def test_full_size_properties():
     assert beq(d[:m], want).all()
 
 
+def test_snap_pipeline_variants(monkeypatch):
+    """The candidate-list nearest-poly pipeline (hbn_snap.cuh): island-restricted batches, the
+    device-side fallback when the candidate scratch overflows, and the lane-group kernel must all
+    give the reference's refs and points."""
+    for name in ("t_building", "c4_building"):
+        pf = gpu_pathfinder(name)
+        ref = ref_pathfinder(name)
+        n = 30000
+        pts = query_points(name, n, 41, jitter=0.05)
+        rng = np.random.default_rng(2)
+        pts[:6000] += rng.normal(0, 0.7, (6000, 3)).astype(np.float32)  # off the mesh, between storeys
+        pts[6000:6003] = np.nan
+        want_p, want_r, want_i = ref.snap_batch(pts, 8)
+        isl = rng.integers(0, ref.num_islands, n).astype(np.int32)
+        isl[::3] = want_i[::3]  # a third of the points ask for the island they are on
+        isl[isl < 0] = 0
+        wp, wr = ref.snap_island_batch(pts, isl)
+        for env in ({}, {"HBN_SNAP_CAP": "1000"}, {"HBN_SNAP_GROUP": "1"}):
+            for k in ("HBN_SNAP_CAP", "HBN_SNAP_GROUP"):
+                monkeypatch.delenv(k, raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            got_p, got_r, got_i = pf.snap_points(pts)
+            assert (got_r == want_r).all() and (got_i == want_i).all() and beq(got_p, want_p).all(), env
+            gp, gr, gi = pf.snap_points(pts, isl)
+            assert (gr == wr).all() and beq(gp, wp).all(), env
+
+
+def test_lane_search_small_grid_generation_wrap(monkeypatch):
+    """k_astar_lane with one block per SM: every lane serves ~40 queries, so node-table
+    generations wrap and the warp-cooperative wipe runs; results must equal the full grid's and
+    the oracle's."""
+    from workloads.scenes import NavMeshGeom, pointnav_pairs
+    name = "c4_building"
+    n = 200_000
+    st, en = pointnav_pairs(NavMeshGeom(navmesh_image(name)), n, 13)
+    full = gpu_pathfinder(name).find_paths(st, en)["geodesic_distance"]
+    monkeypatch.setenv("HBN_FP_BLOCKS_PER_SM", "1")
+    pf = gpu_pathfinder(name)
+    d = pf.find_paths(st, en)["geodesic_distance"]
+    d2 = pf.find_paths(st, en)["geodesic_distance"]  # generations persist across launches
+    assert beq(d, full).all() and beq(d2, full).all()
+    m = 4000
+    want = ref_pathfinder(name).find_path_batch(st[:m], en[:m], 0, 8)[0]
+    assert beq(d[:m], want).all()
+
+
 @pytest.mark.parametrize("width", ["lane", "4", "8", "16", "32", "warp"])
 def test_find_path_search_variants(width, monkeypatch):
     """Every mapping of the search onto the machine (HBN_FP_G lanes per query in lock step, or the

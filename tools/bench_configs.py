@@ -71,38 +71,40 @@ def main():
         assert ref.load_bytes(img)
         return img, pf, ref, NavMeshGeom(img)
 
-    # ---- C2: 1024 envs, per step try_step + geodesic distance to the goal ------------------
+    # ---- C2: 1024 envs (and more), per step try_step + geodesic distance to the goal ---------
     img, pf, ref, geom = load("c2_apartment")
-    envs, steps = 1024, max(10, int(100 * args.scale))
-    pos0, goal = uniform_pairs(geom, envs, 3, jitter=0.0)
-    pos0 = ref.snap_batch(pos0)[0]
-    tgts = [step_targets(pos0, 100 + k) - pos0 for k in range(steps)]  # displacement per step
-    goal_d = T(goal)
-    disp_d = [T(t) for t in tgts]
+    for envs in (1024, 65536):
+        steps = max(10, int((100 if envs == 1024 else 20) * args.scale))
+        pos0, goal = uniform_pairs(geom, envs, 3, jitter=0.0)
+        pos0 = ref.snap_batch(pos0, threads)[0]
+        tgts = [step_targets(pos0, 100 + k) - pos0 for k in range(steps)]  # displacement per step
+        goal_d = T(goal)
+        disp_d = [T(t) for t in tgts]
 
-    def c2_gpu():
-        p = T(pos0)
-        d = None
-        for k in range(steps):
-            p = pf.try_steps(p, p + disp_d[k])
-            d = pf.find_paths(p, goal_d)["geodesic_distance"]
-        return p, d
+        def c2_gpu():
+            p = T(pos0)
+            d = None
+            for k in range(steps):
+                p = pf.try_steps(p, p + disp_d[k])
+                d = pf.find_paths(p, goal_d)["geodesic_distance"]
+            return p, d
 
-    dt, (p_g, d_g) = gpu_time(c2_gpu, reps=2, warm=1)
+        dt, (p_g, d_g) = gpu_time(c2_gpu, reps=2, warm=1)
 
-    def c2_cpu():
-        p = pos0.copy()
-        d = None
-        for k in range(steps):
-            p = ref.try_step_batch(p, p + tgts[k], True, threads)
-            d = ref.find_path_batch(p, goal, 0, threads)[0]
-        return p, d
+        def c2_cpu():
+            p = pos0.copy()
+            d = None
+            for k in range(steps):
+                p = ref.try_step_batch(p, p + tgts[k], True, threads)
+                d = ref.find_path_batch(p, goal, 0, threads)[0]
+            return p, d
 
-    dtc, (p_c, d_c) = cpu_time(c2_cpu)
-    emit(config="C2 PointNav step: 1024 envs on c2_apartment, try_step + geodesic_distance per step, "
-                f"{steps} dependent steps (one launch sequence per step)",
-         unit="env-steps/s", b200=envs * steps / dt, reference_cpu=envs * steps / dtc, cores=threads,
-         us_per_step_b200=1e6 * dt / steps, bit_exact=beq(p_g.cpu().numpy(), p_c) and beq(d_g.cpu().numpy(), d_c))
+        dtc, (p_c, d_c) = cpu_time(c2_cpu)
+        emit(config=f"C2 PointNav step: {envs} envs on c2_apartment, try_step + geodesic_distance per step, "
+                    f"{steps} dependent steps (one launch sequence per step)",
+             unit="env-steps/s", b200=envs * steps / dt, reference_cpu=envs * steps / dtc, cores=threads,
+             us_per_step_b200=1e6 * dt / steps,
+             bit_exact=beq(p_g.cpu().numpy(), p_c) and beq(d_g.cpu().numpy(), d_c))
 
     # ---- C3: multi-goal, 4096 starts x 64 goals -------------------------------------------
     img, pf, ref, geom = load("c3_multiroom")
