@@ -18,7 +18,8 @@ from .._lib import HbnError, check
 from .sharding import gather as gather_shards, shard_slice, shard_slices  # noqa: E402,F401
 
 __all__ = ["shard_slices", "shard_slice", "gather_shards", "PathFinder", "ShortestPath", "MultiGoalShortestPath", "HitRecord", "NavMeshSettings",
-           "GreedyFollowerCodes", "GreedyGeodesicFollowerImpl", "GreedyGeodesicFollower", "HbnError"]
+           "GreedyFollowerCodes", "GreedyGeodesicFollowerImpl", "GreedyGeodesicFollower",
+           "GreedyGeodesicFollowerBatch", "GreedyGeodesicFollowerBatchImpl", "HbnError"]
 
 MAX_PATH_POINTS = 256  # MAX_POLYS, PathFinder.cpp:1443
 
@@ -612,4 +613,5 @@ class PathFinder:
 
 
 from .greedy_follower import (GreedyFollowerCodes, GreedyGeodesicFollower,  # noqa: E402
+                              GreedyGeodesicFollowerBatch, GreedyGeodesicFollowerBatchImpl,
                               GreedyGeodesicFollowerImpl)
