@@ -423,6 +423,15 @@ struct LaneSearch {
         const LaneRecA ba = *recA(bslot);
         const LaneRecB bb = *recB(bslot);
         size--;
+#if defined(__CUDA_ARCH__)
+        {  // the popped poly's link records are needed right after the sift: start them towards L1 now
+          const char* lp = reinterpret_cast<const char*>(&nav.links[bb.lnk & 0x07ffffffu]);
+          const int cnt = static_cast<int>(bb.lnk >> 27);
+#pragma unroll
+          for (int k = 0; k < CH; ++k)
+            if (k < cnt) asm volatile("prefetch.global.L1 [%0];" ::"l"(lp + 32 * k));
+        }
+#endif
         heapPopSift(size);
         recA(bslot)->cost = laneSetClosed(ba.cost);
 #if defined(__CUDA_ARCH__)

@@ -178,7 +178,7 @@ void emu_find_path_lane(void* h, const float* starts, const float* ends, long n,
   std::vector<float> K(TS);
   std::vector<uint16_t> S(TS);
   std::vector<uint32_t> ring(kMaxPathPolys);
-  LaneSearch<1, TS, 3> s{};
+  LaneSearch<1, TS, 4> s{};  // the shipped configuration: 4 links per load stage
   s.K = K.data(); s.S = S.data();
   s.tab = reinterpret_cast<uint16_t*>(base);
   s.rec = base + laneTabBytes(nav.numKeys);
