@@ -163,6 +163,37 @@ def test_hostemu_queries_match_oracle(name):
     emu.emu_destroy(h)
 
 
+@pytest.mark.parametrize("name", ["t_building", "c4_building"])
+def test_hostemu_snap_list_on_multi_storey_tiles(name):
+    """The narrowed BV walk + lower-bound pruning of hbn_snap.h on tiled multi-storey meshes: points
+    on the mesh, between storeys, off the mesh and island-restricted must get the reference's poly and
+    point; the pipeline must evaluate far fewer candidates than the reference visits."""
+    emu, h = _emu_handle(name)
+    pf = ref_pathfinder(name)
+    n = 8000
+    pts = query_points(name, n, 77, jitter=0.05)
+    rng = np.random.default_rng(1)
+    pts[:1600] += rng.normal(0, 0.6, (1600, 3)).astype(np.float32)
+    pts[1600:2400, 1] += rng.uniform(-3, 3, 800).astype(np.float32)
+    lo, hi = pf.get_bounds()
+    pts[2400:2600] = rng.uniform(lo - 3, hi + 3, (200, 3)).astype(np.float32)
+    o_pts, o_refs, o_isl = pf.snap_batch(pts, 8)
+    e_pts = np.zeros_like(pts)
+    e_refs = np.zeros(n, np.uint32)
+    e_isl = np.zeros(n, np.int32)
+    nc = (C.c_long * 2)()
+    emu.emu_snap_list(h, P(pts, f32p), None, C.c_long(n), P(e_pts, f32p), P(e_refs, u32p), P(e_isl, i32p), nc)
+    assert (o_refs == e_refs).all() and (o_isl == e_isl).all() and beq(o_pts, e_pts).all()
+    assert nc[1] <= nc[0] < 30 * n  # the reference's box collects ~50-60 candidates per point here
+    isl = rng.integers(0, pf.num_islands, n).astype(np.int32)
+    isl[::3] = np.maximum(o_isl[::3], 0)
+    oi_pts, oi_refs = pf.snap_island_batch(pts, isl)
+    emu.emu_snap_list(h, P(pts, f32p), P(isl, i32p), C.c_long(n), P(e_pts, f32p), P(e_refs, u32p), P(e_isl, i32p),
+                      nc)
+    assert (oi_refs == e_refs).all() and beq(oi_pts, e_pts).all()
+    emu.emu_destroy(h)
+
+
 @pytest.mark.parametrize("name", ["c2_apartment", "c3_multiroom", "t_building", "c4_building"])
 def test_hostemu_lane_search_matches_oracle(name):
     """hbn_astar_lane.h (the per-lane state machine of k_astar_lane) against Detour's findPath:
