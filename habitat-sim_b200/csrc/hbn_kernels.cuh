@@ -15,6 +15,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "hbn_query.h"
+#include "hbn_snap.h"
 #include "hbn_astar_warp.cuh"
 
 namespace hbn {
@@ -41,7 +42,11 @@ __global__ void __launch_bounds__(256) k_snap(NavView nav, const float* __restri
        q += groupsPerGrid) {
     const float c[3] = {pts[3 * q], pts[3 * q + 1], pts[3 * q + 2]};
     const int isl = islands ? islands[q] : -1;
-    const Nearest r = findNearestPoly(nav, grp, c, ext, isl, queue[gInBlock]);
+    // lane 0 of the group finds the xz half-extent that is enough (a 0.1 m column walk, hbn_snap.h)
+    float rxz = 0.f;
+    if (grp.lane() == 0) rxz = snapRadius(nav, c, ext, isl);
+    rxz = grp.shfl(rxz, 0);
+    const Nearest r = findNearestPoly(nav, grp, c, ext, isl, queue[gInBlock], rxz);
     grp.sync();
     if (grp.lane() == 0) {
       const bool ok = r.g != kNoPoly;

@@ -270,9 +270,13 @@ HBN_HD void nearestConsider(const NavView& nav, const float* center, int islandF
 }
 
 // candQueue: 2*W uint32 of scratch owned by the group (shared memory on the device).
+// rxz < 0: the reference's box.  rxz >= 0 narrows the box in x and z (hbn_snap.h snapRadius picks a
+// half-extent that keeps every candidate that can win; the loose leaves behind a tile's BV tree
+// are still tested against the full box).
 template <class G>
 HBN_HD Nearest findNearestPoly(const NavView& nav, const G& grp, const float* center,
-                               const float* halfExt, int islandFilter, uint32_t* candQueue) {
+                               const float* halfExt, int islandFilter, uint32_t* candQueue,
+                               float rxz = -1.f) {
   constexpr int W = G::kWidth;
   Nearest res;
   res.g = kNoPoly;
@@ -288,8 +292,9 @@ HBN_HD Nearest findNearestPoly(const NavView& nav, const G& grp, const float* ce
   acc.over = false;
   float qmin[3], qmax[3];
   for (int k = 0; k < 3; ++k) {
-    qmin[k] = center[k] - halfExt[k];
-    qmax[k] = center[k] + halfExt[k];
+    const float h = (k != 1 && rxz >= 0.f) ? rxz : halfExt[k];
+    qmin[k] = center[k] - h;
+    qmax[k] = center[k] + h;
   }
   // calcTileLoc, DN.cpp:1191-1195
   int minx = static_cast<int>(floorf((qmin[0] - nav.orig[0]) / nav.tileWidth));
@@ -312,7 +317,8 @@ HBN_HD Nearest findNearestPoly(const NavView& nav, const G& grp, const float* ce
       for (uint32_t c = c0; c < c1; ++c) {
         const TileRec& tr = nav.tiles[nav.tileOrder[c]];
         const uint32_t count = tr.bvCount ? tr.bvCount : tr.polyCount;
-        uint16_t bmin[3], bmax[3];
+        uint16_t bmin[3], bmax[3];    // quantised query box of this walk
+        uint16_t fbmin[3], fbmax[3];  // ... and the reference's full box (loose leaves)
         if (tr.bvCount) {
           // quantised query box, DQ.cpp:749-765
           const float qfac = tr.bvQuantFactor;
@@ -321,6 +327,10 @@ HBN_HD Nearest findNearestPoly(const NavView& nav, const G& grp, const float* ce
             const float mx = fclamp(qmax[k], tr.bmin[k], tr.bmax[k]) - tr.bmin[k];
             bmin[k] = static_cast<uint16_t>(static_cast<uint16_t>(static_cast<int>(qfac * mn)) & 0xfffe);
             bmax[k] = static_cast<uint16_t>(static_cast<uint16_t>(static_cast<int>(qfac * mx + 1)) | 1);
+            const float fmn = fclamp(center[k] - halfExt[k], tr.bmin[k], tr.bmax[k]) - tr.bmin[k];
+            const float fmx = fclamp(center[k] + halfExt[k], tr.bmin[k], tr.bmax[k]) - tr.bmin[k];
+            fbmin[k] = static_cast<uint16_t>(static_cast<uint16_t>(static_cast<int>(qfac * fmn)) & 0xfffe);
+            fbmax[k] = static_cast<uint16_t>(static_cast<uint16_t>(static_cast<int>(qfac * fmx + 1)) | 1);
           }
         }
         uint32_t pnode = 0;
@@ -333,8 +343,10 @@ HBN_HD Nearest findNearestPoly(const NavView& nav, const G& grp, const float* ce
           if (valid) {
             if (tr.bvCount) {
               const BvRec n = nav.bv[tr.bvStart + idx];
-              const bool ov = overlapQuant(bmin, bmax, n.bmin, n.bmax);
               const bool leaf = n.i >= 0;
+              const bool loose = leaf && (n.i & kBvLooseBit) != 0;
+              const bool ov = loose ? overlapQuant(fbmin, fbmax, n.bmin, n.bmax)
+                                    : overlapQuant(bmin, bmax, n.bmin, n.bmax);
               isSkip = !ov && !leaf;
               esc = -n.i;
               isCand = ov && leaf && ((n.i & kBvFailBit) == 0);

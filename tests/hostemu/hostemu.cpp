@@ -87,7 +87,10 @@ void emu_snap(void* h, const float* pts, const int* islands, long n, float* out_
   HostGroup grp;
   uint32_t q[2];
   for (long i = 0; i < n; ++i) {
-    const Nearest r = findNearestPoly(e->nav, grp, pts + 3 * i, kExt, islands ? islands[i] : -1, q);
+    // as k_snap: the narrowed box of snapRadius (emu_find_path & co. keep the reference's box)
+    const int isl = islands ? islands[i] : -1;
+    const float rxz = snapRadius(e->nav, pts + 3 * i, kExt, isl);
+    const Nearest r = findNearestPoly(e->nav, grp, pts + 3 * i, kExt, isl, q, rxz);
     const bool ok = r.g != kNoPoly;
     for (int k = 0; k < 3; ++k) out_pts[3 * i + k] = ok ? r.pt[k] : NAN;
     if (out_refs) out_refs[i] = ok ? e->nav.polys[r.g].ref : 0u;

@@ -185,6 +185,9 @@ def test_hostemu_snap_list_on_multi_storey_tiles(name):
     emu.emu_snap_list(h, P(pts, f32p), None, C.c_long(n), P(e_pts, f32p), P(e_refs, u32p), P(e_isl, i32p), nc)
     assert (o_refs == e_refs).all() and (o_isl == e_isl).all() and beq(o_pts, e_pts).all()
     assert nc[1] <= nc[0] < 30 * n  # the reference's box collects ~50-60 candidates per point here
+    # the lane-group kernel's walk with the same narrowed box (k_snap, small batches)
+    emu.emu_snap(h, P(pts, f32p), None, C.c_long(n), P(e_pts, f32p), P(e_refs, u32p), P(e_isl, i32p))
+    assert (o_refs == e_refs).all() and (o_isl == e_isl).all() and beq(o_pts, e_pts).all()
     isl = rng.integers(0, pf.num_islands, n).astype(np.int32)
     isl[::3] = np.maximum(o_isl[::3], 0)
     oi_pts, oi_refs = pf.snap_island_batch(pts, isl)
