@@ -5,6 +5,8 @@ oracle bit for bit.  No CUDA call is made here."""
 import ctypes as C
 import os
 import re
+import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -235,6 +237,69 @@ def test_hostemu_lane_search_matches_oracle(name):
             assert (corr[i, :k] == r["corridor"][i, :k]).all(), i
     assert searched_any > n  # most queries do need a search
     emu.emu_destroy(h)
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_hostemu_fuzz_random_scenes(seed):
+    """Fresh procedural scenes (not the cached benchmark ones): a seeded multi-room floor plan and a
+    tiled two-storey building with ramps, built by the reference's Recast; the product's nearest-poly
+    pipeline and lane search must reproduce the oracle on each."""
+    from oracle.ref import RefPathFinder
+    from workloads import meshgen
+    from workloads.scenes import NavMeshGeom
+    emu = hostemu()
+    for gen, kw, tiled in ((meshgen.multi_room, dict(nx=4 + seed % 3, nz=3 + seed % 2, seed=seed), False),
+                           (meshgen.building, dict(nx=5, nz=4, floors=2, ramps_per_floor=2, closed_rooms=1,
+                                                   seed=seed), True)):
+        v, t = gen(**kw)
+        ref = RefPathFinder()
+        assert ref.build_tiled(v, t, 128) if tiled else ref.build(v, t)
+        img = ref.save_bytes()
+        ref = RefPathFinder()
+        assert ref.load_bytes(img)
+        h = C.c_void_p(emu.emu_create(img, C.c_long(len(img))))
+        assert h
+        rng = np.random.default_rng(seed)
+        n = 700
+        geom = NavMeshGeom(img)
+        pts = geom.sample(2 * n, rng) + rng.normal(0, 0.15, (2 * n, 3)).astype(np.float32)
+        pts = pts.astype(np.float32)
+        o_pts, o_refs, o_isl = ref.snap_batch(pts)
+        e_pts = np.zeros_like(pts)
+        e_refs = np.zeros(2 * n, np.uint32)
+        e_isl = np.zeros(2 * n, np.int32)
+        nc = (C.c_long * 2)()
+        emu.emu_snap_list(h, P(pts, f32p), None, C.c_long(2 * n), P(e_pts, f32p), P(e_refs, u32p), P(e_isl, i32p), nc)
+        assert (o_refs == e_refs).all() and (o_isl == e_isl).all() and beq(o_pts, e_pts).all()
+        emu.emu_snap(h, P(pts, f32p), None, C.c_long(2 * n), P(e_pts, f32p), P(e_refs, u32p), P(e_isl, i32p))
+        assert (o_refs == e_refs).all() and beq(o_pts, e_pts).all()
+        st, en = pts[:n].copy(), pts[n:].copy()
+        r = ref.find_path_raw_batch(st, en)
+        corr = np.zeros((n, 256), np.uint32)
+        info = np.zeros((n, 4), np.uint32)
+        emu.emu_find_path_lane(h, P(st, f32p), P(en, f32p), C.c_long(n), 0, 1, P(corr, u32p), P(info, u32p))
+        done = info[:, 3] == 1
+        assert done.sum() > n // 4 and (info[:, 3] != 3).all()
+        assert (info[done, 0] == r["astar_status"][done]).all()
+        assert (info[done, 2] == r["nodes_used"][done]).all()
+        for i in np.nonzero(done)[0]:
+            k = r["num_polys"][i]
+            assert min(info[i, 1], 256) == k and (corr[i, :k] == r["corridor"][i, :k]).all()
+        emu.emu_destroy(h)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference runs on the host cores only: one JSON line with the contract's keys."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--cpu-sample", "4000"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "find_path_queries_per_sec"
+    assert line["unit"] == "queries/s" and line["higher_is_better"] is True and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in line["config"] and 0.2 < line["found_fraction"] < 1.0
 
 
 def test_uniform_stream_definition_matches_oracle():
