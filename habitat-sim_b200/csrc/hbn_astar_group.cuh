@@ -88,7 +88,8 @@ enum : uint8_t {
   kClsTrivial = 1,   // pathStart == pathEnd (PF.cpp:1434-1436)
   kClsSamePoly = 2,  // startRef == endRef (DQ.cpp:996-1001)
   kClsInvalid = 3,   // non-finite snapped point: findPath fails with INVALID_PARAM
-  kClsSearch = 4
+  kClsSearch = 4,
+  kClsSkip = 5       // masked out by the caller (multi-goal pruning): outputs are left alone
 };
 
 struct AStarGArgs {
@@ -486,6 +487,7 @@ __global__ void __launch_bounds__(256) k_fp_classify(NavView nav, const uint32_t
                                                      const float* __restrict__ sPt,
                                                      const uint32_t* __restrict__ eG,
                                                      const float* __restrict__ ePt, int64_t n, int startDiv,
+                                                     const uint8_t* __restrict__ mask,
                                                      uint8_t* __restrict__ cls, uint8_t* __restrict__ bucket,
                                                      uint32_t* __restrict__ hist, uint32_t* __restrict__ workCount) {
   __shared__ uint32_t histS[kFpBuckets];
@@ -496,7 +498,9 @@ __global__ void __launch_bounds__(256) k_fp_classify(NavView nav, const uint32_t
     const int64_t qs = startDiv > 1 ? q / startDiv : q;
     const uint32_t s = sG[qs], e = eG[q];
     uint8_t c = kClsNone, b = kFpNoBucket;
-    if (s != kNoPoly && e != kNoPoly) {
+    if (mask && !mask[q]) {
+      c = kClsSkip;
+    } else if (s != kNoPoly && e != kNoPoly) {
       const float sp[3] = {sPt[3 * qs], sPt[3 * qs + 1], sPt[3 * qs + 2]};
       const float ep[3] = {ePt[3 * q], ePt[3 * q + 1], ePt[3 * q + 2]};
       if (vfuzzyEq(sp, ep)) {
@@ -585,6 +589,7 @@ struct FpFunnelArgs {
   int32_t* out_ncorridor;
   uint32_t* out_status;
   unsigned long long* workCtr;
+  int fillSkipped;  // kClsSkip queries: write an infinite distance (else nothing)
 };
 
 // findStraightPath + pathLength (PF.cpp:1456-1466) and every per-query output, one thread per
@@ -594,6 +599,10 @@ __global__ void __launch_bounds__(128) k_fp_funnel(NavView nav, FpFunnelArgs a) 
   if (q >= a.n) return;
   const int64_t qs = a.startDiv > 1 ? q / a.startDiv : q;
   const uint8_t c = a.cls[q];
+  if (c == kClsSkip) {
+    if (a.fillSkipped) a.out_dist[q] = infF();
+    return;
+  }
   float dist = infF();
   int npts = 0, ncorr = 0;
   uint32_t stA = 0, stS = 0, corrLinks = 0;

@@ -81,7 +81,7 @@ struct hbn_navmesh {
   int64_t launches = 0;
   std::recursive_mutex mu;
   // scratch (device)
-  DevBuf sG, eG, e2G, sPt, ePt, epPt, lastPoly, lists, counters, wsL, wsFp, io, work, mgDist, mgBounds, mgOrder, mgEnd;
+  DevBuf sG, eG, e2G, sPt, ePt, epPt, lastPoly, lists, counters, wsL, wsFp, io, work, mgDist, mgBounds, mgOrder, mgEnd, mgMask;
   // lock-step find_path (hbn_astar_group.cuh): class, search list, status, corridor rings, node records
   DevBuf fpCls, fpBucket, fpWork, fpStat, fpLen, fpCorr, wsFpG;
   int fpG = 1;          // lanes per query of k_astar_g; 0 = one query per warp (k_findpath_w tiers only);
@@ -424,7 +424,7 @@ void hbn_navmesh_destroy(hbn_navmesh_t nm) {
   for (void* d : nm->devArrays) cudaFree(d);
   for (DevBuf* b : {&nm->sG, &nm->eG, &nm->e2G, &nm->sPt, &nm->ePt, &nm->epPt, &nm->lastPoly,
                     &nm->lists, &nm->counters, &nm->wsL, &nm->wsFp, &nm->io, &nm->work, &nm->mgDist,
-                    &nm->mgBounds, &nm->mgOrder, &nm->mgEnd, &nm->fpCls, &nm->fpWork, &nm->fpStat,
+                    &nm->mgBounds, &nm->mgOrder, &nm->mgEnd, &nm->mgMask, &nm->fpCls, &nm->fpWork, &nm->fpStat,
                     &nm->fpLen, &nm->fpCorr, &nm->fpBucket, &nm->wsFpG, &nm->wsLane, &nm->laneGen, &nm->snapCnt, &nm->snapOff,
                     &nm->snapG, &nm->snapQ, &nm->snapD, &nm->snapOut, &nm->snapBest, &nm->snapTmp, &nm->snapTodo})
     b->release();
@@ -584,10 +584,14 @@ static int warpTierLaunch(hbn_navmesh_t nm, FindPathArgs a, bool smallTier, uint
 constexpr int64_t kFpChunk = 1 << 20;  // queries per pass of the lock-step pipeline (1 KB corridor ring each)
 
 // n (start, end) pairs; startDiv > 1: pair q uses start q / startDiv (multi-goal layout)
+// pairMask (lock-step pipeline only): queries with a zero byte are skipped -- their outputs are left
+// alone, or get an infinite distance with kFpFillSkipped.  kFpReuseSnaps: the projectToPoly results
+// of the previous call on the same points are still in the scratch.
+enum { kFpReuseSnaps = 1 << 16, kFpFillSkipped = 1 << 17 };
 static int findPathLaunch(hbn_navmesh_t nm, const float* starts, const float* ends, int64_t n,
                           int startDiv, float* out_dist, int32_t* out_npts, float* out_pts, int max_pts,
                           uint32_t* out_corridor, int32_t* out_ncorridor, uint32_t* out_status,
-                          int flags, void* stream) {
+                          int flags, void* stream, const uint8_t* pairMask = nullptr) {
   if (!nm || (n > 0 && (!starts || !ends || !out_dist))) return fail(HBN_ERR_INVALID, "null argument");
   if (n <= 0) return HBN_OK;
   const int64_t nStarts = startDiv > 1 ? n / startDiv : n;
@@ -615,12 +619,15 @@ static int findPathLaunch(hbn_navmesh_t nm, const float* starts, const float* en
     for (auto& e : pe.e) CK(cudaEventCreate(&e));
     CK(cudaEventRecord(pe.e[0], st));
   }
-  if ((rc = snapLaunch(nm, starts, nullptr, nStarts, static_cast<float*>(nm->sPt.p),
-                       static_cast<uint32_t*>(nm->sG.p), nullptr, nullptr, nullptr, 0.f, st)))
-    return rc;
-  if ((rc = snapLaunch(nm, ends, nullptr, n, static_cast<float*>(nm->ePt.p),
-                       static_cast<uint32_t*>(nm->eG.p), nullptr, nullptr, nullptr, 0.f, st)))
-    return rc;
+  if (pairMask && !nm->fpG) return fail(HBN_ERR_INVALID, "pair masks need the lock-step find_path pipeline");
+  if ((flags & kFpReuseSnaps) == 0) {
+    if ((rc = snapLaunch(nm, starts, nullptr, nStarts, static_cast<float*>(nm->sPt.p),
+                         static_cast<uint32_t*>(nm->sG.p), nullptr, nullptr, nullptr, 0.f, st)))
+      return rc;
+    if ((rc = snapLaunch(nm, ends, nullptr, n, static_cast<float*>(nm->ePt.p),
+                         static_cast<uint32_t*>(nm->eG.p), nullptr, nullptr, nullptr, 0.f, st)))
+      return rc;
+  }
   if (nm->profile) CK(cudaEventRecord(pe.e[1], st));
   unsigned long long* workCtr = (flags & HBN_FP_COUNT_WORK) ? static_cast<unsigned long long*>(nm->work.p) : nullptr;
   for (int64_t ci = 0; ci < nChunks; ++ci) {
@@ -653,8 +660,9 @@ static int findPathLaunch(hbn_navmesh_t nm, const float* starts, const float* en
     uint8_t* cls = static_cast<uint8_t*>(nm->fpCls.p);
     uint32_t* work = static_cast<uint32_t*>(nm->fpWork.p);
     uint8_t* bucket = static_cast<uint8_t*>(nm->fpBucket.p);
-    k_fp_classify<<<static_cast<unsigned>((cn + 255) / 256), 256, 0, st>>>(nm->view, a.sG, a.sPt, a.eG, a.ePt, cn,
-                                                                          startDiv, cls, bucket, cnt + 16, cnt + 4);
+    k_fp_classify<<<static_cast<unsigned>((cn + 255) / 256), 256, 0, st>>>(
+        nm->view, a.sG, a.sPt, a.eG, a.ePt, cn, startDiv, pairMask ? pairMask + c0 : nullptr, cls, bucket, cnt + 16,
+        cnt + 4);
     k_fp_scatter<<<static_cast<unsigned>((cn + 255) / 256), 256, 0, st>>>(bucket, cn, cnt + 16, cnt + 16 + kFpBuckets,
                                                                          work);
     nm->launches += 2;
@@ -705,6 +713,7 @@ static int findPathLaunch(hbn_navmesh_t nm, const float* starts, const float* en
     fa.out_dist = a.out_dist; fa.out_npts = a.out_npts; fa.out_pts = a.out_pts; fa.max_pts = max_pts;
     fa.out_corridor = a.out_corridor; fa.out_ncorridor = a.out_ncorridor; fa.out_status = a.out_status;
     fa.workCtr = workCtr;
+    fa.fillSkipped = (flags & kFpFillSkipped) ? 1 : 0;
     k_fp_funnel<<<static_cast<unsigned>((cn + 127) / 128), 128, 0, st>>>(nm->view, fa);
     nm->launches++;
     CK(cudaGetLastError());
@@ -748,10 +757,33 @@ int hbn_find_path_multigoal_dev(hbn_navmesh_t nm, const float* starts, const flo
   if ((rc = nm->mgDist.ensure(pairs * 4)) || (rc = nm->mgBounds.ensure(pairs * 4)) ||
       (rc = nm->mgOrder.ensure(pairs * 4)) || (wantPts && (rc = nm->mgEnd.ensure(n * 12))))
     return rc;
-  // every (start, goal) pair's findPathInternal, in parallel ...
-  if ((rc = findPathLaunch(nm, starts, ends, pairs, g, static_cast<float*>(nm->mgDist.p), nullptr, nullptr, 0,
-                           nullptr, nullptr, nullptr, 0, stream)))
+  if (g > kMultiGoalFirst && nm->fpG) {
+    // two rounds of pair searches: the kMultiGoalFirst goals of smallest bound of every start, then
+    // the later goals the reference would not skip (hbn_query.h); bounds / order in the select's scratch
+    if ((rc = nm->mgMask.ensure(pairs))) return rc;
+    uint8_t* mask = static_cast<uint8_t*>(nm->mgMask.p);
+    const unsigned sb = static_cast<unsigned>((n + 127) / 128);
+    k_multigoal_round1<<<sb, 128, 0, st>>>(starts, ends, n, g, static_cast<float*>(nm->mgBounds.p),
+                                           static_cast<int32_t*>(nm->mgOrder.p), mask);
+    nm->launches++;
+    CK(cudaGetLastError());
+    if ((rc = findPathLaunch(nm, starts, ends, pairs, g, static_cast<float*>(nm->mgDist.p), nullptr, nullptr, 0,
+                             nullptr, nullptr, nullptr, kFpFillSkipped, stream, mask)))
+      return rc;
+    k_multigoal_round2<<<sb, 128, 0, st>>>(static_cast<uint32_t*>(nm->sG.p), static_cast<uint32_t*>(nm->eG.p),
+                                           static_cast<float*>(nm->mgDist.p), n, g,
+                                           static_cast<float*>(nm->mgBounds.p),
+                                           static_cast<int32_t*>(nm->mgOrder.p), mask);
+    nm->launches++;
+    CK(cudaGetLastError());
+    if ((rc = findPathLaunch(nm, starts, ends, pairs, g, static_cast<float*>(nm->mgDist.p), nullptr, nullptr, 0,
+                             nullptr, nullptr, nullptr, kFpReuseSnaps, stream, mask)))
+      return rc;
+  } else if ((rc = findPathLaunch(nm, starts, ends, pairs, g, static_cast<float*>(nm->mgDist.p), nullptr, nullptr,
+                                  0, nullptr, nullptr, nullptr, 0, stream))) {
+    // every (start, goal) pair's findPathInternal, in parallel ...
     return rc;
+  }
   // ... then the reference's sequential goal loop per start (sG / eG are still in the scratch)
   k_multigoal_select<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(
       starts, ends, static_cast<uint32_t*>(nm->sG.p), static_cast<uint32_t*>(nm->eG.p),

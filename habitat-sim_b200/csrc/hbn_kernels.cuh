@@ -321,6 +321,45 @@ __global__ void __launch_bounds__(128) k_multigoal_select(const float* __restric
   }
 }
 
+// Two-round goal pruning of the batched multi-goal query (hbn_query.h, kMultiGoalFirst).
+// round 1: mask = the first kMultiGoalFirst goals of every start's sorted order
+__global__ void __launch_bounds__(128) k_multigoal_round1(const float* __restrict__ starts,
+                                                          const float* __restrict__ ends, int64_t n, int g,
+                                                          float* __restrict__ bounds, int32_t* __restrict__ order,
+                                                          uint8_t* __restrict__ mask) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float st[3] = {starts[3 * i], starts[3 * i + 1], starts[3 * i + 2]};
+  float* b = bounds + i * g;
+  int32_t* o = order + i * g;
+  for (int k = 0; k < g; ++k) {
+    b[k] = g > 1 ? mnDist(&ends[(i * g + k) * 3], st) : 0.0f;
+    o[k] = k;
+    mask[i * g + k] = 0;
+  }
+  stdSortOrder(o, b, g);
+  for (int k = 0; k < g && k < kMultiGoalFirst; ++k) mask[i * g + o[k]] = 1;
+}
+// round 2: mask = the later goals whose bound does not exceed the reference's running best
+__global__ void __launch_bounds__(128) k_multigoal_round2(const uint32_t* __restrict__ sG,
+                                                          const uint32_t* __restrict__ eG,
+                                                          const float* __restrict__ pairDist, int64_t n, int g,
+                                                          const float* __restrict__ bounds,
+                                                          const int32_t* __restrict__ order,
+                                                          uint8_t* __restrict__ mask) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* b = bounds + i * g;
+  const int32_t* o = order + i * g;
+  bool any = sG[i] != kNoPoly;
+  if (any) {
+    any = false;
+    for (int k = 0; k < g; ++k) any = any || eG[i * g + k] != kNoPoly;
+  }
+  const float rb = any ? multiGoalRunningBest(g, kMultiGoalFirst, eG + i * g, pairDist + i * g, b, o) : -infF();
+  for (int k = 0; k < g; ++k) mask[i * g + o[k]] = (k >= kMultiGoalFirst && !(b[o[k]] > rb)) ? 1 : 0;
+}
+
 // ------------------------------------------------------------------------------------
 struct WallArgs {
   const uint32_t* sG;

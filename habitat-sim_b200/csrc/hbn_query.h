@@ -1535,6 +1535,45 @@ HBN_HD void multiGoalSelect(int n, const float* start, bool startValid, const fl
   *outIndex = bestIdx;
 }
 
+// ---- goal pruning for batched multi-goal queries ------------------------------------------
+// The reference visits the goals in the order of their lower bounds and skips a goal whose bound
+// exceeds the best distance so far (PF.cpp:1541-1569); on a batch the pair searches dominate, so
+// they are done in two rounds: round 1 searches the kMultiGoalFirst goals of smallest bound of every
+// start; round 2 only those later goals whose bound does not exceed the reference's running best
+// after those first goals (`multiGoalRunningBest`).  The running best only shrinks, so a goal left
+// out is one the reference skips without looking at its distance; multiGoalSelect then replays the
+// reference's loop over distances that are real wherever it reads them.
+constexpr int kMultiGoalFirst = 8;
+
+// bounds[], order[] as multiGoalSelect computes them; returns false if the query has no result
+HBN_HD bool multiGoalOrder(int n, const float* start, bool startValid, const float* ends,
+                           const uint32_t* endG, float* bounds, int32_t* order) {
+  if (!startValid || n <= 0) return false;
+  bool anyValid = false;
+  for (int i = 0; i < n; ++i) anyValid = anyValid || endG[i] != kNoPoly;
+  if (!anyValid) return false;
+  for (int i = 0; i < n; ++i) {
+    bounds[i] = n > 1 ? mnDist(&ends[3 * i], start) : 0.0f;
+    order[i] = i;
+  }
+  stdSortOrder(order, bounds, n);
+  return true;
+}
+
+// the reference's `best` after the first `first` goals of the sorted order (dist[] valid for them)
+HBN_HD float multiGoalRunningBest(int n, int first, const uint32_t* endG, const float* dist,
+                                  const float* bounds, const int32_t* order) {
+  float best = infF();
+  for (int k = 0; k < n && k < first; ++k) {
+    const int i = order[k];
+    if (endG[i] == kNoPoly) continue;
+    if (bounds[i] > best) continue;
+    const float d = dist[i];
+    if (d < infF() && d < best) best = d;
+  }
+  return best;
+}
+
 // PathFinder::Impl::tryStep, PF.cpp:1575-1722, phase A: everything up to and including
 // getPolyHeight (:1687).  Inputs are the projectToPoly results of start and end.
 // Returns false if tryStep returns `start` (PF.cpp:1587-1604); else endPoint/lastPoly/startG

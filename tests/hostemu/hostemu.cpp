@@ -218,8 +218,10 @@ void emu_find_path_lane(void* h, const float* starts, const float* ends, long n,
 }
 
 // find_path(MultiGoalShortestPath), fresh object per start: ends [n, g, 3]
+// pruned != 0: the two-round scheme of the batched entry point (kMultiGoalFirst, hbn_query.h):
+// goals left out of both rounds keep an infinite distance; out_searched counts the pair searches.
 void emu_find_path_multigoal(void* h, const float* starts, const float* ends, long n, int g,
-                             float* out_dist, int* out_idx) {
+                             float* out_dist, int* out_idx, int pruned, long* out_searched) {
   Emu* e = static_cast<Emu*>(h);
   HostGroup grp;
   uint32_t q[2];
@@ -233,13 +235,28 @@ void emu_find_path_multigoal(void* h, const float* starts, const float* ends, lo
   for (long i = 0; i < n; ++i) {
     const float* st = starts + 3 * i;
     const Nearest s = findNearestPoly(e->nav, grp, st, kExt, -1, q);
+    std::vector<Nearest> et(g);
     for (int k = 0; k < g; ++k) {
+      et[k] = findNearestPoly(e->nav, grp, ends + (i * g + k) * 3, kExt, -1, q);
+      eG[k] = et[k].g;
+    }
+    auto search = [&](int k) {
       const float* en = ends + (i * g + k) * 3;
-      const Nearest t = findNearestPoly(e->nav, grp, en, kExt, -1, q);
-      eG[k] = t.g;
       memset(w.hash, 0, sizeof(uint32_t) * 2 * cap);
-      const PathResult r = findPathInternal(e->nav, w, st, en, s.g, s.pt, t.g, t.pt, true, nullptr, 0, nullptr);
+      const PathResult r = findPathInternal(e->nav, w, st, en, s.g, s.pt, et[k].g, et[k].pt, true, nullptr, 0, nullptr);
       dist[k] = r.dist;
+      if (out_searched) (*out_searched)++;
+    };
+    if (!pruned) {
+      for (int k = 0; k < g; ++k) search(k);
+    } else {
+      for (int k = 0; k < g; ++k) dist[k] = INFINITY;
+      if (multiGoalOrder(g, st, s.g != kNoPoly, ends + i * g * 3, eG.data(), bounds.data(), order.data())) {
+        for (int k = 0; k < g && k < kMultiGoalFirst; ++k) search(order[k]);
+        const float rb = multiGoalRunningBest(g, kMultiGoalFirst, eG.data(), dist.data(), bounds.data(), order.data());
+        for (int k = kMultiGoalFirst; k < g; ++k)
+          if (!(bounds[order[k]] > rb)) search(order[k]);
+      }
     }
     multiGoalSelect(g, st, s.g != kNoPoly, ends + i * g * 3, eG.data(), dist.data(), bounds.data(),
                     order.data(), &out_dist[i], &out_idx[i]);

@@ -139,6 +139,18 @@ def test_find_path_multigoal(scene):
             m = min(wn[i], 32)
             assert beq(got["points"][i, :m], wp[i, :m]).all()
         assert (wi >= 0).mean() > 0.3
+    # many goals: two rounds of pair searches (kMultiGoalFirst goals first, then those the reference
+    # would not skip) must give the reference's answer
+    n2, g2 = 150, 40
+    st2 = query_points(name, n2, 55)
+    en2 = query_points(name, n2 * g2, 56).reshape(n2, g2, 3)
+    en2[:, 5, 1] += 3.0
+    en2[:, 30, 1] += 2.5
+    en2[::6, 2] = (hi + 50).astype(np.float32)
+    en2[::4, 20] = st2[::4] + rng.normal(0, 0.2, (len(st2[::4]), 3)).astype(np.float32)
+    wd, wi, _, _ = ref.find_path_multigoal_batch(st2, en2, nthreads=8)
+    got = pf.find_paths_multigoal(st2, en2)
+    assert (got["closest_end_point_index"] == wi).all() and beq(got["geodesic_distance"], wd).all()
     # multi-goal == min over the single-goal queries (src/tests/PathFinderTest.cpp:102-134) for
     # goals on the mesh, where the L2 bound cannot exceed the geodesic distance
     st = query_points(name, 200, 53, jitter=0.0)

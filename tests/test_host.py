@@ -365,12 +365,30 @@ def test_hostemu_multigoal_matches_oracle(name):
     for gg in (g, 1):
         e = np.ascontiguousarray(ends[:, :gg])
         wd, wi, _, _ = pf.find_path_multigoal_batch(starts, e)
-        gd = np.zeros(n, np.float32)
-        gi = np.zeros(n, np.int32)
-        emu.emu_find_path_multigoal(h, P(starts, f32p), P(e, f32p), C.c_long(n), C.c_int(gg), P(gd, f32p), P(gi, i32p))
-        assert (gi == wi).all()
-        assert beq(gd, wd).all()
+        for pruned in (0, 1):
+            gd = np.zeros(n, np.float32)
+            gi = np.zeros(n, np.int32)
+            emu.emu_find_path_multigoal(h, P(starts, f32p), P(e, f32p), C.c_long(n), C.c_int(gg), P(gd, f32p),
+                                        P(gi, i32p), pruned, None)
+            assert (gi == wi).all()
+            assert beq(gd, wd).all()
         assert (wi >= 0).mean() > 0.5
+    # many goals: the two-round pruning of the batched entry point must not change anything
+    g2 = 40
+    ends2 = query_points(name, n * g2, 43).reshape(n, g2, 3)
+    ends2[:, 3] = ends2[:, 1]
+    ends2[:, 5, 1] += 3.0
+    ends2[:, 30, 1] += 2.5
+    ends2[::7, 2] = (hi + 50).astype(np.float32)
+    ends2[::5, 20] = starts[::5] + rng.normal(0, 0.3, (len(starts[::5]), 3)).astype(np.float32)
+    wd, wi, _, _ = pf.find_path_multigoal_batch(starts, ends2)
+    gd = np.zeros(n, np.float32)
+    gi = np.zeros(n, np.int32)
+    searched = C.c_long(0)
+    emu.emu_find_path_multigoal(h, P(starts, f32p), P(ends2, f32p), C.c_long(n), C.c_int(g2), P(gd, f32p),
+                                P(gi, i32p), 1, C.byref(searched))
+    assert (gi == wi).all() and beq(gd, wd).all()
+    assert searched.value < 0.6 * n * g2
     emu.emu_destroy(h)
 
 

@@ -63,6 +63,11 @@ def main():
     def emit(**kw):
         print(json.dumps(kw), flush=True)
 
+    only = os.environ.get("BENCH_ONLY", "")  # e.g. BENCH_ONLY=C3
+
+    def want(tag):
+        return not only or tag in only.split(",")
+
     def load(name):
         img = navmesh_bytes(name)
         pf = PathFinder(0)
@@ -73,7 +78,7 @@ def main():
 
     # ---- C2: 1024 envs (and more), per step try_step + geodesic distance to the goal ---------
     img, pf, ref, geom = load("c2_apartment")
-    for envs in (1024, 65536):
+    for envs in ((1024, 65536) if want("C2") else ()):
         steps = max(10, int((100 if envs == 1024 else 20) * args.scale))
         pos0, goal = uniform_pairs(geom, envs, 3, jitter=0.0)
         pos0 = ref.snap_batch(pos0, threads)[0]
@@ -106,24 +111,27 @@ def main():
              us_per_step_b200=1e6 * dt / steps,
              bit_exact=beq(p_g.cpu().numpy(), p_c) and beq(d_g.cpu().numpy(), d_c))
 
-    # ---- C3: multi-goal, 4096 starts x 64 goals -------------------------------------------
-    img, pf, ref, geom = load("c3_multiroom")
-    ns, g = int(4096 * args.scale), 64
-    rng = np.random.default_rng(5)
-    st = geom.sample(ns, rng)
-    en = geom.sample(ns * g, rng).reshape(ns, g, 3)
-    st_d, en_d = T(st), T(en)
-    dt, out = gpu_time(lambda: pf.find_paths_multigoal(st_d, en_d))
-    m = min(ns, 64 * threads)
-    dtc, outc = cpu_time(lambda: ref.find_path_multigoal_batch(st[:m], en[:m], 0, threads))
-    gd = out["geodesic_distance"].cpu().numpy() if hasattr(out["geodesic_distance"], "cpu") else out["geodesic_distance"]
-    gi = out["closest_end_point_index"]
-    gi = gi.cpu().numpy() if hasattr(gi, "cpu") else gi
-    emit(config=f"C3 MultiGoalShortestPath: {ns} starts x {g} goals on c3_multiroom (fresh objects)",
-         unit="starts/s", b200=ns / dt, reference_cpu=m / dtc, cores=threads, cpu_sample=m,
-         pair_searches_per_s_b200=ns * g / dt,
-         bit_exact=beq(gd[:m], outc[0]) and bool((gi[:m] == outc[1]).all()))
+    if want("C3"):
+        # ---- C3: multi-goal, 4096 starts x 64 goals -------------------------------------------
+        img, pf, ref, geom = load("c3_multiroom")
+        ns, g = int(4096 * args.scale), 64
+        rng = np.random.default_rng(5)
+        st = geom.sample(ns, rng)
+        en = geom.sample(ns * g, rng).reshape(ns, g, 3)
+        st_d, en_d = T(st), T(en)
+        dt, out = gpu_time(lambda: pf.find_paths_multigoal(st_d, en_d))
+        m = min(ns, 64 * threads)
+        dtc, outc = cpu_time(lambda: ref.find_path_multigoal_batch(st[:m], en[:m], 0, threads))
+        gd = out["geodesic_distance"].cpu().numpy() if hasattr(out["geodesic_distance"], "cpu") else out["geodesic_distance"]
+        gi = out["closest_end_point_index"]
+        gi = gi.cpu().numpy() if hasattr(gi, "cpu") else gi
+        emit(config=f"C3 MultiGoalShortestPath: {ns} starts x {g} goals on c3_multiroom (fresh objects)",
+             unit="starts/s", b200=ns / dt, reference_cpu=m / dtc, cores=threads, cpu_sample=m,
+             pair_searches_per_s_b200=ns * g / dt,
+             bit_exact=beq(gd[:m], outc[0]) and bool((gi[:m] == outc[1]).all()))
 
+    if not (want("C4") or want("C5")):
+        return
     # ---- C4: snap_point --------------------------------------------------------------------
     img, pf, ref, geom = load("c4_building")
     n = int(1_000_000 * args.scale)
