@@ -17,8 +17,28 @@ from workloads.scenes import NavMeshGeom, navmesh_bytes, step_targets  # noqa: E
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def make(name: str, n: int, seed: int):
-    image = navmesh_bytes(name, cache=False)
+REF_SCENES = "/root/reference/data/test_assets/scenes"
+
+
+def ref_asset_image(name: str) -> bytes:
+    """Navmesh of one of the REFERENCE's own test scenes (data/test_assets/scenes/<name>.glb, read
+    here only): triangles via workloads/glb.py, the stage config's up axis / scale applied
+    (simple_room: up = +z; stage_floor1: scale 2), built by the reference's Recast with default
+    NavMeshSettings and round-tripped through save -> load like every other scene."""
+    from workloads.glb import load_triangles
+    v, t = load_triangles(os.path.join(REF_SCENES, name + ".glb"))
+    if name == "simple_room":
+        v = np.stack([v[:, 0], v[:, 2], -v[:, 1]], 1).astype(np.float32)
+    elif name == "stage_floor1":
+        v = (v * 2.0).astype(np.float32)
+    pf = RefPathFinder()
+    assert pf.build(v, t), name
+    return pf.save_bytes()
+
+
+def make(name: str, n: int, seed: int, image: bytes | None = None):
+    if image is None:
+        image = navmesh_bytes(name, cache=False)
     pf = RefPathFinder()
     assert pf.load_bytes(image)
     geom = NavMeshGeom(image)
@@ -50,13 +70,18 @@ def make(name: str, n: int, seed: int):
         step_targets=tgt, step_sliding=step_s, step_nosliding=step_n, hit_pos=hp, hit_normal=hn,
         hit_dist=hd, rand_islands=isl, rand_pts=rp, rand_refs=rr, mg_ends=mg_ends, mg_dist=mg_d,
         mg_idx=mg_i, mg_npts=mg_n, poly_refs=refs_all, poly_islands=isl_all,
-        num_islands=np.int32(pf.num_islands), area=np.float32(pf.navigable_area()),
+        seed=np.int32(seed), num_islands=np.int32(pf.num_islands), area=np.float32(pf.navigable_area()),
         island_radius=np.array([pf.island_radius(i) for i in range(pf.num_islands)], np.float32),
         island_area=np.array([pf.navigable_area(i) for i in range(pf.num_islands)], np.float32))
     print(name, "ok", n)
 
 
 if __name__ == "__main__":
-    make("c1_room", 200, 11)
-    make("c2_apartment", 400, 12)
-    make("t_building", 400, 13)
+    only = sys.argv[1:]
+    for name, n, seed in (("c1_room", 200, 11), ("c2_apartment", 400, 12), ("t_building", 400, 13)):
+        if not only or name in only:
+            make(name, n, seed)
+    # non-procedural geometry: the reference's own test scenes
+    for asset, n, seed in (("simple_room", 400, 14), ("stage_floor1", 400, 15)):
+        if not only or "ref_" + asset in only:
+            make("ref_" + asset, n, seed, ref_asset_image(asset))

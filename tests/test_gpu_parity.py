@@ -230,7 +230,7 @@ def test_random_points(scene):
     assert beq(a[50:], b).all()
 
 
-@pytest.mark.parametrize("name", ["c1_room", "c2_apartment", "t_building"])
+@pytest.mark.parametrize("name", ["c1_room", "c2_apartment", "t_building", "ref_simple_room", "ref_stage_floor1"])
 def test_golden_vectors(name):
     """committed fixtures (tests/golden/*.npz, made by make_golden.py from the oracle)"""
     g = np.load(os.path.join(GOLD, name + ".npz"))
@@ -250,7 +250,7 @@ def test_golden_vectors(name):
     assert beq(pf.try_steps(g["snap_pts"], g["step_targets"], False), g["step_nosliding"]).all()
     hp, hn, hd = pf.closest_obstacle_surface_points(g["starts"], 2.0)
     assert beq(hd, g["hit_dist"]).all() and beq(hp, g["hit_pos"]).all() and beq(hn, g["hit_normal"]).all()
-    seed = {"c1_room": 11, "c2_apartment": 12, "t_building": 13}[name]
+    seed = int(g["seed"]) if "seed" in g else {"c1_room": 11, "c2_apartment": 12, "t_building": 13}[name]
     rp, rr = pf.random_navigable_points(len(g["rand_islands"]), 10, g["rand_islands"], seed=seed, query0=1000)
     assert (rr == g["rand_refs"]).all() and beq(rp, g["rand_pts"]).all()
     assert pf.num_islands == int(g["num_islands"])
