@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 import struct
 
 import numpy as np
@@ -105,6 +106,41 @@ class NavMeshSettings:
         for k, v in zip(cls._FIELDS, struct.unpack(cls._FMT, b[:56])):
             setattr(s, k, v)
         return s
+
+    # PathFinder.cpp:68-93 + io/JsonEspTypes.cpp:287-331: the 16 serialised fields and their keys
+    # (include_static_objects is not part of the JSON form)
+    _JSON_KEYS = ["cellSize", "cellHeight", "agentHeight", "agentRadius", "agentMaxClimb", "agentMaxSlope",
+                  "regionMinSize", "regionMergeSize", "edgeMaxLen", "edgeMaxError", "vertsPerPoly",
+                  "detailSampleDist", "detailSampleMaxError", "filterLowHangingObstacles", "filterLedgeSpans",
+                  "filterWalkableLowHeightSpans"]
+
+    def read_from_json(self, json_file: str) -> None:
+        """NavMeshSettings::readFromJSON: members present in the file overwrite the fields; a missing
+        file or a parse error is logged, not raised (PathFinder.cpp:68-81)."""
+        import json
+        import logging
+        if not os.path.exists(json_file):
+            logging.getLogger("habitat_sim_b200.nav").error("File %s not found.", json_file)
+            return
+        try:
+            with open(json_file) as f:
+                doc = json.load(f)
+            for key, field in zip(self._JSON_KEYS, self._FIELDS):
+                if key in doc:
+                    cur = getattr(self, field)
+                    setattr(self, field, bool(doc[key]) if isinstance(cur, bool) else float(doc[key]))
+        except Exception:  # noqa: BLE001 (the reference catches everything here)
+            logging.getLogger("habitat_sim_b200.nav").error("Failed to parse %s.", json_file)
+
+    def write_to_json(self, json_file: str) -> None:
+        """NavMeshSettings::writeToJSON (PathFinder.cpp:83-93): 7 decimal places at most."""
+        import json
+        doc = {}
+        for key, field in zip(self._JSON_KEYS, self._FIELDS):
+            v = getattr(self, field)
+            doc[key] = bool(v) if isinstance(v, bool) else round(float(np.float32(v)), 7)
+        with open(json_file, "w") as f:
+            json.dump(doc, f, indent=4)
 
     def __eq__(self, o):
         if not isinstance(o, NavMeshSettings):

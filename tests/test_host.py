@@ -477,3 +477,34 @@ def test_sharding_gloo_world2():
         out, _ = p.communicate(timeout=240)
         assert p.returncode == 0, out[-2000:]
         assert f"rank {rank} ok" in out
+
+
+def test_navmesh_settings_json_like_the_reference(tmp_path):
+    """NavMeshSettings JSON form (PathFinder.cpp:68-93, io/JsonEspTypes.cpp:287-331): round trip as in
+    the reference's tests/test_nav.py:678-695, and the reference's own fixture
+    data/test_assets/test_navmeshsettings.json (its values restated here)."""
+    import json
+    import habitat_sim_b200  # noqa: F401
+    from habitat_sim_b200.nav import NavMeshSettings
+    s = NavMeshSettings()
+    s.set_defaults()
+    s.agent_radius = 0.42
+    path = str(tmp_path / "navmesh_settings.json")
+    s.write_to_json(path)
+    data = json.load(open(path))
+    assert isinstance(data, dict) and len(data) == 16 and abs(data["agentRadius"] - 0.42) < 1e-6
+    s2 = NavMeshSettings()
+    s2.read_from_json(path)
+    assert s == s2
+    fixture = {"cellSize": 0.0123, "cellHeight": 0.234, "agentHeight": 1.2345, "agentRadius": 0.123,
+               "agentMaxClimb": 0.234, "agentMaxSlope": 34.0, "regionMinSize": 23.0, "regionMergeSize": 25.0,
+               "edgeMaxLen": 23.0, "edgeMaxError": 1.345, "vertsPerPoly": 9.0, "detailSampleDist": 9.0,
+               "detailSampleMaxError": 2.0, "filterLowHangingObstacles": False, "filterLedgeSpans": False,
+               "filterWalkableLowHeightSpans": False}
+    json.dump(fixture, open(path, "w"))
+    s3 = NavMeshSettings()
+    s3.read_from_json(path)
+    assert abs(s3.cell_size - 0.0123) < 1e-7 and abs(s3.agent_height - 1.2345) < 1e-6
+    assert s3.verts_per_poly == 9.0 and s3.filter_ledge_spans is False and s3 != s
+    s3.read_from_json(str(tmp_path / "missing.json"))  # logged, not raised
+    assert abs(s3.edge_max_error - 1.345) < 1e-6
