@@ -61,7 +61,7 @@ SYMBOLS = [
     "hbn_find_path_multigoal_dev", "hbn_try_step_dev", "hbn_closest_obstacle_dev",
     "hbn_random_points_dev", "hbn_uniform", "hbn_snap_point", "hbn_is_navigable",
     "hbn_find_path", "hbn_find_path_multigoal", "hbn_try_step", "hbn_closest_obstacle",
-    "hbn_random_points",
+    "hbn_random_points", "hbn_random_points_near_dev", "hbn_random_points_near",
 ]
 
 
@@ -103,6 +103,8 @@ def lib():
                                                                    vp] + extra
             getattr(l, "hbn_random_points" + suffix).argtypes = [vp, C.c_uint64, C.c_uint64, C.c_int64, vp,
                                                                 C.c_int, vp, vp] + extra
+            getattr(l, "hbn_random_points_near" + suffix).argtypes = [vp, C.c_uint64, C.c_uint64, C.c_int64, vp,
+                                                                     C.c_float, vp, C.c_int, vp] + extra
         _lib = l
     return _lib
 

@@ -893,6 +893,24 @@ int hbn_random_points_dev(hbn_navmesh_t nm, uint64_t seed, uint64_t query0, int6
   return HBN_OK;
 }
 
+int hbn_random_points_near_dev(hbn_navmesh_t nm, uint64_t seed, uint64_t query0, int64_t n,
+                               const float* centers, float radius, const int32_t* islands, int max_tries,
+                               float* out_pts, void* stream) {
+  if (!nm || (n > 0 && (!out_pts || !centers))) return fail(HBN_ERR_INVALID, "null argument");
+  if (n <= 0) return HBN_OK;
+  if (nm->flat.totalArea <= 0.0f)
+    return fail(HBN_ERR_NO_AREA, "NavMesh has no navigable area, this indicates an issue with the NavMesh");
+  DeviceGuard g(nm->device);
+  const int groupsPerBlock = 256 / kRandW;
+  int64_t blocks = std::min<int64_t>((n + groupsPerBlock - 1) / groupsPerBlock,
+                                     static_cast<int64_t>(nm->smCount) * 64);
+  k_random_near<kRandW><<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      nm->view, seed, query0, n, centers, radius, islands, max_tries, out_pts);
+  nm->launches++;
+  CK(cudaGetLastError());
+  return HBN_OK;
+}
+
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------
@@ -1064,6 +1082,20 @@ int hbn_random_points(hbn_navmesh_t nm, uint64_t seed, uint64_t query0, int64_t 
   if ((rc = io.prepare()) || (rc = io.h2d())) return rc;
   if ((rc = hbn_random_points_dev(nm, seed, query0, n, islands ? io.dev<int32_t>(oI) : nullptr, max_tries,
                                   io.dev<float>(oP), out_refs ? io.dev<uint32_t>(oR) : nullptr, nm->stream)))
+    return rc;
+  return io.d2h();
+}
+
+int hbn_random_points_near(hbn_navmesh_t nm, uint64_t seed, uint64_t query0, int64_t n, const float* centers,
+                           float radius, const int32_t* islands, int max_tries, float* out_pts) {
+  HOST_PROLOGUE
+  const size_t oC = io.add(n * 12, centers, nullptr);
+  const size_t oI = islands ? io.add(n * 4, islands, nullptr) : 0;
+  const size_t oP = io.add(n * 12, nullptr, out_pts);
+  if ((rc = io.prepare()) || (rc = io.h2d())) return rc;
+  if ((rc = hbn_random_points_near_dev(nm, seed, query0, n, io.dev<float>(oC), radius,
+                                       islands ? io.dev<int32_t>(oI) : nullptr, max_tries, io.dev<float>(oP),
+                                       nm->stream)))
     return rc;
   return io.d2h();
 }

@@ -501,4 +501,27 @@ __global__ void __launch_bounds__(256) k_random(NavView nav, uint64_t seed, uint
   }
 }
 
+// getRandomNavigablePointInCircle (get_random_navigable_point_near), W lanes per sample
+template <int W>
+__global__ void __launch_bounds__(256) k_random_near(NavView nav, uint64_t seed, uint64_t query0, int64_t n,
+                                                     const float* __restrict__ centers, float radius,
+                                                     const int32_t* __restrict__ islands, int maxTries,
+                                                     float* __restrict__ out_pts) {
+  WarpGroup<W> grp;
+  const int gInBlock = threadIdx.x / W;
+  const int64_t groupsPerGrid = static_cast<int64_t>(gridDim.x) * (blockDim.x / W);
+  for (int64_t q = static_cast<int64_t>(blockIdx.x) * (blockDim.x / W) + gInBlock; q < n;
+       q += groupsPerGrid) {
+    const float c[3] = {centers[3 * q], centers[3 * q + 1], centers[3 * q + 2]};
+    float pt[3];
+    randomPointInCircle(nav, grp, seed, query0 + static_cast<uint64_t>(q), islands ? islands[q] : -1, c, radius,
+                        maxTries, pt);
+    if (grp.lane() == 0) {
+      out_pts[3 * q] = pt[0];
+      out_pts[3 * q + 1] = pt[1];
+      out_pts[3 * q + 2] = pt[2];
+    }
+  }
+}
+
 }  // namespace hbn

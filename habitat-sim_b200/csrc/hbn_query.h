@@ -1244,6 +1244,126 @@ HBN_HD uint32_t findRandomPoint(const NavView& nav, const G& grp, uint64_t seed,
   return g;
 }
 
+// ---------------------------------------------------------------------------------------
+// getRandomNavigablePointInCircle (PF.cpp:1283-1332; Python get_random_navigable_point_near):
+// findRandomPoint with a filter that additionally excludes, among the polys that belong to an
+// island, those off the requested island and those with no "edge" within the radius of the
+// circle centre -- as IslandSystem::setPolyFlagForIslandCircle tests it (PF.cpp:345-393, trap
+// T6: the edge (v[i], v[(i+1) % 3]) whatever the vertex count).  The passing set depends on the
+// query, so the running area sums cannot be tabulated: the filter is evaluated lane-parallel over
+// the tile's ground polys, the f32 area sum and the reservoir draw replayed in poly order.
+// ---------------------------------------------------------------------------------------
+HBN_HD float nanF();  // defined below
+
+HBN_HD bool polyInCircleRange(const PolyRec* p, const float* center, float radSqr) {
+  for (int i = 0; i < p->nv; ++i) {
+    const int n = (i + 1) % 3;
+    float t;
+    if (distPtSegSqr2D(center, &p->v[i * 3], &p->v[n * 3], t) < radSqr) return true;
+  }
+  return false;
+}
+
+template <class G>
+HBN_HD uint32_t findRandomPointCircle(const NavView& nav, const G& grp, uint64_t seed, uint64_t query,
+                                      uint32_t drawBase, int island, const float* center, float radSqr,
+                                      float* outPt, uint32_t* drawsUsed) {
+  constexpr int W = G::kWidth;
+  const int lane = grp.lane();
+  int chosen = -1;
+  {  // tile reservoir, as findRandomPoint (the filter plays no part in it, DQ.cpp:236-251)
+    int best = -1;
+    uint32_t k = 0;
+    for (uint32_t base = 0; base < nav.numTiles; base += W) {
+      const uint32_t ti = base + lane;
+      const bool present = ti < nav.numTiles && nav.tiles[ti].pad[0] != 0;
+      const uint32_t pm = grp.ballot(present);
+      if (present) {
+        const uint32_t rank = k + popc32(pm & ((1u << lane) - 1u));
+        const float tsum = static_cast<float>(rank + 1);
+        const float u = uniform01(seed, query, drawBase + rank);
+        if (u * tsum <= 1.0f) best = static_cast<int>(ti);
+      }
+      k += popc32(pm);
+    }
+    for (int off = W / 2; off > 0; off >>= 1) {
+      const int o = grp.shfl(best, lane ^ off);
+      best = o > best ? o : best;
+    }
+    chosen = best;
+    *drawsUsed = k;
+  }
+  if (chosen < 0) return kNoPoly;
+  const TileRec& tr = nav.tiles[chosen];
+  const uint32_t w0 = tr.randStart, wn = tr.randCount;  // ground polys passing the default filter
+  uint32_t draws = *drawsUsed;
+  float areaSum = 0.0f;
+  uint32_t pick = kNoPoly;
+  for (uint32_t base = 0; base < wn; base += W) {
+    const uint32_t e = base + lane;
+    bool pass = false;
+    uint32_t g = kNoPoly;
+    float area = 0.f;
+    if (e < wn) {
+      const RandEntry re = nav.randEntries[w0 + e];
+      g = re.g;
+      area = re.area;
+      const PolyRec* p = &nav.polys[g];
+      // polys without an island keep their flags (they are in no island's list)
+      pass = p->island < 0 || ((island < 0 || p->island == island) && polyInCircleRange(p, center, radSqr));
+    }
+    uint32_t m = grp.ballot(pass);
+    while (m) {  // DQ.cpp:262-283 over the passing polys, in poly order
+      const int j = ffs32(m) - 1;
+      m &= m - 1;
+      const float aj = grp.shfl(area, j);
+      const uint32_t gj = grp.shfl(g, j);
+      areaSum += aj;
+      const float u = uniform01(seed, query, drawBase + draws);
+      draws++;
+      if (u * areaSum <= aj) pick = gj;
+    }
+  }
+  *drawsUsed = draws;
+  if (pick == kNoPoly) return kNoPoly;
+  const PolyRec* p = &nav.polys[pick];
+  const float s = uniform01(seed, query, drawBase + draws);
+  const float t = uniform01(seed, query, drawBase + draws + 1);
+  *drawsUsed = draws + 2;
+  float pt[3];
+  randomPointInConvexPoly(p->v, p->nv, s, t, pt);
+  float cp[3];
+  bool over;
+  closestPointOnPoly(nav, p, pt, cp, &over);
+  if (vfinite(pt)) vcopy(outPt, cp);
+  else vcopy(outPt, pt);
+  return pick;
+}
+
+// the retry loop of PF.cpp:1304-1318; returns the poly, outPt = NaN on failure
+template <class G>
+HBN_HD uint32_t randomPointInCircle(const NavView& nav, const G& grp, uint64_t seed, uint64_t query, int island,
+                                    const float* center, float radius, int maxTries, float* outPt) {
+  const float radSqr = radius * radius;
+  uint32_t draw = 0;
+  for (int i = 0; i < maxTries; ++i) {
+    uint32_t used = 0;
+    float p[3];
+    const uint32_t g = findRandomPointCircle(nav, grp, seed, query, draw, island, center, radSqr, p, &used);
+    draw += used;
+    if (g != kNoPoly) {
+      const float xd = center[0] - p[0], yd = center[2] - p[2];
+      const float d2 = xd * xd + yd * yd;
+      if (d2 < radSqr) {
+        vcopy(outPt, p);
+        return g;
+      }
+    }
+  }
+  outPt[0] = outPt[1] = outPt[2] = nanF();
+  return kNoPoly;
+}
+
 // =======================================================================================
 // Per-query pipelines (the esp::nav::PathFinder::Impl layer, PF.cpp), one lane each.
 // =======================================================================================

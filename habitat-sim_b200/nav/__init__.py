@@ -539,6 +539,47 @@ class PathFinder:
                                   max_tries, out.ctypes.data, refs.ctypes.data))
         return out, refs
 
+    def random_navigable_points_near(self, circle_centers, radius: float, max_tries: int = 100, island_index=-1,
+                                     seed=None, query0=None):
+        """Batched get_random_navigable_point_near (getRandomNavigablePointInCircle, PF.cpp:1283-1332):
+        one sample per centre [N,3]; NaN rows where max_tries samples all fell outside the circle.
+        island_index: int or [N] array."""
+        h = self._need()
+        L = _lib.lib()
+        seed = self._seed if seed is None else int(seed)
+        torch_in = _is_torch(circle_centers)
+        n = int(circle_centers.shape[0]) if torch_in else len(np.asarray(circle_centers).reshape(-1, 3))
+        if query0 is None:
+            query0 = self._rand_counter
+            self._rand_counter += n
+        isl = None
+        if not isinstance(island_index, (int, np.integer)):
+            isl = island_index
+        else:
+            if island_index != -1 and not (0 <= island_index < self.num_islands):
+                raise ValueError(f"{island_index} not a valid index for this island system.")
+            if self.island_area(int(island_index)) <= 0.0:
+                raise RuntimeError("NavMesh has no navigable area, this indicates an issue with the NavMesh")
+            if island_index != -1:
+                isl = np.full(n, island_index, np.int32)
+        if torch_in:
+            import torch
+            torch_, dev, (c,), st = self._torch_args(circle_centers.float().reshape(-1, 3))
+            if isl is not None and not _is_torch(isl):
+                isl = torch.as_tensor(np.asarray(isl, np.int32), device=dev)
+            out = torch.empty((n, 3), dtype=torch.float32, device=dev)
+            check(L.hbn_random_points_near_dev(h, seed, query0, n, c.data_ptr(), float(radius),
+                                               isl.data_ptr() if isl is not None else None, int(max_tries),
+                                               out.data_ptr(), st))
+            return out
+        c = np.ascontiguousarray(np.asarray(circle_centers, np.float32).reshape(-1, 3))
+        islnp = None if isl is None else np.ascontiguousarray(isl, dtype=np.int32)
+        out = np.empty((n, 3), np.float32)
+        check(L.hbn_random_points_near(h, seed, query0, n, c.ctypes.data, float(radius),
+                                       islnp.ctypes.data if islnp is not None else None, int(max_tries),
+                                       out.ctypes.data))
+        return out
+
     # ---- scalar API, SPB.cpp:177-270 -------------------------------------------------
     def find_path(self, path) -> bool:
         if isinstance(path, MultiGoalShortestPath):
@@ -592,6 +633,12 @@ class PathFinder:
         return self.random_navigable_points(1, max_tries, island_index)[0][0]
 
     # ---- top-down maps, PathFinder.cpp:1833-1896 -------------------------------------
+    def get_random_navigable_point_near(self, circle_center, radius: float, max_tries: int = 100,
+                                        island_index: int = -1):
+        """SPB.cpp:179-183: a random navigable point within `radius` of circle_center (NaN on failure)."""
+        return self.random_navigable_points_near(np.asarray(circle_center, np.float32)[None], radius, max_tries,
+                                                 island_index)[0]
+
     def _topdown_grid(self, meters_per_pixel: float, height: float):
         b1, b2 = self.get_bounds()
         mpp = np.float32(meters_per_pixel)

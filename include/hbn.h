@@ -152,6 +152,13 @@ int hbn_closest_obstacle_dev(hbn_navmesh_t nm, const float* pts, int64_t n, floa
 int hbn_random_points_dev(hbn_navmesh_t nm, uint64_t seed, uint64_t query0, int64_t n,
                           const int32_t* islands, int max_tries, float* out_pts,
                           uint32_t* out_refs, void* stream);
+/* getRandomNavigablePointInCircle, PF.cpp:1283-1332 (Python get_random_navigable_point_near, SPB.cpp:179-183):
+ * sample i is drawn with the filter of setPolyFlagForIslandCircle(centers[i], radius, islands[i])
+ * (PF.cpp:330-393) and accepted when it lies within `radius` of its centre in xz; NaN after
+ * max_tries.  Same counter-based stream as hbn_random_points. */
+int hbn_random_points_near_dev(hbn_navmesh_t nm, uint64_t seed, uint64_t query0, int64_t n,
+                               const float* centers, float radius, const int32_t* islands, int max_tries,
+                               float* out_pts, void* stream);
 float hbn_uniform(uint64_t seed, uint64_t query, uint32_t draw);
 
 /* ---- the same queries with HOST buffers (copies + synchronisation inside) ---------- */
@@ -172,6 +179,8 @@ int hbn_closest_obstacle(hbn_navmesh_t nm, const float* pts, int64_t n, float ma
                          float* out_hit_pos, float* out_hit_normal, float* out_hit_dist);
 int hbn_random_points(hbn_navmesh_t nm, uint64_t seed, uint64_t query0, int64_t n,
                       const int32_t* islands, int max_tries, float* out_pts, uint32_t* out_refs);
+int hbn_random_points_near(hbn_navmesh_t nm, uint64_t seed, uint64_t query0, int64_t n, const float* centers,
+                           float radius, const int32_t* islands, int max_tries, float* out_pts);
 
 #ifdef __cplusplus
 }

@@ -336,4 +336,15 @@ void emu_random_points(void* h, long n, int maxTries, const int* islands, unsign
   }
 }
 
+// get_random_navigable_point_near (randomPointInCircle, hbn_query.h)
+void emu_random_points_near(void* h, long n, const float* centers, float radius, int maxTries,
+                            const int* islands, unsigned long long seed, unsigned long long query0,
+                            float* out_pts) {
+  Emu* e = static_cast<Emu*>(h);
+  HostGroup grp;
+  for (long i = 0; i < n; ++i)
+    randomPointInCircle(e->nav, grp, seed, query0 + i, islands ? islands[i] : -1, centers + 3 * i, radius,
+                        maxTries, out_pts + 3 * i);
+}
+
 }  // extern "C"

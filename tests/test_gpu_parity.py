@@ -212,6 +212,37 @@ def test_closest_obstacle(scene):
     assert beq(pf.distances_to_closest_obstacle(pts[:2000], 0.5), hd5).all()
 
 
+def test_random_points_near(scene):
+    """get_random_navigable_point_near (getRandomNavigablePointInCircle, PF.cpp:1283-1332, trap T6): the
+    oracle's samples on the same uniform stream, plain and island restricted; and the properties the
+    reference's tests/test_nav.py:159-183 checks (navigable, within the radius)."""
+    name, pf, ref = scene
+    n = 1500
+    rng = np.random.default_rng(4)
+    centers = ref.snap_batch(query_points(name, n, 36, jitter=0.05), 8)[0]
+    centers[np.isnan(centers)] = 0
+    isl = np.full(n, -1, np.int32)
+    isl[n // 2:] = rng.integers(0, ref.num_islands, n - n // 2)
+    for radius, tries in ((2.0, 100), (0.5, 8)):
+        want = ref.random_points_near(centers, radius, tries, isl, mode=1, seed=5, query0=40)
+        got = pf.random_navigable_points_near(centers, radius, tries, isl, seed=5, query0=40)
+        assert beq(got, want).all()
+        ok = np.isfinite(got).all(axis=1)
+        assert (np.linalg.norm((got - centers)[ok][:, [0, 2]], axis=1) < radius).all()
+        assert pf.are_navigable(got[ok]).all()
+    import torch
+    dev_out = pf.random_navigable_points_near(torch.from_numpy(centers).cuda(), 2.0, 100, isl, seed=5, query0=40)
+    assert beq(dev_out.cpu().numpy(), ref.random_points_near(centers, 2.0, 100, isl, mode=1, seed=5, query0=40)).all()
+    # scalar API as the reference's test uses it
+    pf.seed(3)
+    for _ in range(20):
+        p = pf.get_random_navigable_point()
+        q = pf.get_random_navigable_point_near(p, 5.0, max_tries=100)
+        assert pf.is_navigable(q) and np.linalg.norm(np.asarray(p) - np.asarray(q)) <= 5.0 + 4.0  # xz test: y may differ
+    with pytest.raises(ValueError):
+        pf.get_random_navigable_point_near(centers[0], 1.0, island_index=999)
+
+
 def test_random_points(scene):
     name, pf, ref = scene
     n = 3000

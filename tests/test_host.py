@@ -162,6 +162,16 @@ def test_hostemu_queries_match_oracle(name):
     emu.emu_random_points(h, C.c_long(m), 10, P(ri, i32p), C.c_ulonglong(99), C.c_ulonglong(5), P(got_p, f32p),
                           P(got_r, u32p))
     assert (want_r == got_r).all() and beq(want_p, got_p).all()
+    # get_random_navigable_point_near: circle filter (trap T6), plain and island restricted
+    centers = np.ascontiguousarray(o_pts[200:200 + m])
+    centers[np.isnan(centers)] = 0
+    for radius, tries in ((1.5, 100), (0.4, 6)):
+        want = pf.random_points_near(centers, radius, tries, ri, mode=1, seed=7, query0=11)
+        got = np.zeros((m, 3), np.float32)
+        emu.emu_random_points_near(h, C.c_long(m), P(centers, f32p), C.c_float(radius), tries, P(ri, i32p),
+                                   C.c_ulonglong(7), C.c_ulonglong(11), P(got, f32p))
+        assert beq(want, got).all()
+        assert np.isfinite(want).all(axis=1).mean() > (0.5 if tries == 100 else 0.02)  # few tries: mostly NaN
     emu.emu_destroy(h)
 
 
