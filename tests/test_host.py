@@ -518,3 +518,23 @@ def test_navmesh_settings_json_like_the_reference(tmp_path):
     assert s3.verts_per_poly == 9.0 and s3.filter_ledge_spans is False and s3 != s
     s3.read_from_json(str(tmp_path / "missing.json"))  # logged, not raised
     assert abs(s3.edge_max_error - 1.345) < 1e-6
+
+
+def test_pathfinder_not_loaded_like_the_reference():
+    """tests/test_nav.py:95-99: a fresh PathFinder is not loaded and has no settings (no device needed);
+    queries on it raise instead of answering from nowhere."""
+    import habitat_sim_b200  # noqa: F401
+    from habitat_sim_b200.nav import HitRecord, MultiGoalShortestPath, PathFinder, ShortestPath
+    pf = PathFinder()
+    assert not pf.is_loaded and pf.nav_mesh_settings is None
+    with pytest.raises(RuntimeError):
+        pf.snap_point(np.zeros(3, np.float32))
+    sp = ShortestPath()  # tests/test_nav.py:273-280
+    sp.requested_start = np.array([0.0, 0.0, 0.0])
+    sp.requested_end = np.array([1.0, 0.0, 1.0])
+    assert np.allclose(sp.requested_start, [0, 0, 0]) and np.allclose(sp.requested_end, [1, 0, 1])
+    assert len(sp.points) == 0
+    mg = MultiGoalShortestPath()
+    assert mg.closest_end_point_index == -1 and len(mg.points) == 0
+    hr = HitRecord()  # tests/test_nav.py:229-234
+    _ = hr.hit_pos, hr.hit_normal, hr.hit_dist
