@@ -83,13 +83,15 @@ class ClockSampler:
             self._stop.wait(0.2)
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        if self.index >= 0:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
         return self
 
     def __exit__(self, *a):
         self._stop.set()
-        self._t.join(timeout=6)
+        if self._t is not None:
+            self._t.join(timeout=6)
 
     def summary(self):
         sm, mx, reasons = [], [], set()
@@ -221,7 +223,8 @@ def main():
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(args.steps)]
     barrier()
-    with ClockSampler(local) as clocks:
+    # rank 0 samples its GPU's clocks (one nvidia-smi poller per node is enough)
+    with ClockSampler(local if rank == 0 else -1) as clocks:
         for k in range(args.steps):
             flush.zero_()  # L2 flush between timed iterations (outside the event pair)
             ev[k][0].record()
