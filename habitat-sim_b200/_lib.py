@@ -61,7 +61,7 @@ SYMBOLS = [
     "hbn_find_path_multigoal_dev", "hbn_try_step_dev", "hbn_closest_obstacle_dev",
     "hbn_random_points_dev", "hbn_uniform", "hbn_snap_point", "hbn_is_navigable",
     "hbn_find_path", "hbn_find_path_multigoal", "hbn_try_step", "hbn_closest_obstacle",
-    "hbn_random_points", "hbn_random_points_near_dev", "hbn_random_points_near",
+    "hbn_random_points", "hbn_random_points_near_dev", "hbn_random_points_near", "hbn_std_sort_order",
 ]
 
 
@@ -75,6 +75,8 @@ def lib():
         l.hbn_last_error.restype = C.c_char_p
         l.hbn_uniform.restype = C.c_float
         l.hbn_uniform.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32]
+        l.hbn_std_sort_order.restype = None
+        l.hbn_std_sort_order.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         l.hbn_navmesh_launch_count.restype = C.c_int64
         l.hbn_navmesh_launch_count.argtypes = [C.c_void_p]
         l.hbn_navmesh_work_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_int]

@@ -388,6 +388,11 @@ int hbn_device_count(void) {
 
 float hbn_uniform(uint64_t seed, uint64_t query, uint32_t draw) { return uniform01(seed, query, draw); }
 
+void hbn_std_sort_order(const float* key, int n, int32_t* order) {
+  for (int i = 0; i < n; ++i) order[i] = i;
+  stdSortOrder(order, key, n);
+}
+
 int hbn_navmesh_create_from_mset(const void* bytes, size_t len, int device, hbn_navmesh_t* out) {
   if (!bytes || !out) return fail(HBN_ERR_INVALID, "null argument");
   *out = nullptr;

@@ -20,7 +20,8 @@ from .sharding import gather as gather_shards, shard_slice, shard_slices  # noqa
 
 __all__ = ["shard_slices", "shard_slice", "gather_shards", "PathFinder", "ShortestPath", "MultiGoalShortestPath", "HitRecord", "NavMeshSettings",
            "GreedyFollowerCodes", "GreedyGeodesicFollowerImpl", "GreedyGeodesicFollower",
-           "GreedyGeodesicFollowerBatch", "GreedyGeodesicFollowerBatchImpl", "HbnError"]
+           "GreedyGeodesicFollowerBatch", "GreedyGeodesicFollowerBatchImpl", "HbnError",
+           "multigoal_find_path", "std_sort_order"]
 
 MAX_PATH_POINTS = 256  # MAX_POLYS, PathFinder.cpp:1443
 
@@ -58,9 +59,11 @@ class ShortestPath:
 class MultiGoalShortestPath:
     """esp::nav::MultiGoalShortestPath, PathFinder.h:81-123 / SPB.cpp:53-74.
 
-    Each find_path() call evaluates the goals like a freshly constructed reference object
-    (PathFinder.cpp:1515-1572); the reference's cross-call pruning cache changes cost, not
-    results (src/tests/PathFinderTest.cpp:136-164)."""
+    The object keeps the reference's private state (MultiGoalShortestPath::Impl, PathFinder.cpp:95-123)
+    so that a REUSED object behaves like the reference's: the goals are projected once per
+    `requested_ends` assignment, the per-goal lower bounds carry over from call to call
+    (PathFinder.cpp:1521-1539), and the validity flags are only ever appended (trap T4: after assigning
+    new ends the flags of the old ones are read)."""
 
     def __init__(self):
         self.requested_start = np.zeros(3, np.float32)
@@ -68,14 +71,81 @@ class MultiGoalShortestPath:
         self.points: list = []
         self.geodesic_distance = float("inf")
         self.closest_end_point_index = -1
+        # Impl
+        self._ends_projected = False                 # "endRefs not empty"
+        self._end_is_valid: list = []                # append only, never cleared (PathFinder.cpp:1497-1500)
+        self._min_theoretical_dist = np.zeros(0, np.float32)
+        self._prev_requested_start = np.zeros(3, np.float32)
 
     @property
     def requested_ends(self):
         return [e.copy() for e in self._requested_ends]
 
     @requested_ends.setter
-    def requested_ends(self, ends):
+    def requested_ends(self, ends):  # setRequestedEnds, PathFinder.cpp:111-118
         self._requested_ends = np.ascontiguousarray(np.asarray(ends, dtype=np.float32).reshape(-1, 3))
+        self._ends_projected = False
+        self._min_theoretical_dist = np.zeros(len(self._requested_ends), np.float32)
+
+
+def _mn_length(d):
+    """Magnum Vector3::length() in float32: sqrt(((0 + x^2) + y^2) + z^2), rows of d."""
+    d = np.asarray(d, np.float32)
+    acc = d[..., 0] * d[..., 0]
+    acc = (acc + d[..., 1] * d[..., 1]).astype(np.float32)
+    acc = (acc + d[..., 2] * d[..., 2]).astype(np.float32)
+    return np.sqrt(acc).astype(np.float32)
+
+
+def multigoal_find_path(path: MultiGoalShortestPath, snap_refs, find_paths, sort_order) -> bool:
+    """PathFinder::Impl::findPath(MultiGoalShortestPath&) (PathFinder.cpp:1470-1572) over batched
+    primitives: snap_refs(pts [N,3]) -> poly refs [N] (0 = not projectable); find_paths(starts, ends,
+    max_points) -> dict(geodesic_distance, num_points, points); sort_order(keys) -> the goal order
+    std::sort leaves (unstable, PathFinder.cpp:1544-1548).  All goal searches of a call go through ONE
+    find_paths call; the reference's sequential goal loop is then replayed over the results."""
+    path.geodesic_distance = float("inf")
+    path.closest_end_point_index = -1
+    path.points = []
+    start = _vec3(path.requested_start)
+    ends = path._requested_ends
+    if int(snap_refs(start[None])[0]) == 0:  # findPathSetup: the start does not project
+        return False
+    if not path._ends_projected:
+        if len(ends):
+            valid = np.asarray(snap_refs(ends)) != 0
+            path._end_is_valid.extend(bool(v) for v in valid)
+            path._ends_projected = True
+            if not valid.any():
+                return False
+        # with no ends at all nothing is cached and the loop below has nothing to visit
+    g = len(ends)
+    if g > 1:
+        moved = np.float32(find_paths(start[None], path._prev_requested_start[None], 0)["geodesic_distance"][0])
+        l2 = _mn_length(ends - start[None])
+        with np.errstate(invalid="ignore"):
+            path._min_theoretical_dist = np.maximum((path._min_theoretical_dist - moved).astype(np.float32), l2)
+        path._prev_requested_start = start.copy()
+    if g == 0:
+        return False
+    order = sort_order(np.ascontiguousarray(path._min_theoretical_dist, np.float32))
+    res = find_paths(np.repeat(start[None], g, 0), ends, MAX_PATH_POINTS)
+    dist = np.asarray(res["geodesic_distance"], np.float32)
+    best = np.float32(np.inf)
+    for i in order:
+        i = int(i)
+        if not path._end_is_valid[i]:
+            continue
+        if path._min_theoretical_dist[i] > best:
+            continue
+        d = dist[i]
+        if d < np.inf and d < best:
+            path._min_theoretical_dist[i] = d
+            best = d
+            n = int(res["num_points"][i])
+            path.points = [np.array(res["points"][i, k], np.float32) for k in range(n)]
+            path.closest_end_point_index = i
+    path.geodesic_distance = float(best)
+    return bool(best < np.inf)
 
 
 class NavMeshSettings:
@@ -149,6 +219,15 @@ class NavMeshSettings:
             if not abs(getattr(self, k) - getattr(o, k)) < 1e-5:
                 return False
         return all(getattr(self, k) == getattr(o, k) for k in self._FIELDS[13:])
+
+
+def std_sort_order(keys) -> np.ndarray:
+    """argsort of float32 keys exactly as libstdc++'s std::sort leaves it (introsort, unstable): the
+    goal order of PathFinder.cpp:1542-1548.  Host code of libhbn (hbn_std_sort_order)."""
+    k = np.ascontiguousarray(keys, np.float32)
+    order = np.empty(len(k), np.int32)
+    _lib.lib().hbn_std_sort_order(k.ctypes.data, len(k), order.ctypes.data)
+    return order
 
 
 class PathFinder:
@@ -584,19 +663,9 @@ class PathFinder:
     # ---- scalar API, SPB.cpp:177-270 -------------------------------------------------
     def find_path(self, path) -> bool:
         if isinstance(path, MultiGoalShortestPath):
-            path.points = []
-            path.geodesic_distance = float("inf")
-            path.closest_end_point_index = -1
-            ends = path._requested_ends
-            if len(ends) == 0:
-                return False
-            r = self.find_paths_multigoal(_vec3(path.requested_start)[None], ends[None], MAX_PATH_POINTS)
-            d = float(r["geodesic_distance"][0])
-            path.geodesic_distance = d
-            path.closest_end_point_index = int(r["closest_end_point_index"][0])
-            n = int(r["num_points"][0])
-            path.points = [r["points"][0, i].copy() for i in range(n)]
-            return d < math.inf
+            self._need()
+            return multigoal_find_path(path, lambda p: self.snap_points(p)[1],
+                                       lambda s, e, m: self.find_paths(s, e, m), std_sort_order)
         r = self.find_paths(_vec3(path.requested_start)[None], _vec3(path.requested_end)[None],
                             MAX_PATH_POINTS)
         d = float(r["geodesic_distance"][0])

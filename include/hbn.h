@@ -160,6 +160,9 @@ int hbn_random_points_near_dev(hbn_navmesh_t nm, uint64_t seed, uint64_t query0,
                                const float* centers, float radius, const int32_t* islands, int max_tries,
                                float* out_pts, void* stream);
 float hbn_uniform(uint64_t seed, uint64_t query, uint32_t draw);
+/* order[0..n) <- the permutation std::sort (libstdc++ introsort, unstable) leaves when sorting 0..n-1
+ * by key: the goal order of findPath(MultiGoalShortestPath&), PF.cpp:1542-1548.  Host function. */
+void hbn_std_sort_order(const float* key, int n, int32_t* order);
 
 /* ---- the same queries with HOST buffers (copies + synchronisation inside) ---------- */
 int hbn_snap_point(hbn_navmesh_t nm, const float* pts, const int32_t* islands, int64_t n,

@@ -538,3 +538,48 @@ def test_pathfinder_not_loaded_like_the_reference():
     assert mg.closest_end_point_index == -1 and len(mg.points) == 0
     hr = HitRecord()  # tests/test_nav.py:229-234
     _ = hr.hit_pos, hr.hit_normal, hr.hit_dist
+
+
+def test_multigoal_object_state_matches_reference_twin():
+    """A REUSED MultiGoalShortestPath (PathFinder.cpp:95-123, :1470-1572; trap T4): bounds carried from
+    call to call, goals projected once per assignment, validity flags only appended.  The drop-in's
+    host logic (multigoal_find_path) runs here over oracle-backed primitives and must track the
+    reference's stateful object call by call."""
+    import habitat_sim_b200  # noqa: F401
+    from habitat_sim_b200.nav import MultiGoalShortestPath, multigoal_find_path, std_sort_order
+    from oracle.ref import RefMultiGoal
+    for name in ("c2_apartment", "t_building"):
+        ref = ref_pathfinder(name)
+        lo, hi = ref.get_bounds()
+
+        def snap_refs(p):
+            return ref.snap_batch(np.asarray(p, np.float32).reshape(-1, 3))[1]
+
+        def find_paths(s, e, m):
+            d, n, pts = ref.find_path_batch(s, e, m)
+            return dict(geodesic_distance=d, num_points=n, points=pts)
+
+        rng = np.random.default_rng(17)
+        walk = query_points(name, 40, 61, jitter=0.05)
+        walk[1:] = walk[:-1] + rng.normal(0, 0.4, (39, 3)).astype(np.float32) * np.float32([1, 0, 1])  # a moving agent
+        ends_a = query_points(name, 7, 62)
+        ends_a[2, 1] += 3.0                                 # bound above the geodesic distance
+        ends_b = query_points(name, 5, 63)
+        ends_b[0] = (hi + 50).astype(np.float32)            # invalid goal where the old list had a valid one
+        ends_c = np.concatenate([query_points(name, 8, 64), ((hi + 50).astype(np.float32))[None]])
+        twin = RefMultiGoal(ref)
+        mine = MultiGoalShortestPath()
+        for ends, lo_i, hi_i in ((ends_a, 0, 14), (ends_b, 14, 26), (ends_c, 26, 40)):
+            twin.set_ends(ends)
+            mine.requested_ends = ends
+            for s in walk[lo_i:hi_i]:
+                ok, d, idx, pts = twin.find(s)
+                mine.requested_start = s
+                got = multigoal_find_path(mine, snap_refs, find_paths, std_sort_order)
+                assert got == ok and mine.closest_end_point_index == idx
+                assert np.float32(mine.geodesic_distance) == np.float32(d) or (np.isinf(d) and np.isinf(mine.geodesic_distance))
+                assert len(mine.points) == len(pts) and all(beq(a, b).all() for a, b in zip(mine.points, pts))
+        # off-mesh start: nothing changes, False
+        mine.requested_start = (hi + 80).astype(np.float32)
+        assert not multigoal_find_path(mine, snap_refs, find_paths, std_sort_order)
+        assert mine.closest_end_point_index == -1 and mine.points == []

@@ -152,3 +152,31 @@ def test_greedy_follower_keys_radius_and_goal_cache(pathfinder):  # test_nav.py:
     assert f.last_goal is None
     path = f.find_path(rot, start, goal)  # ends with the stop key (None), test_nav.py:831-845
     assert path[-1] is None and all(a in ("move_forward", "turn_left", "turn_right") for a in path[:-1])
+
+
+def test_reused_multigoal_object_tracks_the_reference():
+    """The stateful MultiGoalShortestPath (bounds carried over, goals projected once, trap T4) through
+    the real PathFinder against the oracle's stateful twin."""
+    from habitat_sim_b200.nav import MultiGoalShortestPath
+    from oracle.ref import RefMultiGoal
+    from conftest import beq, query_points
+    name = "t_building"
+    pf, ref = gpu_pathfinder(name), ref_pathfinder(name)
+    lo, hi = ref.get_bounds()
+    rng = np.random.default_rng(18)
+    walk = query_points(name, 24, 71, jitter=0.05)
+    walk[1:] = walk[:-1] + rng.normal(0, 0.4, (23, 3)).astype(np.float32) * np.float32([1, 0, 1])
+    ends_a = query_points(name, 6, 72)
+    ends_a[2, 1] += 3.0
+    ends_b = query_points(name, 4, 73)
+    ends_b[0] = (hi + 50).astype(np.float32)
+    twin, mine = RefMultiGoal(ref), MultiGoalShortestPath()
+    for ends, a, b in ((ends_a, 0, 12), (ends_b, 12, 24)):
+        twin.set_ends(ends)
+        mine.requested_ends = ends
+        for s in walk[a:b]:
+            ok, d, idx, pts = twin.find(s)
+            mine.requested_start = s
+            assert pf.find_path(mine) == ok and mine.closest_end_point_index == idx
+            assert np.float32(mine.geodesic_distance) == np.float32(d) or (np.isinf(d) and np.isinf(mine.geodesic_distance))
+            assert len(mine.points) == len(pts) and all(beq(x, y).all() for x, y in zip(mine.points, pts))
