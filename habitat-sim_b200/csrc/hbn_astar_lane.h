@@ -193,6 +193,7 @@ struct LaneSearch {
     static_assert(HS == 32, "device build: one lane per column");
     const int lane = threadIdx.x & 31;
     int pos = -1;
+    __syncwarp();  // the other lanes are about to read this lane's heap entries: order its stores first
     uint32_t m = __ballot_sync(0xffffffffu, need);
     while (m) {
       const int l = __ffs(m) - 1;
