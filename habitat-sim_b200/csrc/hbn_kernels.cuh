@@ -12,6 +12,8 @@
 //  k_wall<..>      same workspace scheme for findDistanceToWall's Dijkstra.
 //  k_trystep_*     one thread per query (64-node BFS in local memory).
 //  k_random<W>     W lanes per sample; both reservoir scans run lane-parallel.
+//  k_random_near<W> get_random_navigable_point_near: the circle / island filter evaluated lane-parallel
+//                  per try, area sums and draws replayed in poly order.
 #pragma once
 #include <cuda_runtime.h>
 #include "hbn_query.h"
