@@ -111,6 +111,7 @@ struct AStarGArgs {
   int allCorridors;           // extract the corridor of unsuccessful searches too
   unsigned long long* workCtr;
   unsigned int* fault;
+  int laneLimit;              // k_astar_lane: lanes of a warp that take queries (0 = all 32); small batches spread over more warps
 };
 
 enum { kGIdle = 0, kGSearch = 1, kGDone = 2 };

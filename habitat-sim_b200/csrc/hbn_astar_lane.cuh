@@ -24,15 +24,15 @@ template <int TS>
 __host__ __device__ constexpr size_t laneSharedBytes() { return static_cast<size_t>(TS) * 32 * 6; }
 
 // TS: heap entries per lane in shared memory; MINB: resident one-warp blocks per SM the
-// register allocation must allow; CH: links per load stage.
-template <int TS, int MINB, int CH>
+// register allocation must allow; CH: links per load stage; V: heap code variant (LaneSearch).
+template <int TS, int MINB, int CH, int V = 1>
 __global__ void __launch_bounds__(32, MINB) k_astar_lane(NavView nav, AStarGArgs a, LaneScratch sc) {
   constexpr uint32_t FULL = 0xffffffffu;
   extern __shared__ __align__(16) char smem[];
   const int lane = threadIdx.x;
   const uint32_t ltMask = (1u << lane) - 1u;
   const size_t slotId = static_cast<size_t>(blockIdx.x) * 32 + lane;
-  LaneSearch<32, TS, CH> s;
+  LaneSearch<32, TS, CH, V> s;
   s.K = reinterpret_cast<float*>(smem) + lane;
   s.S = reinterpret_cast<uint16_t*>(smem + static_cast<size_t>(TS) * 32 * 4) + lane;
   s.G = reinterpret_cast<LaneHeapEnt*>(sc.heap + slotId * kLaneHeapBytes);
@@ -40,7 +40,10 @@ __global__ void __launch_bounds__(32, MINB) k_astar_lane(NavView nav, AStarGArgs
   s.rec = sc.rec + slotId * kLaneRecBytes;
   s.cv = nullptr;
   s.gen = sc.gen[slotId];
-  s.mode = kLIdle;
+  // A batch smaller than the grid is spread over more warps (a.laneLimit lanes each): the lanes
+  // of a warp diverge in the heap loops, so fewer queries per warp = fewer instructions per step
+  // on the latency chain of a small batch.
+  s.mode = (a.laneLimit <= 0 || lane < a.laneLimit) ? kLIdle : kLDone;
   s.q = 0; s.endG = 0; s.size = 0; s.nodeCount = 0; s.status = 0; s.xk = 0; s.xcur = 0;
   s.expanded = s.nLinks = s.nNeigh = 0;
   const uint32_t nWork = *a.workCount;

@@ -104,7 +104,8 @@ struct HBN_ALIGN(16) LaneHeapPair {
 
 // per-lane global scratch, one region per kind
 constexpr size_t kLaneRecBytes = static_cast<size_t>(kMaxNodes) * 32;
-constexpr size_t kLaneHeapBytes = static_cast<size_t>(kMaxNodes + 2) * sizeof(LaneHeapEnt);
+// a multiple of 32: a 4-entry group of every lane's heap then sits in ONE 32 B sector
+constexpr size_t kLaneHeapBytes = (static_cast<size_t>(kMaxNodes + 2) * sizeof(LaneHeapEnt) + 31) & ~static_cast<size_t>(31);
 HBN_HD size_t laneTabBytes(uint32_t numKeys) { return (static_cast<size_t>(numKeys) * 2 + 15) & ~static_cast<size_t>(15); }
 HBN_HD size_t laneScratchBytes(uint32_t numKeys) {
   return laneTabBytes(numKeys) + kLaneRecBytes + kLaneHeapBytes;
@@ -128,10 +129,14 @@ HBN_HD void laneLoadLink(const LinkRec* p, LaneLinkLo& lo, LaneLinkHi& hi) {
 // HS: distance (in elements) between consecutive shared heap entries of this lane (32 on the
 // device, 1 in the host build); TS: heap entries kept in shared memory (odd, so that the
 // children 2i+1, 2i+2 of an entry are both on the same side and pair-aligned in global);
-// CH: links per load stage (registers vs. rounds).
+// CH: links per load stage (registers vs. rounds); V: code variant of the heap operations --
+// 1 = one heap level per HBM round trip; 2 = the sift-down fetches children AND grandchildren
+// of an HBM-level entry together (two levels per round trip), the bubble-up that ends a pop
+// compares against the key it has just moved instead of re-loading it, and the replay has one
+// bubble-up site for pushes and modifies.  Both go through the same heap states.
 // step() contains warp collectives on the device: all 32 lanes of the warp must call it
 // together, whatever their mode.
-template <int HS, int TS, int CH>
+template <int HS, int TS, int CH, int V = 1>
 struct LaneSearch {
   static constexpr int kLaneChunk = CH;  // links handled per load stage
   static_assert((TS & 1) == 1, "TS must be odd");
@@ -247,12 +252,88 @@ struct LaneSearch {
     }
     hset(i, key, slot);
   }
+  // bubbleUp whose first comparison is against a parent key the caller already holds (pkv)
+  HBN_HD void heapUpK(int i, const float key, const uint32_t slot, const bool pkv, const float pk0) const {
+    if (!(i == 0 || (pkv && !(pk0 > key)))) {
+      while (i > 0) {
+        const int parent = (i - 1) >> 1;
+        float pk;
+        uint32_t ps;
+        hget(parent, pk, ps);
+        if (!(pk > key)) break;
+        hset(i, pk, ps);
+        i = parent;
+      }
+    }
+    hset(i, key, slot);
+  }
+  static HBN_HD LaneHeapPair loadPair(const LaneHeapEnt* p) { return *reinterpret_cast<const LaneHeapPair*>(p); }
   // dtNodeQueue::pop's trickleDown (DNode.cpp:169-184) for a heap that has `n` entries left
   HBN_HD void heapPopSift(const int n) const {
     float lk;
     uint32_t ls;
     hget(n, lk, ls);
     int i = 0, child = 1;
+    if constexpr (V >= 2) {
+      static_assert((TS & 3) == 3, "grandchildren 4i+3..4i+6 must start a 4-entry group of the global part");
+      float moved = 0.f;  // the key the last iteration moved up: it is the parent of the hole `i`
+      while (child < n) {
+        if (child < TS) {  // shared levels: one at a time
+          float c0 = K[child * HS], c1 = K[(child + 1) * HS];
+          uint32_t s0 = S[child * HS], s1 = S[(child + 1) * HS];
+          if ((child + 1) < n && c0 > c1) {
+            c0 = c1;
+            s0 = s1;
+            child++;
+          }
+          hset(i, c0, s0);
+          moved = c0;
+          i = child;
+          child = 2 * i + 1;
+        } else {
+          // HBM levels: the children pair and the four grandchildren (entries 2*child+1 ..
+          // 2*child+4, contiguous) are independent loads of one round trip; the grandchildren
+          // lie inside the lane's array whenever one of them is a heap entry (2*child+4 <= n+3).
+          const int gc = 2 * child + 1;
+          const LaneHeapPair p = loadPair(&G[child - TS]);
+          LaneHeapPair q0 = LaneHeapPair{{0.f, 0u}, {0.f, 0u}}, q1 = q0;
+          if (gc < n) {
+            q0 = loadPair(&G[gc - TS]);
+            q1 = loadPair(&G[gc + 2 - TS]);
+          }
+          float c0 = p.a.key, c1 = p.b.key;
+          uint32_t s0 = p.a.slot, s1 = p.b.slot;
+          bool second = false;
+          if ((child + 1) < n && c0 > c1) {
+            c0 = c1;
+            s0 = s1;
+            child++;
+            second = true;
+          }
+          hset(i, c0, s0);
+          moved = c0;
+          i = child;
+          child = 2 * i + 1;
+          if (child < n) {  // then gc < n held: q0 / q1 are loaded
+            c0 = second ? q1.a.key : q0.a.key;
+            c1 = second ? q1.b.key : q0.b.key;
+            s0 = second ? q1.a.slot : q0.a.slot;
+            s1 = second ? q1.b.slot : q0.b.slot;
+            if ((child + 1) < n && c0 > c1) {
+              c0 = c1;
+              s0 = s1;
+              child++;
+            }
+            hset(i, c0, s0);
+            moved = c0;
+            i = child;
+            child = 2 * i + 1;
+          }
+        }
+      }
+      heapUpK(i, lk, ls, i > 0, moved);
+      return;
+    }
     while (child < n) {  // child is odd; child + 1 <= n is inside the arrays
       float c0, c1;
       uint32_t s0, s1;
@@ -547,6 +628,28 @@ struct LaneSearch {
         const bool isModify = mine && (qSlot[j] & 0x10000u) != 0;
         const uint32_t slot = qSlot[j] & 0xffffu;
         const int hp = findPosAll(isModify, slot);
+        if constexpr (V >= 2) {
+          if (mine) {
+            int at = size;
+            bool pkv = false;
+            float pk = 0.f;
+            if (isModify) {
+              at = hp;
+              if (hp < 0) stop = kLEvFault;  // an open node that is not in the heap would be a bug
+            } else {
+              pkv = pkValid && pushed < 2;
+              pk = pushed == 0 ? pk0 : pk1;
+              pushed++;
+              size++;
+            }
+            // A key fetched at pop time may be stale by now, but only too LARGE: between two pops
+            // every operation is a bubble-up, which can only lower the key held at a position.
+            // So "parent <= new key" on the stale value implies it on the current one (the entry
+            // stays where it is), and in the other case heapUpK reloads.  No invalidation needed.
+            if (at >= 0) heapUpK(at, qKey[j], slot, pkv, pk);
+          }
+          continue;
+        }
         if (mine) {
           if (isModify) {
             if (hp < 0) stop = kLEvFault;  // an open node that is not in the heap would be a bug
@@ -566,7 +669,7 @@ struct LaneSearch {
           }
         }
       }
-      pkValid = false;  // a further chunk of links starts from other positions
+      if (V < 2) pkValid = false;  // a further chunk of links starts from other positions
     }
     if (stop == kLEvPoolExhausted) {
       ev = finishSearch(allCorridors);

@@ -92,6 +92,7 @@ struct hbn_navmesh {
   DevBuf wsLane, laneGen;
   int blocksFpLane = 0;
   int laneCfg = 0;      // HBN_LANE_CFG: shared heap levels / warps per SM variant (tuning)
+  bool laneSpread = false;  // HBN_LANE_SPREAD=1: batches smaller than the grid use fewer lanes per warp (tuning)
   // pinned staging for the host-buffer entry points
   void* pinned = nullptr;
   size_t pinnedCap = 0;
@@ -152,6 +153,10 @@ const void* laneKernel(int cfg, size_t* shared) {
     case 2: *shared = laneSharedBytes<31>(); return reinterpret_cast<const void*>(&k_astar_lane<31, 20, 2>);
     case 3: *shared = laneSharedBytes<63>(); return reinterpret_cast<const void*>(&k_astar_lane<63, 18, 2>);
     case 4: *shared = laneSharedBytes<31>(); return reinterpret_cast<const void*>(&k_astar_lane<31, 17, 3>);
+    // heap code variant 2 (two heap levels per HBM round trip, see LaneSearch): not measured yet
+    case 5: *shared = laneSharedBytes<63>(); return reinterpret_cast<const void*>(&k_astar_lane<63, 16, 4, 2>);
+    case 6: *shared = laneSharedBytes<31>(); return reinterpret_cast<const void*>(&k_astar_lane<31, 16, 4, 2>);
+    case 7: *shared = laneSharedBytes<31>(); return reinterpret_cast<const void*>(&k_astar_lane<31, 20, 2, 2>);
     default: *shared = laneSharedBytes<kLaneTS>(); return reinterpret_cast<const void*>(&k_astar_lane<kLaneTS, kLaneMinB, 4>);
   }
 }
@@ -236,6 +241,7 @@ int finishCreate(HostNavMesh& mesh, const int32_t* islands, int device, hbn_navm
   if (nm->fpG != 0 && nm->fpG != 1 && nm->fpG != 4 && nm->fpG != 8 && nm->fpG != 16 && nm->fpG != 32) nm->fpG = 8;
   {
     if (const char* e = getenv("HBN_LANE_CFG")) nm->laneCfg = atoi(e);
+    if (const char* e = getenv("HBN_LANE_SPREAD")) nm->laneSpread = atoi(e) != 0;
     size_t smLane = 0;
     const void* fn = laneKernel(nm->laneCfg, &smLane);
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smLane)));
@@ -690,7 +696,10 @@ static int findPathLaunch(hbn_navmesh_t nm, const float* starts, const float* en
     if (nm->fpG == 1) {
       LaneScratch sc{};
       if ((rc = laneScratch(nm, st, &sc))) return rc;
-      const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(nm->blocksFpLane, (cn + 31) / 32));
+      int64_t lanes = 32;  // queries per warp
+      if (nm->laneSpread) lanes = std::max<int64_t>(1, std::min<int64_t>(32, (cn + nm->blocksFpLane - 1) / nm->blocksFpLane));
+      ga.laneLimit = static_cast<int>(lanes);
+      const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(nm->blocksFpLane, (cn + lanes - 1) / lanes));
       size_t smLane = 0;
       const void* fn = laneKernel(nm->laneCfg, &smLane);
       void* kargs[] = {&nm->view, &ga, &sc};

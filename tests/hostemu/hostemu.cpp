@@ -169,19 +169,21 @@ void emu_find_path(void* h, const float* starts, const float* ends, long n, int 
 // lane) on ONE lane slot reused by all n queries, so table generations wrap and get wiped.
 // out_info [n,4]: {findPath status (0 = no search), corridor length, nodes allocated, event};
 // out_corridor [n,256] poly refs of the (possibly truncated) corridor.
-void emu_find_path_lane(void* h, const float* starts, const float* ends, long n, int fastFail, int allCorridors,
-                        unsigned* out_corridor, unsigned* out_info) {
+}  // extern "C"
+
+template <int TS, int V>
+static void laneSearchRun(void* h, const float* starts, const float* ends, long n, int fastFail, int allCorridors,
+                          unsigned* out_corridor, unsigned* out_info) {
   Emu* e = static_cast<Emu*>(h);
   HostGroup grp;
   uint32_t q[2];
-  constexpr int TS = 63;
   const NavView& nav = e->nav;
   std::vector<char> scratch(laneScratchBytes(nav.numKeys) + 64, 0);
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(scratch.data()) + 15) & ~uintptr_t(15));
   std::vector<float> K(TS);
   std::vector<uint16_t> S(TS);
   std::vector<uint32_t> ring(kMaxPathPolys);
-  LaneSearch<1, TS, 4> s{};  // the shipped configuration: 4 links per load stage
+  LaneSearch<1, TS, 4, V> s{};  // 4 links per load stage, as shipped
   s.K = K.data(); s.S = S.data();
   s.tab = reinterpret_cast<uint16_t*>(base);
   s.rec = base + laneTabBytes(nav.numKeys);
@@ -215,6 +217,192 @@ void emu_find_path_lane(void* h, const float* starts, const float* ends, long n,
       out_corridor[i * kMaxPathPolys + k] = nav.polys[k == 0 ? a.g : nav.links[via].nei].ref;
     }
   }
+}
+
+// dtNodeQueue restated plainly (DNode.cpp:156-200, DNode.h:118-142) over (key, node) pairs: the
+// yardstick of the heap fuzz below.
+struct PlainQueue {
+  std::vector<float> k;
+  std::vector<uint32_t> s;
+  void bubbleUp(int i, float key, uint32_t node) {
+    int parent = (i - 1) / 2;
+    while (i > 0 && k[parent] > key) {
+      k[i] = k[parent]; s[i] = s[parent];
+      i = parent;
+      parent = (i - 1) / 2;
+    }
+    k[i] = key; s[i] = node;
+  }
+  void trickleDown(int i, float key, uint32_t node) {
+    const int size = static_cast<int>(k.size());
+    int child = i * 2 + 1;
+    while (child < size) {
+      if (child + 1 < size && k[child] > k[child + 1]) child++;
+      k[i] = k[child]; s[i] = s[child];
+      i = child;
+      child = i * 2 + 1;
+    }
+    bubbleUp(i, key, node);
+  }
+  void push(float key, uint32_t node) {
+    k.push_back(0.f); s.push_back(0u);
+    bubbleUp(static_cast<int>(k.size()) - 1, key, node);
+  }
+  uint32_t pop() {
+    const uint32_t r = s[0];
+    const float lk = k.back();
+    const uint32_t ls = s.back();
+    k.pop_back(); s.pop_back();
+    if (!k.empty()) trickleDown(0, lk, ls);
+    return r;
+  }
+  void modify(uint32_t node, float key) {
+    for (size_t i = 0; i < s.size(); ++i)
+      if (s[i] == node) { bubbleUp(static_cast<int>(i), key, node); return; }
+  }
+};
+
+template <int TS, int V>
+static long laneHeapFuzz(unsigned seed, long ops, int keyLevels) {
+  std::vector<float> K(TS);
+  std::vector<uint16_t> S(TS);
+  std::vector<LaneHeapEnt> G(kMaxNodes + 2 + 8);
+  LaneSearch<1, TS, 4, V> h{};
+  h.K = K.data(); h.S = S.data(); h.G = G.data();
+  h.size = 0;
+  PlainQueue ref;
+  std::vector<float> keyOf(kMaxNodes, 0.f);
+  std::vector<char> open(kMaxNodes, 0);
+  uint64_t st = seed * 0x9E3779B97F4A7C15ull + 1;
+  auto rnd = [&]() { st = st * 6364136223846793005ull + 1442695040888963407ull; return static_cast<uint32_t>(st >> 33); };
+  uint32_t nextNode = 0;
+  for (long op = 0; op < ops; ++op) {
+    const uint32_t r = rnd() % 100;
+    // grow towards the pool size, then mix; keys from a few levels only: ties everywhere
+    const bool canPush = nextNode < static_cast<uint32_t>(kMaxNodes);
+    if ((r < 55 && canPush) || h.size == 0) {
+      if (!canPush) break;
+      const float key = static_cast<float>(rnd() % static_cast<uint32_t>(keyLevels)) * 0.25f;
+      const uint32_t node = nextNode++;
+      keyOf[node] = key; open[node] = 1;
+      ref.push(key, node);
+      if (V >= 2 && h.size > 0 && (rnd() & 1)) {  // with the parent key held, as the replay does
+        float pk; uint32_t ps;
+        h.hget((h.size - 1) >> 1, pk, ps);
+        h.heapUpK(h.size, key, node, true, pk);
+      } else if (V >= 2) {
+        h.heapUpK(h.size, key, node, false, 0.f);
+      } else {
+        h.heapUp(h.size, key, node);
+      }
+      h.size++;
+    } else if (r < 85) {
+      const uint32_t a = ref.pop();
+      const uint32_t b = h.S[0];
+      h.size--;
+      h.heapPopSift(h.size);
+      open[a] = 0;
+      if (a != b) return op + 1;
+    } else {  // decrease-key of a random open node
+      uint32_t node = rnd() % nextNode;
+      uint32_t tries = 0;
+      while (!open[node] && tries++ < 64) node = rnd() % nextNode;
+      if (!open[node]) continue;
+      const float dec = static_cast<float>(rnd() % 3) * 0.25f;
+      const float key = keyOf[node] - dec;
+      keyOf[node] = key;
+      ref.modify(node, key);
+      const int pos = h.findPosAll(true, node);
+      if (pos < 0) return op + 1;
+      if (V >= 2) h.heapUpK(pos, key, node, false, 0.f); else h.heapUp(pos, key, node);
+    }
+    if (static_cast<size_t>(h.size) != ref.k.size()) return op + 1;
+    for (int i = 0; i < h.size; ++i) {
+      float k; uint32_t s;
+      h.hget(i, k, s);
+      if (k != ref.k[i] || s != ref.s[i]) return op + 1;
+    }
+  }
+  return 0;
+}
+
+// Variant <TS, V> against the shipped <63, 1> in lock step on the same queries: after every
+// step() both must hold the same heap (every entry), node count, best node and event -- a
+// difference that happens not to change the corridor still counts.  Returns 0, or 1 + the index
+// of the first query that diverges.
+template <int TS, int V>
+static long laneLockstep(void* h, const float* starts, const float* ends, long n, int fastFail) {
+  Emu* e = static_cast<Emu*>(h);
+  HostGroup grp;
+  uint32_t q[2];
+  const NavView& nav = e->nav;
+  const size_t per = laneScratchBytes(nav.numKeys) + 64;
+  std::vector<char> sa(per, 0), sb(per, 0);
+  std::vector<float> Ka(63), Kb(TS);
+  std::vector<uint16_t> Sa(63), Sb(TS);
+  std::vector<uint32_t> ra(kMaxPathPolys), rb(kMaxPathPolys);
+  LaneSearch<1, 63, 4, 1> a{};
+  LaneSearch<1, TS, 4, V> b{};
+  auto carve = [&](auto& s, std::vector<char>& buf, std::vector<float>& K, std::vector<uint16_t>& S) {
+    char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(buf.data()) + 15) & ~uintptr_t(15));
+    s.K = K.data(); s.S = S.data();
+    s.tab = reinterpret_cast<uint16_t*>(base);
+    s.rec = base + laneTabBytes(nav.numKeys);
+    s.G = reinterpret_cast<LaneHeapEnt*>(s.rec + kLaneRecBytes);
+    s.gen = 0;
+    s.mode = kLIdle;
+  };
+  carve(a, sa, Ka, Sa);
+  carve(b, sb, Kb, Sb);
+  for (long i = 0; i < n; ++i) {
+    const Nearest s = findNearestPoly(nav, grp, starts + 3 * i, kExt, -1, q);
+    const Nearest t = findNearestPoly(nav, grp, ends + 3 * i, kExt, -1, q);
+    if (s.g == kNoPoly || t.g == kNoPoly || s.g == t.g) continue;
+    if (nav.polys[s.g].island < 0 || nav.polys[s.g].island != nav.polys[t.g].island) continue;
+    if (a.gen >= kLaneGenMax) {
+      memset(a.tab, 0, laneTabBytes(nav.numKeys)); a.gen = 0;
+      memset(b.tab, 0, laneTabBytes(nav.numKeys)); b.gen = 0;
+    }
+    a.begin(nav, static_cast<uint32_t>(i), s.g, s.pt, t.g, t.pt, ra.data());
+    b.begin(nav, static_cast<uint32_t>(i), s.g, s.pt, t.g, t.pt, rb.data());
+    int ev = kLEvNone;
+    while (ev == kLEvNone) {
+      ev = a.step(nav, fastFail != 0, true);
+      const int evb = b.step(nav, fastFail != 0, true);
+      if (ev != evb || a.size != b.size || a.nodeCount != b.nodeCount || a.lastBest != b.lastBest ||
+          a.mode != b.mode || a.xk != b.xk)
+        return i + 1;
+      if (a.mode == kLSearch)
+        for (int j = 0; j < a.size; ++j) {
+          float ka, kb;
+          uint32_t na, nb;
+          a.hget(j, ka, na);
+          b.hget(j, kb, nb);
+          if (ka != kb || na != nb) return i + 1;
+        }
+    }
+    if (a.status != b.status || memcmp(ra.data(), rb.data(), sizeof(uint32_t) * kMaxPathPolys) != 0) return i + 1;
+  }
+  return 0;
+}
+
+extern "C" {
+
+void emu_find_path_lane(void* h, const float* starts, const float* ends, long n, int fastFail, int allCorridors,
+                        unsigned* out_corridor, unsigned* out_info) {
+  laneSearchRun<63, 1>(h, starts, ends, n, fastFail, allCorridors, out_corridor, out_info);  // the shipped configuration
+}
+
+// The same with `ts` heap entries in the "shared" array (small values push most heap levels
+// through the global-memory code) and code variant `v` (LaneSearch's V).  Returns 0, or -1
+// for a combination that is not instantiated.
+int emu_find_path_lane_v(void* h, int ts, int v, const float* starts, const float* ends, long n, int fastFail,
+                         int allCorridors, unsigned* out_corridor, unsigned* out_info) {
+#define HBN_EMU_LANE(T, VV) \
+  if (ts == T && v == VV) { laneSearchRun<T, VV>(h, starts, ends, n, fastFail, allCorridors, out_corridor, out_info); return 0; }
+  HBN_EMU_LANE(3, 1) HBN_EMU_LANE(3, 2) HBN_EMU_LANE(7, 2) HBN_EMU_LANE(31, 2) HBN_EMU_LANE(63, 2)
+#undef HBN_EMU_LANE
+  return -1;
 }
 
 // find_path(MultiGoalShortestPath), fresh object per start: ends [n, g, 3]
@@ -345,6 +533,23 @@ void emu_random_points_near(void* h, long n, const float* centers, float radius,
   for (long i = 0; i < n; ++i)
     randomPointInCircle(e->nav, grp, seed, query0 + i, islands ? islands[i] : -1, centers + 3 * i, radius,
                         maxTries, out_pts + 3 * i);
+}
+
+// Heap code of hbn_astar_lane.h against dtNodeQueue restated plainly: random push / pop / modify
+// sequences over keys from `keyLevels` values (ties everywhere), every heap entry compared after
+// every operation.  Returns 0, the 1-based index of the first diverging operation, or -1.
+long emu_lane_heap_fuzz(int ts, int v, unsigned seed, long ops, int keyLevels) {
+#define HBN_EMU_HEAP(T, VV) if (ts == T && v == VV) return laneHeapFuzz<T, VV>(seed, ops, keyLevels);
+  HBN_EMU_HEAP(3, 1) HBN_EMU_HEAP(3, 2) HBN_EMU_HEAP(7, 2) HBN_EMU_HEAP(31, 2) HBN_EMU_HEAP(63, 1) HBN_EMU_HEAP(63, 2)
+#undef HBN_EMU_HEAP
+  return -1;
+}
+
+long emu_lane_lockstep(void* h, int ts, int v, const float* starts, const float* ends, long n, int fastFail) {
+#define HBN_EMU_LOCK(T, VV) if (ts == T && v == VV) return laneLockstep<T, VV>(h, starts, ends, n, fastFail);
+  HBN_EMU_LOCK(3, 1) HBN_EMU_LOCK(3, 2) HBN_EMU_LOCK(7, 2) HBN_EMU_LOCK(31, 2) HBN_EMU_LOCK(63, 2)
+#undef HBN_EMU_LOCK
+  return -1;
 }
 
 }  // extern "C"

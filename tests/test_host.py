@@ -249,6 +249,81 @@ def test_hostemu_lane_search_matches_oracle(name):
     emu.emu_destroy(h)
 
 
+@pytest.mark.parametrize("ts,v", [(3, 1), (3, 2), (7, 2), (31, 2), (63, 2)])
+@pytest.mark.parametrize("name", ["c3_multiroom", "c4_building"])
+def test_hostemu_lane_search_variants(name, ts, v):
+    """The heap-code variants of hbn_astar_lane.h (V = 2: two heap levels per global-memory round
+    trip in the sift-down, bubble-up against keys already held, one bubble-up site in the replay)
+    and small shared parts (ts = 3: nearly every heap level goes through the global-memory code)
+    go through the reference's heap states: status words, node counts and corridors equal
+    Detour's, in Detour-exact mode (all corridors) and with fast fail."""
+    emu, h = _emu_handle(name)
+    pf = ref_pathfinder(name)
+    n = 800
+    if name == "c4_building":
+        from workloads.scenes import NavMeshGeom, pointnav_pairs
+        st, en = pointnav_pairs(NavMeshGeom(navmesh_image(name)), n, 7)
+    else:
+        pts = query_points(name, 2 * n, 35)
+        st, en = pts[:n].copy(), pts[n:].copy()
+    r = pf.find_path_raw_batch(st, en)
+    SUCCESS = 1 << 30
+    emu.emu_find_path_lane_v.restype = C.c_int
+    for ff, allc in ((0, 1), (1, 0)):
+        corr = np.zeros((n, 256), np.uint32)
+        info = np.zeros((n, 4), np.uint32)
+        rc = emu.emu_find_path_lane_v(h, ts, v, P(st, f32p), P(en, f32p), C.c_long(n), ff, allc, P(corr, u32p),
+                                      P(info, u32p))
+        assert rc == 0
+        assert (info[:, 3] != 3).all(), "fault event"
+        done = info[:, 3] == 1
+        assert done.sum() > n // 2
+        ok_ref = r["astar_status"] == SUCCESS
+        assert (ok_ref[done] == (info[done, 0] == SUCCESS)).all()
+        if ff == 0:
+            assert (info[done, 0] == r["astar_status"][done]).all()
+            assert (info[done, 2] == r["nodes_used"][done]).all()
+        for i in np.nonzero(done)[0]:
+            if ff and not ok_ref[i]:
+                continue
+            k = r["num_polys"][i]
+            assert min(info[i, 1], 256) == k, (i, info[i], k)
+            assert (corr[i, :k] == r["corridor"][i, :k]).all(), i
+    emu.emu_destroy(h)
+
+
+@pytest.mark.parametrize("ts,v", [(3, 1), (3, 2), (7, 2), (31, 2), (63, 1), (63, 2)])
+def test_hostemu_lane_heap_fuzz(ts, v):
+    """The heap code of hbn_astar_lane.h (two-level storage, one or two levels per round trip)
+    against dtNodeQueue restated plainly (DNode.cpp:156-200): random push / pop / modify sequences
+    up to the pool size, keys from few values so that sibling and parent ties are everywhere,
+    every heap entry compared after every operation."""
+    emu = hostemu()
+    emu.emu_lane_heap_fuzz.restype = C.c_long
+    for levels in (3, 16, 1 << 20):
+        for seed in range(6):
+            assert emu.emu_lane_heap_fuzz(ts, v, seed, C.c_long(8000), levels) == 0, (levels, seed)
+
+
+@pytest.mark.parametrize("ts,v", [(3, 1), (3, 2), (7, 2), (31, 2), (63, 2)])
+@pytest.mark.parametrize("name", ["c3_multiroom", "c4_building"])
+def test_hostemu_lane_variants_lockstep(name, ts, v):
+    """Every variant in lock step with the shipped one: same heap entries, node count, best node
+    and event after every step() of every query (stronger than equal corridors)."""
+    emu, h = _emu_handle(name)
+    n = 600
+    if name == "c4_building":
+        from workloads.scenes import NavMeshGeom, pointnav_pairs
+        st, en = pointnav_pairs(NavMeshGeom(navmesh_image(name)), n, 9)
+    else:
+        pts = query_points(name, 2 * n, 37)
+        st, en = pts[:n].copy(), pts[n:].copy()
+    emu.emu_lane_lockstep.restype = C.c_long
+    for ff in (0, 1):
+        assert emu.emu_lane_lockstep(h, ts, v, P(st, f32p), P(en, f32p), C.c_long(n), ff) == 0
+    emu.emu_destroy(h)
+
+
 @pytest.mark.parametrize("seed", [11, 12, 13])
 def test_hostemu_fuzz_random_scenes(seed):
     """Fresh procedural scenes (not the cached benchmark ones): a seeded multi-room floor plan and a

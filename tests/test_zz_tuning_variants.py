@@ -1,0 +1,62 @@
+"""GPU parity of the OPT-IN tuning variants of k_astar_lane (not the shipped configuration):
+HBN_LANE_CFG 5-7 = heap code variant 2 of hbn_astar_lane.h (two heap levels per HBM round trip),
+HBN_LANE_SPREAD = a small batch spread over more warps.  Their host twins are checked on the
+CPU (tests/test_host.py: heap fuzz, lock step with the shipped variant); here the device build
+must give the reference's corridors, status words and distances too.  The file sorts last on
+purpose: these kernels are candidates to be measured, the shipped path is tested before them."""
+import numpy as np
+import pytest
+
+from conftest import beq, gpu_pathfinder, navmesh_image, query_points, ref_pathfinder
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_against_reference(pf, ref, st, en):
+    want = ref.find_path_raw_batch(st, en, max_pts=32, nthreads=8)
+    got = pf.find_paths(st, en, max_points=32, corridors=True, exact_status=True)
+    assert beq(got["geodesic_distance"], want["dist"]).all()
+    astar_ran = (want["flags"] & 2) != 0
+    assert (got["status"][astar_ran, 0] == want["astar_status"][astar_ran]).all()
+    assert (got["num_corridor"][astar_ran] == want["num_polys"][astar_ran]).all()
+    for i in np.nonzero(astar_ran)[0]:
+        k = want["num_polys"][i]
+        assert (got["corridor"][i, :k] == want["corridor"][i, :k]).all()
+    fast = pf.find_paths(st, en)  # default mode: stop at pool exhaustion
+    assert beq(fast["geodesic_distance"], want["dist"]).all()
+
+
+def _pairs(name, n, seed):
+    from workloads.scenes import NavMeshGeom, pointnav_pairs
+    if name == "c4_building":
+        return pointnav_pairs(NavMeshGeom(navmesh_image(name)), n, seed)
+    pts = query_points(name, 2 * n, seed)
+    return pts[:n].copy(), pts[n:].copy()
+
+
+@pytest.mark.parametrize("cfg", ["5", "6", "7"])
+def test_lane_heap_variant_2(cfg, monkeypatch):
+    monkeypatch.setenv("HBN_LANE_CFG", cfg)
+    for name, n in (("t_building", 3000), ("c4_building", 6000)):
+        st, en = _pairs(name, n, 21)
+        _check_against_reference(gpu_pathfinder(name), ref_pathfinder(name), st, en)
+    # a full grid: the shipped kernel's distances on 200 k queries
+    st, en = _pairs("c4_building", 200_000, 23)
+    d = gpu_pathfinder("c4_building").find_paths(st, en)["geodesic_distance"]
+    monkeypatch.delenv("HBN_LANE_CFG")
+    full = gpu_pathfinder("c4_building").find_paths(st, en)["geodesic_distance"]
+    assert beq(d, full).all()
+
+
+@pytest.mark.parametrize("n", [1, 33, 1024, 5000, 100_000])
+def test_lane_spread_small_batches(n, monkeypatch):
+    monkeypatch.setenv("HBN_LANE_SPREAD", "1")
+    for name in ("c2_apartment", "c4_building"):
+        st, en = _pairs(name, n, 25)
+        pf = gpu_pathfinder(name)
+        d = pf.find_paths(st, en)["geodesic_distance"]
+        m = min(n, 5000)
+        want = ref_pathfinder(name).find_path_batch(st[:m], en[:m], 0, 8)[0]
+        assert beq(d[:m], want).all()
+        if n <= 5000:
+            _check_against_reference(pf, ref_pathfinder(name), st, en)

@@ -1,5 +1,6 @@
 """One C2 PointNav step sequence (1024 envs: try_step + geodesic distance), for a launch list:
-    ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file out.csv python tools/c2_step.py [envs] [steps]"""
+    ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file out.csv python tools/c2_step.py [envs] [steps]
+HBN_LANE_SPREAD=1 spreads a batch smaller than the grid over more warps (fewer queries per warp)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
