@@ -92,7 +92,7 @@ struct hbn_navmesh {
   DevBuf wsLane, laneGen;
   int blocksFpLane = 0;
   int laneCfg = 0;      // HBN_LANE_CFG: shared heap levels / warps per SM variant (tuning)
-  bool laneSpread = false;  // HBN_LANE_SPREAD=1: batches smaller than the grid use fewer lanes per warp (tuning)
+  bool laneSpread = true;   // batches smaller than the grid use fewer lanes per warp (HBN_LANE_SPREAD=0: always 32)
   // pinned staging for the host-buffer entry points
   void* pinned = nullptr;
   size_t pinnedCap = 0;

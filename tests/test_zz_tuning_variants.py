@@ -1,9 +1,12 @@
-"""GPU parity of the OPT-IN tuning variants of k_astar_lane (not the shipped configuration):
-HBN_LANE_CFG 5-7 = heap code variant 2 of hbn_astar_lane.h (two heap levels per HBM round trip),
-HBN_LANE_SPREAD = a small batch spread over more warps.  Their host twins are checked on the
-CPU (tests/test_host.py: heap fuzz, lock step with the shipped variant); here the device build
-must give the reference's corridors, status words and distances too.  The file sorts last on
-purpose: these kernels are candidates to be measured, the shipped path is tested before them."""
+"""GPU parity of the tuning variants of k_astar_lane: HBN_LANE_CFG 5-7 = heap code variant 2 of
+hbn_astar_lane.h (two heap levels per HBM round trip; opt-in, measured slower in round 1) and
+lane spreading (a batch smaller than the grid uses fewer lanes per warp; on by default,
+HBN_LANE_SPREAD=0 restores 32 queries per warp).  Their host twins are checked on the CPU
+(tests/test_host.py: heap fuzz, lock step with the shipped variant); here the device build must
+give the reference's corridors, status words and distances too.  The file sorts last on
+purpose: the shipped configuration is tested before the variants."""
+import functools
+
 import numpy as np
 import pytest
 
@@ -26,6 +29,7 @@ def _check_against_reference(pf, ref, st, en):
     assert beq(fast["geodesic_distance"], want["dist"]).all()
 
 
+@functools.lru_cache(maxsize=None)
 def _pairs(name, n, seed):
     from workloads.scenes import NavMeshGeom, pointnav_pairs
     if name == "c4_building":
@@ -48,9 +52,10 @@ def test_lane_heap_variant_2(cfg, monkeypatch):
     assert beq(d, full).all()
 
 
-@pytest.mark.parametrize("n", [1, 33, 1024, 5000, 100_000])
-def test_lane_spread_small_batches(n, monkeypatch):
-    monkeypatch.setenv("HBN_LANE_SPREAD", "1")
+@pytest.mark.parametrize("spread,n", [("1", 1), ("1", 33), ("1", 1024), ("1", 5000), ("1", 100_000),
+                                      ("0", 33), ("0", 5000)])
+def test_lane_spread_small_batches(spread, n, monkeypatch):
+    monkeypatch.setenv("HBN_LANE_SPREAD", spread)
     for name in ("c2_apartment", "c4_building"):
         st, en = _pairs(name, n, 25)
         pf = gpu_pathfinder(name)
