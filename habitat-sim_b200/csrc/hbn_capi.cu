@@ -324,9 +324,18 @@ int snapLaunch(hbn_navmesh* nm, const float* pts, const int32_t* islands, int64_
   const int64_t maxBlocks = static_cast<int64_t>(nm->smCount) * 64;
   const bool forceGroup = getenv("HBN_SNAP_GROUP") != nullptr;  // testing: the lane-group kernel only
   if (n < kSnapSmall || forceGroup) {
-    const int64_t blocks = std::min(maxBlocks, (n + groupsPerBlock - 1) / groupsPerBlock);
-    k_snap<kSnapW><<<static_cast<unsigned>(blocks), 256, 0, st>>>(nm->view, pts, islands, n, out_pts, out_g,
-                                                                  out_refs, out_isl, out_nav, maxYDelta, nullptr);
+    int64_t blocks = std::min(maxBlocks, (n + groupsPerBlock - 1) / groupsPerBlock);
+    unsigned threads = 256;
+    // HBN_SNAP_SPREAD=1 (tuning, not measured yet): one lane group per warp, so the groups of a
+    // small batch neither share a warp's issue slots nor diverge against each other
+    const char* sp = getenv("HBN_SNAP_SPREAD");
+    const bool spread = sp && atoi(sp) != 0;
+    if (spread && n < kSnapSmall) {
+      threads = kSnapW;
+      blocks = n;
+    }
+    k_snap<kSnapW><<<static_cast<unsigned>(blocks), threads, 0, st>>>(nm->view, pts, islands, n, out_pts, out_g,
+                                                                      out_refs, out_isl, out_nav, maxYDelta, nullptr);
     nm->launches++;
     CK(cudaGetLastError());
     return HBN_OK;

@@ -65,3 +65,20 @@ def test_lane_spread_small_batches(spread, n, monkeypatch):
         assert beq(d[:m], want).all()
         if n <= 5000:
             _check_against_reference(pf, ref_pathfinder(name), st, en)
+
+
+def test_snap_spread_small_batches(monkeypatch):
+    """HBN_SNAP_SPREAD=1 (opt-in): k_snap<8> launched with one lane group per warp."""
+    monkeypatch.setenv("HBN_SNAP_SPREAD", "1")
+    for name in ("c2_apartment", "t_building"):
+        pf, ref = gpu_pathfinder(name), ref_pathfinder(name)
+        for n in (1, 7, 1024, 4000):
+            pts = query_points(name, n, 41 + n)
+            wp, wr, wi = ref.snap_batch(pts)
+            gp, gr, gi = pf.snap_points(pts)
+            assert (gr == wr).all() and (gi == wi).all() and beq(gp, wp).all()
+            st = pts[: n // 2 + 1]
+            en = query_points(name, len(st), 43 + n)
+            want = ref.find_path_batch(st, en, 0, 8)[0]
+            assert beq(pf.find_paths(st, en)["geodesic_distance"], want).all()
+            assert beq(pf.try_steps(st, en), ref.try_step_batch(st, en)).all()

@@ -58,8 +58,9 @@ os.environ.pop("HBN_LANE_CFG")
 
 img2 = navmesh_bytes("c2_apartment")
 base = None
-for spread in ("0", "1"):
+for spread, snap_spread in (("0", "0"), ("1", "0"), ("1", "1")):
     os.environ["HBN_LANE_SPREAD"] = spread
+    os.environ["HBN_SNAP_SPREAD"] = snap_spread
     pf = PathFinder(0)
     assert pf.load_nav_mesh_bytes(img2)
     pf.set_profiling(True)
@@ -73,7 +74,7 @@ for spread in ("0", "1"):
     if base is None:
         base = as_u32(d).copy()
     same = int((as_u32(d) == base).sum())
-    say(f"C2 {len(d)} queries HBN_LANE_SPREAD={spread}: path {1e3 * t['path_ms'] / t['calls']:.0f} us snap "
+    say(f"C2 {len(d)} queries HBN_LANE_SPREAD={spread} HBN_SNAP_SPREAD={snap_spread}: path {1e3 * t['path_ms'] / t['calls']:.0f} us snap "
         f"{1e3 * t['snap_ms'] / t['calls']:.0f} us device, {1e6 * wall:.0f} us wall per call; equal: {same}/{len(d)}"
         f"  [t={time.time() - t00:.1f}s]")
     del pf
