@@ -109,11 +109,16 @@ def pointnav_pairs(geom: NavMeshGeom, n: int, seed: int, local_frac: float = 0.5
         pool = geom.sample(max(20000, n_local // 4), rng)
         ys = np.array([1.0, local_radius / 0.5, 1.0])  # |dy| > 0.5 m lies outside the ball
         tree = cKDTree(pool * ys)
-        nb = tree.query_ball_point(starts[:n_local] * ys, local_radius, return_sorted=False)
         pick = rng.random(n_local)
-        for i, lst in enumerate(nb):
-            if lst:
-                ends[i] = pool[lst[int(pick[i] * len(lst))]]
+        # in chunks, on all cores: a 1 M batch has ~1400 neighbours per start (0.7 G indices in
+        # all); every start is answered independently, so the lists do not depend on the split
+        chunk = 20000
+        for c0 in range(0, n_local, chunk):
+            nb = tree.query_ball_point(starts[c0:min(c0 + chunk, n_local)] * ys, local_radius,
+                                       return_sorted=False, workers=-1)
+            for i, lst in enumerate(nb, start=c0):
+                if lst:
+                    ends[i] = pool[lst[int(pick[i] * len(lst))]]
     perm = rng.permutation(n)
     starts, ends = starts[perm], ends[perm]
     if jitter:
