@@ -157,6 +157,13 @@ const void* laneKernel(int cfg, size_t* shared) {
     case 5: *shared = laneSharedBytes<63>(); return reinterpret_cast<const void*>(&k_astar_lane<63, 16, 4, 2>);
     case 6: *shared = laneSharedBytes<31>(); return reinterpret_cast<const void*>(&k_astar_lane<31, 16, 4, 2>);
     case 7: *shared = laneSharedBytes<31>(); return reinterpret_cast<const void*>(&k_astar_lane<31, 20, 2, 2>);
+    // 39 / 47 / 55 shared heap entries: room for 19-24 warps per SM (ptxas gives 96 registers for 17-20
+    // one-warp blocks, 80 for 21-25); not measured yet
+    case 8: *shared = laneSharedBytes<47>(); return reinterpret_cast<const void*>(&k_astar_lane<47, 20, 3>);
+    case 9: *shared = laneSharedBytes<47>(); return reinterpret_cast<const void*>(&k_astar_lane<47, 20, 2>);
+    case 10: *shared = laneSharedBytes<55>(); return reinterpret_cast<const void*>(&k_astar_lane<55, 19, 3>);
+    case 11: *shared = laneSharedBytes<47>(); return reinterpret_cast<const void*>(&k_astar_lane<47, 20, 3, 2>);
+    case 12: *shared = laneSharedBytes<39>(); return reinterpret_cast<const void*>(&k_astar_lane<39, 24, 2>);
     default: *shared = laneSharedBytes<kLaneTS>(); return reinterpret_cast<const void*>(&k_astar_lane<kLaneTS, kLaneMinB, 4>);
   }
 }
