@@ -321,6 +321,29 @@ struct DeviceGuard {
 constexpr int64_t kSnapChunk = 1 << 18;   // points per pass of the candidate-list pipeline
 constexpr int64_t kSnapSmall = 4096;      // below this one k_snap<8> launch is cheaper than five kernels + a scan
 
+// HBN_SNAP_DUAL=1 (tuning, not measured yet): two small independent projectToPoly batches in one
+// k_snap_dual launch.  Returns false when the pair does not qualify (the caller then launches
+// them one after the other).
+bool snapDualLaunch(hbn_navmesh* nm, const float* ptsA, int64_t nA, float* outPtsA, uint32_t* outGA,
+                    const float* ptsB, int64_t nB, float* outPtsB, uint32_t* outGB, cudaStream_t st, int* rc) {
+  *rc = HBN_OK;
+  const char* e = getenv("HBN_SNAP_DUAL");
+  if (!e || atoi(e) == 0 || nA <= 0 || nB <= 0 || nA >= kSnapSmall || nB >= kSnapSmall || getenv("HBN_SNAP_GROUP"))
+    return false;
+  const char* sp = getenv("HBN_SNAP_SPREAD");
+  const bool spread = sp && atoi(sp) != 0;
+  const int64_t n = nA + nB;
+  const unsigned threads = spread ? kSnapW : 256;
+  const int64_t gpb = threads / kSnapW;
+  const int64_t blocks = (n + gpb - 1) / gpb;
+  k_snap_dual<kSnapW><<<static_cast<unsigned>(blocks), threads, 0, st>>>(nm->view, SnapJob{ptsA, nA, outPtsA, outGA},
+                                                                        SnapJob{ptsB, nB, outPtsB, outGB});
+  nm->launches++;
+  const cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) *rc = fail(HBN_ERR_CUDA, std::string("k_snap_dual: ") + cudaGetErrorString(ce));
+  return true;
+}
+
 // projectToPoly for n points.  Large batches: count -> scan -> fill -> eval -> select
 // (hbn_snap.cuh), nothing read back by the host; small ones: the lane-group kernel.
 int snapLaunch(hbn_navmesh* nm, const float* pts, const int32_t* islands, int64_t n, float* out_pts,
@@ -648,12 +671,17 @@ static int findPathLaunch(hbn_navmesh_t nm, const float* starts, const float* en
   }
   if (pairMask && !nm->fpG) return fail(HBN_ERR_INVALID, "pair masks need the lock-step find_path pipeline");
   if ((flags & kFpReuseSnaps) == 0) {
-    if ((rc = snapLaunch(nm, starts, nullptr, nStarts, static_cast<float*>(nm->sPt.p),
-                         static_cast<uint32_t*>(nm->sG.p), nullptr, nullptr, nullptr, 0.f, st)))
-      return rc;
-    if ((rc = snapLaunch(nm, ends, nullptr, n, static_cast<float*>(nm->ePt.p),
-                         static_cast<uint32_t*>(nm->eG.p), nullptr, nullptr, nullptr, 0.f, st)))
-      return rc;
+    if (snapDualLaunch(nm, starts, nStarts, static_cast<float*>(nm->sPt.p), static_cast<uint32_t*>(nm->sG.p), ends, n,
+                       static_cast<float*>(nm->ePt.p), static_cast<uint32_t*>(nm->eG.p), st, &rc)) {
+      if (rc) return rc;
+    } else {
+      if ((rc = snapLaunch(nm, starts, nullptr, nStarts, static_cast<float*>(nm->sPt.p),
+                           static_cast<uint32_t*>(nm->sG.p), nullptr, nullptr, nullptr, 0.f, st)))
+        return rc;
+      if ((rc = snapLaunch(nm, ends, nullptr, n, static_cast<float*>(nm->ePt.p),
+                           static_cast<uint32_t*>(nm->eG.p), nullptr, nullptr, nullptr, 0.f, st)))
+        return rc;
+    }
   }
   if (nm->profile) CK(cudaEventRecord(pe.e[1], st));
   unsigned long long* workCtr = (flags & HBN_FP_COUNT_WORK) ? static_cast<unsigned long long*>(nm->work.p) : nullptr;
@@ -849,8 +877,12 @@ int hbn_try_step_dev(hbn_navmesh_t nm, const float* starts, const float* ends, i
   float* sPt = static_cast<float*>(nm->sPt.p);
   float* ep = static_cast<float*>(nm->epPt.p);
   uint32_t* last = static_cast<uint32_t*>(nm->lastPoly.p);
-  if ((rc = snapLaunch(nm, starts, nullptr, n, sPt, sG, nullptr, nullptr, nullptr, 0.f, st))) return rc;
-  if ((rc = snapLaunch(nm, ends, nullptr, n, nullptr, eG, nullptr, nullptr, nullptr, 0.f, st))) return rc;
+  if (snapDualLaunch(nm, starts, n, sPt, sG, ends, n, nullptr, eG, st, &rc)) {
+    if (rc) return rc;
+  } else {
+    if ((rc = snapLaunch(nm, starts, nullptr, n, sPt, sG, nullptr, nullptr, nullptr, 0.f, st))) return rc;
+    if ((rc = snapLaunch(nm, ends, nullptr, n, nullptr, eG, nullptr, nullptr, nullptr, 0.f, st))) return rc;
+  }
   k_trystep_a<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(nm->view, ends, sG, sPt, eG, n,
                                                                       allow_sliding, ep, last);
   nm->launches++;

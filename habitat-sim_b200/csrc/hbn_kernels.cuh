@@ -75,6 +75,48 @@ __global__ void __launch_bounds__(256) k_snap(NavView nav, const float* __restri
   }
 }
 
+// Two independent projectToPoly batches in ONE launch (find_path's starts and ends, try_step's
+// start and end): small batches are latency chains, and two half-empty launches back to back
+// cost twice the chain.  Group q serves point q of job a, or point q - a.n of job b.
+struct SnapJob {
+  const float* pts;
+  int64_t n;
+  float* out_pts;     // nullable
+  uint32_t* out_g;    // nullable
+};
+
+template <int W>
+__global__ void __launch_bounds__(256) k_snap_dual(NavView nav, SnapJob a, SnapJob b) {
+  __shared__ uint32_t queue[256 / W][2 * W];
+  WarpGroup<W> grp;
+  const int gInBlock = threadIdx.x / W;
+  const int64_t groupsPerGrid = static_cast<int64_t>(gridDim.x) * (blockDim.x / W);
+  const float ext[3] = {2.f, 4.f, 2.f};
+  const int64_t n = a.n + b.n;
+  for (int64_t q = static_cast<int64_t>(blockIdx.x) * (blockDim.x / W) + gInBlock; q < n; q += groupsPerGrid) {
+    const bool first = q < a.n;
+    const int64_t i = first ? q : q - a.n;
+    const float* pts = first ? a.pts : b.pts;
+    float* out_pts = first ? a.out_pts : b.out_pts;
+    uint32_t* out_g = first ? a.out_g : b.out_g;
+    const float c[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+    float rxz = 0.f;
+    if (grp.lane() == 0) rxz = snapRadius(nav, c, ext, -1);
+    rxz = grp.shfl(rxz, 0);
+    const Nearest r = findNearestPoly(nav, grp, c, ext, -1, queue[gInBlock], rxz);
+    grp.sync();
+    if (grp.lane() == 0) {
+      const bool ok = r.g != kNoPoly;
+      if (out_pts) {
+        out_pts[3 * i] = ok ? r.pt[0] : nanF();
+        out_pts[3 * i + 1] = ok ? r.pt[1] : nanF();
+        out_pts[3 * i + 2] = ok ? r.pt[2] : nanF();
+      }
+      if (out_g) out_g[i] = r.g;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // workspace placement
 //   kWsShared : every array in shared memory

@@ -67,9 +67,13 @@ def test_lane_spread_small_batches(spread, n, monkeypatch):
             _check_against_reference(pf, ref_pathfinder(name), st, en)
 
 
-def test_snap_spread_small_batches(monkeypatch):
-    """HBN_SNAP_SPREAD=1 (opt-in): k_snap<8> launched with one lane group per warp."""
-    monkeypatch.setenv("HBN_SNAP_SPREAD", "1")
+@pytest.mark.parametrize("spread,dual", [("1", "0"), ("0", "1"), ("1", "1")])
+def test_snap_spread_small_batches(spread, dual, monkeypatch):
+    """Opt-in small-batch snap variants: HBN_SNAP_SPREAD=1 launches k_snap<8> with one lane group
+    per warp; HBN_SNAP_DUAL=1 serves two independent snap batches (find_path's starts and ends,
+    try_step's start and end) in one k_snap_dual launch."""
+    monkeypatch.setenv("HBN_SNAP_SPREAD", spread)
+    monkeypatch.setenv("HBN_SNAP_DUAL", dual)
     for name in ("c2_apartment", "t_building"):
         pf, ref = gpu_pathfinder(name), ref_pathfinder(name)
         for n in (1, 7, 1024, 4000):

@@ -58,9 +58,10 @@ os.environ.pop("HBN_LANE_CFG")
 
 img2 = navmesh_bytes("c2_apartment")
 base = None
-for spread, snap_spread in (("0", "0"), ("1", "0"), ("1", "1")):
+for spread, snap_spread, dual in (("0", "0", "0"), ("1", "0", "0"), ("1", "1", "0"), ("1", "0", "1"), ("1", "1", "1")):
     os.environ["HBN_LANE_SPREAD"] = spread
     os.environ["HBN_SNAP_SPREAD"] = snap_spread
+    os.environ["HBN_SNAP_DUAL"] = dual
     pf = PathFinder(0)
     assert pf.load_nav_mesh_bytes(img2)
     pf.set_profiling(True)
@@ -71,11 +72,19 @@ for spread, snap_spread in (("0", "0"), ("1", "0"), ("1", "1")):
         d = pf.find_paths(q["c2s"], q["c2e"])["geodesic_distance"]
     wall = (time.perf_counter() - t0) / 20
     t = pf.phase_times()
+    pf.try_steps(q["c2s"], q["c2e"])
+    t0 = time.perf_counter()
+    for _ in range(20):
+        ts = pf.try_steps(q["c2s"], q["c2s"] + np.float32(0.25) * (q["c2e"] - q["c2s"]) /
+                          np.linalg.norm(q["c2e"] - q["c2s"], axis=1, keepdims=True).astype(np.float32))
+    wall_ts = (time.perf_counter() - t0) / 20
     if base is None:
         base = as_u32(d).copy()
+        base_ts = as_u32(ts).copy()
     same = int((as_u32(d) == base).sum())
-    say(f"C2 {len(d)} queries HBN_LANE_SPREAD={spread} HBN_SNAP_SPREAD={snap_spread}: path {1e3 * t['path_ms'] / t['calls']:.0f} us snap "
-        f"{1e3 * t['snap_ms'] / t['calls']:.0f} us device, {1e6 * wall:.0f} us wall per call; equal: {same}/{len(d)}"
+    same_ts = int((as_u32(ts) == base_ts).all(axis=1).sum())
+    say(f"C2 {len(d)} queries HBN_LANE_SPREAD={spread} HBN_SNAP_SPREAD={snap_spread} HBN_SNAP_DUAL={dual}: path {1e3 * t['path_ms'] / t['calls']:.0f} us snap "
+        f"{1e3 * t['snap_ms'] / t['calls']:.0f} us device, {1e6 * wall:.0f} us wall per call; equal: {same}/{len(d)}; try_steps {1e6 * wall_ts:.0f} us wall, equal {same_ts}/{len(ts)}"
         f"  [t={time.time() - t00:.1f}s]")
     del pf
     gc.collect()
