@@ -139,6 +139,10 @@ HBN_HD void laneLoadLink(const LinkRec* p, LaneLinkLo& lo, LaneLinkHi& hi) {
 template <int HS, int TS, int CH, int V = 1>
 struct LaneSearch {
   static constexpr int kLaneChunk = CH;  // links handled per load stage
+  // V: 1 shipped; 2 heap code variant 2; 3 = 1 + node-table entries of the popped poly's
+  // neighbours prefetched into L2 before the sift-down (device only); 4 = 2 + that prefetch
+  static constexpr bool kHeap2 = V == 2 || V == 4;
+  static constexpr bool kTabPrefetch = V >= 3;
   static_assert((TS & 1) == 1, "TS must be odd");
   // memory of this lane
   float* K;        // shared: heap keys
@@ -274,7 +278,7 @@ struct LaneSearch {
     uint32_t ls;
     hget(n, lk, ls);
     int i = 0, child = 1;
-    if constexpr (V >= 2) {
+    if constexpr (kHeap2) {
       static_assert((TS & 3) == 3, "grandchildren 4i+3..4i+6 must start a 4-entry group of the global part");
       float moved = 0.f;  // the key the last iteration moved up: it is the parent of the hole `i`
       while (child < n) {
@@ -512,6 +516,18 @@ struct LaneSearch {
 #pragma unroll
           for (int k = 0; k < CH; ++k)
             if (k < cnt) asm volatile("prefetch.global.L1 [%0];" ::"l"(lp + 32 * k));
+          if constexpr (kTabPrefetch) {
+            // The table entries of the neighbours are a DRAM round trip that only starts after
+            // the sift-down today.  Their keys sit in the (L2-resident) link records: fetch those
+            // now and start the entries towards L2, so that round trip overlaps the sift's.
+            uint32_t nk[CH];
+#pragma unroll
+            for (int k = 0; k < CH; ++k)
+              nk[k] = k < cnt ? __ldg(reinterpret_cast<const uint32_t*>(lp + 32 * k + 28)) : 0u;
+#pragma unroll
+            for (int k = 0; k < CH; ++k)
+              if (k < cnt && nk[k] < nav.numKeys) asm volatile("prefetch.global.L2 [%0];" ::"l"(tab + nk[k]));
+          }
         }
 #endif
         heapPopSift(size);
@@ -628,7 +644,7 @@ struct LaneSearch {
         const bool isModify = mine && (qSlot[j] & 0x10000u) != 0;
         const uint32_t slot = qSlot[j] & 0xffffu;
         const int hp = findPosAll(isModify, slot);
-        if constexpr (V >= 2) {
+        if constexpr (kHeap2) {
           if (mine) {
             int at = size;
             bool pkv = false;
@@ -669,7 +685,7 @@ struct LaneSearch {
           }
         }
       }
-      if (V < 2) pkValid = false;  // a further chunk of links starts from other positions
+      if (!kHeap2) pkValid = false;  // a further chunk of links starts from other positions
     }
     if (stop == kLEvPoolExhausted) {
       ev = finishSearch(allCorridors);

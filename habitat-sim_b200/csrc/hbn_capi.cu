@@ -164,6 +164,9 @@ const void* laneKernel(int cfg, size_t* shared) {
     case 10: *shared = laneSharedBytes<55>(); return reinterpret_cast<const void*>(&k_astar_lane<55, 19, 3>);
     case 11: *shared = laneSharedBytes<47>(); return reinterpret_cast<const void*>(&k_astar_lane<47, 20, 3, 2>);
     case 12: *shared = laneSharedBytes<39>(); return reinterpret_cast<const void*>(&k_astar_lane<39, 24, 2>);
+    // node-table prefetch before the sift-down (LaneSearch V = 3); not measured yet
+    case 13: *shared = laneSharedBytes<63>(); return reinterpret_cast<const void*>(&k_astar_lane<63, 16, 4, 3>);
+    case 14: *shared = laneSharedBytes<47>(); return reinterpret_cast<const void*>(&k_astar_lane<47, 20, 3, 3>);
     default: *shared = laneSharedBytes<kLaneTS>(); return reinterpret_cast<const void*>(&k_astar_lane<kLaneTS, kLaneMinB, 4>);
   }
 }

@@ -286,11 +286,11 @@ static long laneHeapFuzz(unsigned seed, long ops, int keyLevels) {
       const uint32_t node = nextNode++;
       keyOf[node] = key; open[node] = 1;
       ref.push(key, node);
-      if (V >= 2 && h.size > 0 && (rnd() & 1)) {  // with the parent key held, as the replay does
+      if (h.kHeap2 && h.size > 0 && (rnd() & 1)) {  // with the parent key held, as the replay does
         float pk; uint32_t ps;
         h.hget((h.size - 1) >> 1, pk, ps);
         h.heapUpK(h.size, key, node, true, pk);
-      } else if (V >= 2) {
+      } else if (h.kHeap2) {
         h.heapUpK(h.size, key, node, false, 0.f);
       } else {
         h.heapUp(h.size, key, node);
@@ -314,7 +314,7 @@ static long laneHeapFuzz(unsigned seed, long ops, int keyLevels) {
       ref.modify(node, key);
       const int pos = h.findPosAll(true, node);
       if (pos < 0) return op + 1;
-      if (V >= 2) h.heapUpK(pos, key, node, false, 0.f); else h.heapUp(pos, key, node);
+      if (h.kHeap2) h.heapUpK(pos, key, node, false, 0.f); else h.heapUp(pos, key, node);
     }
     if (static_cast<size_t>(h.size) != ref.k.size()) return op + 1;
     for (int i = 0; i < h.size; ++i) {
@@ -549,7 +549,7 @@ long emu_lane_heap_fuzz(int ts, int v, unsigned seed, long ops, int keyLevels) {
 long emu_lane_lockstep(void* h, int ts, int v, const float* starts, const float* ends, long n, int fastFail) {
 #define HBN_EMU_LOCK(T, VV) if (ts == T && v == VV) return laneLockstep<T, VV>(h, starts, ends, n, fastFail);
   HBN_EMU_LOCK(3, 1) HBN_EMU_LOCK(3, 2) HBN_EMU_LOCK(7, 2) HBN_EMU_LOCK(31, 2) HBN_EMU_LOCK(63, 2)
-  HBN_EMU_LOCK(47, 1) HBN_EMU_LOCK(47, 2) HBN_EMU_LOCK(55, 1) HBN_EMU_LOCK(39, 1)
+  HBN_EMU_LOCK(47, 1) HBN_EMU_LOCK(47, 2) HBN_EMU_LOCK(55, 1) HBN_EMU_LOCK(39, 1) HBN_EMU_LOCK(63, 3) HBN_EMU_LOCK(47, 4)
 #undef HBN_EMU_LOCK
   return -1;
 }
