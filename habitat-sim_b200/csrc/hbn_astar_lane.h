@@ -143,6 +143,9 @@ struct LaneSearch {
   // neighbours prefetched into L2 before the sift-down (device only); 4 = 2 + that prefetch
   static constexpr bool kHeap2 = V == 2 || V == 4;
   static constexpr bool kTabPrefetch = V >= 3;
+  // V = 5: 3 + at every sift-down level the four grandchildren (one 32 B sector) are started
+  // towards L2 while the children are compared, so only the first HBM level pays DRAM latency
+  static constexpr bool kSiftPrefetch = V == 5;
   static_assert((TS & 1) == 1, "TS must be odd");
   // memory of this lane
   float* K;        // shared: heap keys
@@ -341,6 +344,13 @@ struct LaneSearch {
     while (child < n) {  // child is odd; child + 1 <= n is inside the arrays
       float c0, c1;
       uint32_t s0, s1;
+#if defined(__CUDA_ARCH__)
+      if constexpr (kSiftPrefetch) {
+        static_assert(!kSiftPrefetch || (TS & 3) == 3, "a grandchildren group must not straddle the shared part");
+        const int gc = 2 * child + 1;
+        if (gc >= TS && gc < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(&G[gc - TS]));
+      }
+#endif
       if (child < TS) {
         c0 = K[child * HS];
         c1 = K[(child + 1) * HS];

@@ -167,6 +167,9 @@ const void* laneKernel(int cfg, size_t* shared) {
     // node-table prefetch before the sift-down (LaneSearch V = 3); not measured yet
     case 13: *shared = laneSharedBytes<63>(); return reinterpret_cast<const void*>(&k_astar_lane<63, 16, 4, 3>);
     case 14: *shared = laneSharedBytes<47>(); return reinterpret_cast<const void*>(&k_astar_lane<47, 20, 3, 3>);
+    // + grandchildren prefetch in the sift-down (V = 5)
+    case 15: *shared = laneSharedBytes<63>(); return reinterpret_cast<const void*>(&k_astar_lane<63, 16, 4, 5>);
+    case 16: *shared = laneSharedBytes<47>(); return reinterpret_cast<const void*>(&k_astar_lane<47, 20, 3, 5>);
     default: *shared = laneSharedBytes<kLaneTS>(); return reinterpret_cast<const void*>(&k_astar_lane<kLaneTS, kLaneMinB, 4>);
   }
 }
