@@ -25,8 +25,8 @@ __host__ __device__ constexpr size_t laneSharedBytes() { return static_cast<size
 
 // TS: heap entries per lane in shared memory; MINB: resident one-warp blocks per SM the
 // register allocation must allow; CH: links per load stage; V: heap code variant (LaneSearch).
-template <int TS, int MINB, int CH, int V = 1>
-__global__ void __launch_bounds__(32, MINB) k_astar_lane(NavView nav, AStarGArgs a, LaneScratch sc) {
+template <int TS, int CH, int V>
+__device__ __forceinline__ void astarLaneBody(const NavView& nav, const AStarGArgs& a, const LaneScratch& sc) {
   constexpr uint32_t FULL = 0xffffffffu;
   extern __shared__ __align__(16) char smem[];
   const int lane = threadIdx.x;
@@ -105,6 +105,18 @@ __global__ void __launch_bounds__(32, MINB) k_astar_lane(NavView nav, AStarGArgs
     }
   }
   sc.gen[slotId] = s.gen;
+}
+
+template <int TS, int MINB, int CH, int V = 1>
+__global__ void __launch_bounds__(32, MINB) k_astar_lane(NavView nav, AStarGArgs a, LaneScratch sc) {
+  astarLaneBody<TS, CH, V>(nav, a, sc);
+}
+
+// The same with the register budget given directly: ptxas turns "MINB one-warp blocks" into 96
+// registers for 17-20 blocks and 80 for 21-25, although 18 blocks would allow 112 and 19 blocks 104.
+template <int TS, int REGS, int CH, int V = 1>
+__global__ void __maxnreg__(REGS) k_astar_lane_r(NavView nav, AStarGArgs a, LaneScratch sc) {
+  astarLaneBody<TS, CH, V>(nav, a, sc);
 }
 
 }  // namespace hbn

@@ -170,6 +170,10 @@ const void* laneKernel(int cfg, size_t* shared) {
     // + grandchildren prefetch in the sift-down (V = 5)
     case 15: *shared = laneSharedBytes<63>(); return reinterpret_cast<const void*>(&k_astar_lane<63, 16, 4, 5>);
     case 16: *shared = laneSharedBytes<47>(); return reinterpret_cast<const void*>(&k_astar_lane<47, 20, 3, 5>);
+    // register budgets ptxas does not pick by itself: 18 warps x 112, 19 x 104 (not measured yet)
+    case 17: *shared = laneSharedBytes<63>(); return reinterpret_cast<const void*>(&k_astar_lane_r<63, 112, 4>);
+    case 18: *shared = laneSharedBytes<55>(); return reinterpret_cast<const void*>(&k_astar_lane_r<55, 104, 4>);
+    case 19: *shared = laneSharedBytes<55>(); return reinterpret_cast<const void*>(&k_astar_lane_r<55, 104, 3>);
     default: *shared = laneSharedBytes<kLaneTS>(); return reinterpret_cast<const void*>(&k_astar_lane<kLaneTS, kLaneMinB, 4>);
   }
 }
@@ -327,17 +331,17 @@ struct DeviceGuard {
 constexpr int64_t kSnapChunk = 1 << 18;   // points per pass of the candidate-list pipeline
 constexpr int64_t kSnapSmall = 4096;      // below this one k_snap<8> launch is cheaper than five kernels + a scan
 
-// HBN_SNAP_DUAL=1 (tuning, not measured yet): two small independent projectToPoly batches in one
-// k_snap_dual launch.  Returns false when the pair does not qualify (the caller then launches
-// them one after the other).
+// Two small independent projectToPoly batches in one k_snap_dual launch (HBN_SNAP_DUAL=0: off).
+// Returns false when the pair does not qualify (the caller then launches them one after the
+// other).  1024 C2 points: find_path's snap phase 71 -> 38 us, with spreading 28 us.
 bool snapDualLaunch(hbn_navmesh* nm, const float* ptsA, int64_t nA, float* outPtsA, uint32_t* outGA,
                     const float* ptsB, int64_t nB, float* outPtsB, uint32_t* outGB, cudaStream_t st, int* rc) {
   *rc = HBN_OK;
   const char* e = getenv("HBN_SNAP_DUAL");
-  if (!e || atoi(e) == 0 || nA <= 0 || nB <= 0 || nA >= kSnapSmall || nB >= kSnapSmall || getenv("HBN_SNAP_GROUP"))
+  if ((e && atoi(e) == 0) || nA <= 0 || nB <= 0 || nA >= kSnapSmall || nB >= kSnapSmall || getenv("HBN_SNAP_GROUP"))
     return false;
   const char* sp = getenv("HBN_SNAP_SPREAD");
-  const bool spread = sp && atoi(sp) != 0;
+  const bool spread = !sp || atoi(sp) != 0;
   const int64_t n = nA + nB;
   const unsigned threads = spread ? kSnapW : 256;
   const int64_t gpb = threads / kSnapW;
@@ -362,10 +366,11 @@ int snapLaunch(hbn_navmesh* nm, const float* pts, const int32_t* islands, int64_
   if (n < kSnapSmall || forceGroup) {
     int64_t blocks = std::min(maxBlocks, (n + groupsPerBlock - 1) / groupsPerBlock);
     unsigned threads = 256;
-    // HBN_SNAP_SPREAD=1 (tuning, not measured yet): one lane group per warp, so the groups of a
-    // small batch neither share a warp's issue slots nor diverge against each other
+    // one lane group per warp (blocks of 8 threads): the groups of a small batch neither share a
+    // warp's issue slots nor diverge against each other, and 1024 points cover the SMs instead
+    // of 32 blocks (HBN_SNAP_SPREAD=0: blocks of 256 threads)
     const char* sp = getenv("HBN_SNAP_SPREAD");
-    const bool spread = sp && atoi(sp) != 0;
+    const bool spread = !sp || atoi(sp) != 0;
     if (spread && n < kSnapSmall) {
       threads = kSnapW;
       blocks = n;

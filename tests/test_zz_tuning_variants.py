@@ -1,7 +1,9 @@
-"""GPU parity of the tuning variants of k_astar_lane: HBN_LANE_CFG 5-7 = heap code variant 2 of
-hbn_astar_lane.h (two heap levels per HBM round trip; opt-in, measured slower in round 1) and
-lane spreading (a batch smaller than the grid uses fewer lanes per warp; on by default,
-HBN_LANE_SPREAD=0 restores 32 queries per warp).  Their host twins are checked on the CPU
+"""GPU parity of the tuning variants: HBN_LANE_CFG = other instantiations of k_astar_lane (shared
+heap entries, warps per SM, links per stage, heap code variant 2, prefetches; opt-in, none
+faster so far), lane spreading (a batch smaller than the grid uses fewer lanes per warp) and
+the small-batch snap launches (one lane group per warp, two batches per launch); the last
+three are on by default and can be switched off (HBN_LANE_SPREAD / HBN_SNAP_SPREAD /
+HBN_SNAP_DUAL = 0).  Their host twins are checked on the CPU
 (tests/test_host.py: heap fuzz, lock step with the shipped variant); here the device build must
 give the reference's corridors, status words and distances too.  The file sorts last on
 purpose: the shipped configuration is tested before the variants."""
@@ -38,7 +40,7 @@ def _pairs(name, n, seed):
     return pts[:n].copy(), pts[n:].copy()
 
 
-@pytest.mark.parametrize("cfg", ["5", "6", "7", "8", "9", "10", "11", "12", "13", "14", "15", "16"])
+@pytest.mark.parametrize("cfg", ["5", "6", "7", "8", "9", "10", "11", "12", "13", "14", "15", "16", "17", "18", "19"])
 def test_lane_kernel_configs(cfg, monkeypatch):
     monkeypatch.setenv("HBN_LANE_CFG", cfg)
     for name, n in (("t_building", 3000), ("c4_building", 6000)):
@@ -67,11 +69,12 @@ def test_lane_spread_small_batches(spread, n, monkeypatch):
             _check_against_reference(pf, ref_pathfinder(name), st, en)
 
 
-@pytest.mark.parametrize("spread,dual", [("1", "0"), ("0", "1"), ("1", "1")])
+@pytest.mark.parametrize("spread,dual", [("1", "0"), ("0", "1"), ("1", "1"), ("0", "0")])
 def test_snap_spread_small_batches(spread, dual, monkeypatch):
-    """Opt-in small-batch snap variants: HBN_SNAP_SPREAD=1 launches k_snap<8> with one lane group
-    per warp; HBN_SNAP_DUAL=1 serves two independent snap batches (find_path's starts and ends,
-    try_step's start and end) in one k_snap_dual launch."""
+    """Small-batch snap launches, every combination of the two knobs (both on by default):
+    HBN_SNAP_SPREAD launches k_snap<8> with one lane group per warp; HBN_SNAP_DUAL serves two
+    independent snap batches (find_path's starts and ends, try_step's start and end) in one
+    k_snap_dual launch."""
     monkeypatch.setenv("HBN_SNAP_SPREAD", spread)
     monkeypatch.setenv("HBN_SNAP_DUAL", dual)
     for name in ("c2_apartment", "t_building"):
