@@ -174,6 +174,9 @@ const void* laneKernel(int cfg, size_t* shared) {
     case 17: *shared = laneSharedBytes<63>(); return reinterpret_cast<const void*>(&k_astar_lane_r<63, 112, 4>);
     case 18: *shared = laneSharedBytes<55>(); return reinterpret_cast<const void*>(&k_astar_lane_r<55, 104, 4>);
     case 19: *shared = laneSharedBytes<55>(); return reinterpret_cast<const void*>(&k_astar_lane_r<55, 104, 3>);
+    // modify scan: shared part of the heap first (V = 6; not measured yet)
+    case 20: *shared = laneSharedBytes<63>(); return reinterpret_cast<const void*>(&k_astar_lane<63, 16, 4, 6>);
+    case 21: *shared = laneSharedBytes<63>(); return reinterpret_cast<const void*>(&k_astar_lane_r<63, 112, 4, 6>);
     default: *shared = laneSharedBytes<kLaneTS>(); return reinterpret_cast<const void*>(&k_astar_lane<kLaneTS, kLaneMinB, 4>);
   }
 }
