@@ -170,10 +170,12 @@ const void* laneKernel(int cfg, size_t* shared) {
     // + grandchildren prefetch in the sift-down (V = 5)
     case 15: *shared = laneSharedBytes<63>(); return reinterpret_cast<const void*>(&k_astar_lane<63, 16, 4, 5>);
     case 16: *shared = laneSharedBytes<47>(); return reinterpret_cast<const void*>(&k_astar_lane<47, 20, 3, 5>);
-    // register budgets ptxas does not pick by itself: 18 warps x 112, 19 x 104 (not measured yet)
+    // register budgets ptxas does not pick by itself: 112 (17 warps at 63 entries), 104 (19 warps) (not measured yet)
     case 17: *shared = laneSharedBytes<63>(); return reinterpret_cast<const void*>(&k_astar_lane_r<63, 112, 4>);
     case 18: *shared = laneSharedBytes<55>(); return reinterpret_cast<const void*>(&k_astar_lane_r<55, 104, 4>);
     case 19: *shared = laneSharedBytes<55>(); return reinterpret_cast<const void*>(&k_astar_lane_r<55, 104, 3>);
+    // 59 entries: 18 blocks fit the shared memory (12 KB + 1 KB reserved per block allows 17 at 63 entries)
+    case 22: *shared = laneSharedBytes<59>(); return reinterpret_cast<const void*>(&k_astar_lane_r<59, 112, 4>);
     // modify scan: shared part of the heap first (V = 6; not measured yet)
     case 20: *shared = laneSharedBytes<63>(); return reinterpret_cast<const void*>(&k_astar_lane<63, 16, 4, 6>);
     case 21: *shared = laneSharedBytes<63>(); return reinterpret_cast<const void*>(&k_astar_lane_r<63, 112, 4, 6>);
