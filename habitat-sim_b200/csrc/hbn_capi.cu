@@ -176,6 +176,8 @@ const void* laneKernel(int cfg, size_t* shared) {
     case 19: *shared = laneSharedBytes<55>(); return reinterpret_cast<const void*>(&k_astar_lane_r<55, 104, 3>);
     // 59 entries: 18 blocks fit the shared memory (12 KB + 1 KB reserved per block allows 17 at 63 entries)
     case 22: *shared = laneSharedBytes<59>(); return reinterpret_cast<const void*>(&k_astar_lane_r<59, 112, 4>);
+    // 95 entries (85 % of the pops find the whole open list in shared memory) at 11 warps per SM
+    case 23: *shared = laneSharedBytes<95>(); return reinterpret_cast<const void*>(&k_astar_lane<95, 11, 4>);
     // modify scan: shared part of the heap first (V = 6; not measured yet)
     case 20: *shared = laneSharedBytes<63>(); return reinterpret_cast<const void*>(&k_astar_lane<63, 16, 4, 6>);
     case 21: *shared = laneSharedBytes<63>(); return reinterpret_cast<const void*>(&k_astar_lane_r<63, 112, 4, 6>);

@@ -40,7 +40,7 @@ def _pairs(name, n, seed):
     return pts[:n].copy(), pts[n:].copy()
 
 
-@pytest.mark.parametrize("cfg", ["5", "6", "7", "8", "9", "10", "11", "12", "13", "14", "15", "16", "17", "18", "19", "20", "21", "22"])
+@pytest.mark.parametrize("cfg", ["5", "6", "7", "8", "9", "10", "11", "12", "13", "14", "15", "16", "17", "18", "19", "20", "21", "22", "23"])
 def test_lane_kernel_configs(cfg, monkeypatch):
     monkeypatch.setenv("HBN_LANE_CFG", cfg)
     for name, n in (("t_building", 3000), ("c4_building", 6000)):

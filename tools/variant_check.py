@@ -37,7 +37,7 @@ def as_u32(a):
 
 img = navmesh_bytes("c4_building")
 base = None
-for cfg in (os.environ.get("VARIANT_CFGS") or "0,17,22,20,21,18,19,1,8,10,13,15").split(","):
+for cfg in (os.environ.get("VARIANT_CFGS") or "0,17,22,20,21,18,19,23,1,8,10,13,15").split(","):
     os.environ["HBN_LANE_CFG"] = cfg
     pf = PathFinder(0)
     assert pf.load_nav_mesh_bytes(img)
