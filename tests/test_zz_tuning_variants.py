@@ -82,6 +82,7 @@ def test_snap_spread_small_batches(spread, dual, monkeypatch):
     HBN_SNAP_SPREAD launches k_snap<8> with one lane group per warp; HBN_SNAP_DUAL serves two
     independent snap batches (find_path's starts and ends, try_step's start and end) in one
     k_snap_dual launch."""
+    from workloads.scenes import step_targets
     monkeypatch.setenv("HBN_SNAP_SPREAD", spread)
     monkeypatch.setenv("HBN_SNAP_DUAL", dual)
     for name in ("c2_apartment", "t_building"):
@@ -95,4 +96,9 @@ def test_snap_spread_small_batches(spread, dual, monkeypatch):
             en = query_points(name, len(st), 43 + n)
             want = ref.find_path_batch(st, en, 0, 8)[0]
             assert beq(pf.find_paths(st, en)["geodesic_distance"], want).all()
-            assert beq(pf.try_steps(st, en), ref.try_step_batch(st, en)).all()
+            s = wp[: len(st)].copy()  # try_step inputs as in test_gpu_parity.test_try_step
+            s[np.isnan(s)] = 0
+            t = step_targets(s, 5, 0.25)
+            t[: len(s) // 4] = step_targets(s[: len(s) // 4], 6, 2.5)
+            for sliding in (True, False):
+                assert beq(pf.try_steps(s, t, sliding), ref.try_step_batch(s, t, sliding, 8)).all()
