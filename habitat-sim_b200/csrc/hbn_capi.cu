@@ -146,43 +146,46 @@ int laneScratch(hbn_navmesh* nm, cudaStream_t st, LaneScratch* out) {
   return HBN_OK;
 }
 
-// lane-per-query search variants: {heap entries in shared, resident warps per SM, links per load stage}
+// lane-per-query search instantiations (HBN_LANE_CFG; 0 = shipped).  Template arguments: heap
+// entries in shared memory, resident warps per SM (or registers for k_astar_lane_r), links per
+// load stage, code variant V of LaneSearch.  All are bit-exact (tests/test_zz_tuning_variants.py);
+// times of the find_path phase on 200 k C4 queries are in profiles/r1_summary.md.
 const void* laneKernel(int cfg, size_t* shared) {
+#define HBN_LANE_CASE(N, TS, ...) \
+  case N: *shared = laneSharedBytes<TS>(); return reinterpret_cast<const void*>(&__VA_ARGS__);
   switch (cfg) {
-    case 1: *shared = laneSharedBytes<63>(); return reinterpret_cast<const void*>(&k_astar_lane<63, 17, 3>);
-    case 2: *shared = laneSharedBytes<31>(); return reinterpret_cast<const void*>(&k_astar_lane<31, 20, 2>);
-    case 3: *shared = laneSharedBytes<63>(); return reinterpret_cast<const void*>(&k_astar_lane<63, 18, 2>);
-    case 4: *shared = laneSharedBytes<31>(); return reinterpret_cast<const void*>(&k_astar_lane<31, 17, 3>);
-    // heap code variant 2 (two heap levels per HBM round trip, see LaneSearch): not measured yet
-    case 5: *shared = laneSharedBytes<63>(); return reinterpret_cast<const void*>(&k_astar_lane<63, 16, 4, 2>);
-    case 6: *shared = laneSharedBytes<31>(); return reinterpret_cast<const void*>(&k_astar_lane<31, 16, 4, 2>);
-    case 7: *shared = laneSharedBytes<31>(); return reinterpret_cast<const void*>(&k_astar_lane<31, 20, 2, 2>);
-    // 39 / 47 / 55 shared heap entries: room for 19-24 warps per SM (ptxas gives 96 registers for 17-20
-    // one-warp blocks, 80 for 21-25); not measured yet
-    case 8: *shared = laneSharedBytes<47>(); return reinterpret_cast<const void*>(&k_astar_lane<47, 20, 3>);
-    case 9: *shared = laneSharedBytes<47>(); return reinterpret_cast<const void*>(&k_astar_lane<47, 20, 2>);
-    case 10: *shared = laneSharedBytes<55>(); return reinterpret_cast<const void*>(&k_astar_lane<55, 19, 3>);
-    case 11: *shared = laneSharedBytes<47>(); return reinterpret_cast<const void*>(&k_astar_lane<47, 20, 3, 2>);
-    case 12: *shared = laneSharedBytes<39>(); return reinterpret_cast<const void*>(&k_astar_lane<39, 24, 2>);
-    // node-table prefetch before the sift-down (LaneSearch V = 3); not measured yet
-    case 13: *shared = laneSharedBytes<63>(); return reinterpret_cast<const void*>(&k_astar_lane<63, 16, 4, 3>);
-    case 14: *shared = laneSharedBytes<47>(); return reinterpret_cast<const void*>(&k_astar_lane<47, 20, 3, 3>);
-    // + grandchildren prefetch in the sift-down (V = 5)
-    case 15: *shared = laneSharedBytes<63>(); return reinterpret_cast<const void*>(&k_astar_lane<63, 16, 4, 5>);
-    case 16: *shared = laneSharedBytes<47>(); return reinterpret_cast<const void*>(&k_astar_lane<47, 20, 3, 5>);
-    // register budgets ptxas does not pick by itself: 112 (17 warps at 63 entries), 104 (19 warps) (not measured yet)
-    case 17: *shared = laneSharedBytes<63>(); return reinterpret_cast<const void*>(&k_astar_lane_r<63, 112, 4>);
-    case 18: *shared = laneSharedBytes<55>(); return reinterpret_cast<const void*>(&k_astar_lane_r<55, 104, 4>);
-    case 19: *shared = laneSharedBytes<55>(); return reinterpret_cast<const void*>(&k_astar_lane_r<55, 104, 3>);
-    // 59 entries: 18 blocks fit the shared memory (12 KB + 1 KB reserved per block allows 17 at 63 entries)
-    case 22: *shared = laneSharedBytes<59>(); return reinterpret_cast<const void*>(&k_astar_lane_r<59, 112, 4>);
+    // measured in round 1, none faster than the shipped one
+    HBN_LANE_CASE(1, 63, k_astar_lane<63, 17, 3>)      // 150.5 ms per 1 M (shipped 153.7 in that run)
+    HBN_LANE_CASE(2, 31, k_astar_lane<31, 20, 2>)      // 158.7
+    HBN_LANE_CASE(3, 63, k_astar_lane<63, 18, 2>)      // 169.6
+    HBN_LANE_CASE(4, 31, k_astar_lane<31, 17, 3>)      // 202.0
+    HBN_LANE_CASE(5, 63, k_astar_lane<63, 16, 4, 2>)   // heap code variant 2: 38.97 ms per 200 k (shipped 37.22)
+    HBN_LANE_CASE(6, 31, k_astar_lane<31, 16, 4, 2>)   // 49.92
+    HBN_LANE_CASE(7, 31, k_astar_lane<31, 20, 2, 2>)   // 46.20
+    HBN_LANE_CASE(8, 47, k_astar_lane<47, 20, 3>)      // 38.13 (shipped 37.00 in that run)
+    HBN_LANE_CASE(12, 39, k_astar_lane<39, 24, 2>)     // 46.52
+    HBN_LANE_CASE(13, 63, k_astar_lane<63, 16, 4, 3>)  // node-table prefetch before the sift-down: 37.93
+    HBN_LANE_CASE(15, 63, k_astar_lane<63, 16, 4, 5>)  // + grandchildren prefetch in the sift-down: 37.59
+    HBN_LANE_CASE(16, 47, k_astar_lane<47, 20, 3, 5>)  // 38.92
+    // built and host-tested, not measured yet
+    HBN_LANE_CASE(9, 47, k_astar_lane<47, 20, 2>)
+    HBN_LANE_CASE(10, 55, k_astar_lane<55, 19, 3>)
+    HBN_LANE_CASE(11, 47, k_astar_lane<47, 20, 3, 2>)
+    HBN_LANE_CASE(14, 47, k_astar_lane<47, 20, 3, 3>)
+    // register budgets ptxas does not pick by itself ("17-20 one-warp blocks" become 96 registers):
+    // 112 = 17 warps at 63 entries (12 KB + 1 KB reserved per block), 18 at 59; 104 = 19 warps
+    HBN_LANE_CASE(17, 63, k_astar_lane_r<63, 112, 4>)
+    HBN_LANE_CASE(18, 55, k_astar_lane_r<55, 104, 4>)
+    HBN_LANE_CASE(19, 55, k_astar_lane_r<55, 104, 3>)
+    HBN_LANE_CASE(22, 59, k_astar_lane_r<59, 112, 4>)
+    // modify scan looks through the shared part of the heap first (V = 6)
+    HBN_LANE_CASE(20, 63, k_astar_lane<63, 16, 4, 6>)
+    HBN_LANE_CASE(21, 63, k_astar_lane_r<63, 112, 4, 6>)
     // 95 entries (85 % of the pops find the whole open list in shared memory) at 11 warps per SM
-    case 23: *shared = laneSharedBytes<95>(); return reinterpret_cast<const void*>(&k_astar_lane<95, 11, 4>);
-    // modify scan: shared part of the heap first (V = 6; not measured yet)
-    case 20: *shared = laneSharedBytes<63>(); return reinterpret_cast<const void*>(&k_astar_lane<63, 16, 4, 6>);
-    case 21: *shared = laneSharedBytes<63>(); return reinterpret_cast<const void*>(&k_astar_lane_r<63, 112, 4, 6>);
+    HBN_LANE_CASE(23, 95, k_astar_lane<95, 11, 4>)
     default: *shared = laneSharedBytes<kLaneTS>(); return reinterpret_cast<const void*>(&k_astar_lane<kLaneTS, kLaneMinB, 4>);
   }
+#undef HBN_LANE_CASE
 }
 
 const void* groupKernel(int g) {
