@@ -324,6 +324,55 @@ def test_hostemu_lane_variants_lockstep(name, ts, v):
     emu.emu_destroy(h)
 
 
+@pytest.mark.parametrize("name", ["c3_multiroom", "t_building"])
+def test_hostemu_out_of_the_ordinary_inputs(name):
+    """Regimes the seeded workloads do not reach: try_step from unsnapped starts towards targets
+    0.05 to 30 m away and off in height (moveAlongSurface's 64-node pool and 48-slot queue run
+    full, trap T9), wall distance with radii from 0 to 1e6, snaps around the edges of the
+    +-(2, 4, 2) m pick box and the climb threshold.  Bit-exact against the oracle."""
+    emu, h = _emu_handle(name)
+    ref = ref_pathfinder(name)
+    n = 1500
+    rng = np.random.default_rng(7)
+    s = np.ascontiguousarray(query_points(name, n, 51))
+    e = query_points(name, n, 52)
+    d = e - s
+    length = np.linalg.norm(d, axis=1, keepdims=True)
+    length[length == 0] = 1
+    step = rng.choice([0.05, 0.25, 1.0, 2.5, 6.0, 15.0, 30.0], size=(n, 1)).astype(np.float32)
+    t = (s + d / length * step).astype(np.float32)
+    t[::7] = e[::7]
+    t[::11, 1] += rng.normal(0, 1.0, len(t[::11])).astype(np.float32)
+    t = np.ascontiguousarray(t)
+    for sliding in (1, 0):
+        want = ref.try_step_batch(s, t, bool(sliding), 4)
+        got = np.zeros_like(s)
+        emu.emu_try_step(h, P(s, f32p), P(t, f32p), C.c_long(n), sliding, P(got, f32p))
+        assert beq(got, want).all(), sliding
+    for r in (0.0, 0.05, 7.5, 1e6):
+        hp, hn, hd = ref.obstacle_batch(s, r, 4)
+        out = np.zeros((n, 7), np.float32)
+        ov = np.zeros(n, np.int32)
+        emu.emu_obstacle(h, P(s, f32p), C.c_long(n), C.c_float(r), 2048, P(out, f32p), P(ov, i32p))
+        assert not ov.any()
+        assert beq(out[:, 6], hd).all() and beq(out[:, :3], hp).all() and beq(out[:, 3:6], hn).all(), r
+    p2 = s.copy()
+    p2[:, 1] += rng.choice([-4.2, -4.0, -3.99, -1.0, -0.2, 0.19, 0.2, 0.21, 1.0, 2.9, 3.99, 4.0, 4.01],
+                           size=n).astype(np.float32)
+    p2[:, 0] += rng.choice([0, 1.99, 2.0, 2.01, -2.0], size=n).astype(np.float32)
+    wp, wr, wi = ref.snap_batch(p2, 4)
+    assert (wr == 0).any() and (wr != 0).any()
+    e_pts = np.zeros_like(p2)
+    e_refs = np.zeros(n, np.uint32)
+    e_isl = np.zeros(n, np.int32)
+    nc = (C.c_long * 2)()
+    emu.emu_snap_list(h, P(p2, f32p), None, C.c_long(n), P(e_pts, f32p), P(e_refs, u32p), P(e_isl, i32p), nc)
+    assert (wr == e_refs).all() and (wi == e_isl).all() and beq(wp, e_pts).all()
+    emu.emu_snap(h, P(p2, f32p), None, C.c_long(n), P(e_pts, f32p), P(e_refs, u32p), P(e_isl, i32p))
+    assert (wr == e_refs).all() and (wi == e_isl).all() and beq(wp, e_pts).all()
+    emu.emu_destroy(h)
+
+
 @pytest.mark.parametrize("seed", [11, 12, 13])
 def test_hostemu_fuzz_random_scenes(seed):
     """Fresh procedural scenes (not the cached benchmark ones): a seeded multi-room floor plan and a

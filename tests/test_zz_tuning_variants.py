@@ -102,3 +102,38 @@ def test_snap_spread_small_batches(spread, dual, monkeypatch):
             t[: len(s) // 4] = step_targets(s[: len(s) // 4], 6, 2.5)
             for sliding in (True, False):
                 assert beq(pf.try_steps(s, t, sliding), ref.try_step_batch(s, t, sliding, 8)).all()
+
+
+@pytest.mark.parametrize("name", ["c3_multiroom", "t_building"])
+def test_out_of_the_ordinary_inputs(name):
+    """The device twin of tests/test_host.py::test_hostemu_out_of_the_ordinary_inputs: try_step from
+    unsnapped starts towards targets 0.05 to 30 m away, wall distance with radii from 0 to 1e6,
+    snaps around the edges of the pick box (small batch: lane-group kernel; large: candidate lists)."""
+    pf, ref = gpu_pathfinder(name), ref_pathfinder(name)
+    n = 6000
+    rng = np.random.default_rng(7)
+    s = np.ascontiguousarray(query_points(name, n, 51))
+    e = query_points(name, n, 52)
+    d = e - s
+    length = np.linalg.norm(d, axis=1, keepdims=True)
+    length[length == 0] = 1
+    step = rng.choice([0.05, 0.25, 1.0, 2.5, 6.0, 15.0, 30.0], size=(n, 1)).astype(np.float32)
+    t = (s + d / length * step).astype(np.float32)
+    t[::7] = e[::7]
+    t[::11, 1] += rng.normal(0, 1.0, len(t[::11])).astype(np.float32)
+    for sliding in (True, False):
+        assert beq(pf.try_steps(s, t, sliding), ref.try_step_batch(s, t, sliding, 8)).all(), sliding
+        m = 1000  # the small-batch launches
+        assert beq(pf.try_steps(s[:m], t[:m], sliding), ref.try_step_batch(s[:m], t[:m], sliding, 8)).all()
+    for r in (0.0, 0.05, 7.5, 1e6):
+        hp, hn, hd = ref.obstacle_batch(s, r, 8)
+        gp, gn, gd = pf.closest_obstacle_surface_points(s, r)
+        assert beq(gd, hd).all() and beq(gp, hp).all() and beq(gn, hn).all(), r
+    p2 = s.copy()
+    p2[:, 1] += rng.choice([-4.2, -4.0, -3.99, -1.0, -0.2, 0.19, 0.2, 0.21, 1.0, 2.9, 3.99, 4.0, 4.01],
+                           size=n).astype(np.float32)
+    p2[:, 0] += rng.choice([0, 1.99, 2.0, 2.01, -2.0], size=n).astype(np.float32)
+    wp, wr, wi = ref.snap_batch(p2, 8)
+    for m in (n, 1000):
+        gp, gr, gi = pf.snap_points(p2[:m])
+        assert (gr == wr[:m]).all() and (gi == wi[:m]).all() and beq(gp, wp[:m]).all()
