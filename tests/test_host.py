@@ -373,6 +373,36 @@ def test_hostemu_out_of_the_ordinary_inputs(name):
     emu.emu_destroy(h)
 
 
+@pytest.mark.parametrize("g", [1, 9, 200])
+def test_hostemu_multigoal_odd_goal_sets(g):
+    """MultiGoalShortestPath with goal sets the workloads do not produce: one goal, 200 goals,
+    duplicated goals (equal bounds: the order of the unstable std::sort decides), NaN goals, a goal
+    equal to the start, rows where nothing is reachable -- with every pair searched and with the
+    two-round pruning of the batched entry point."""
+    name = "t_building"
+    emu, h = _emu_handle(name)
+    ref = ref_pathfinder(name)
+    n = 120
+    st = np.ascontiguousarray(query_points(name, n, 71 + g))
+    en = query_points(name, n * g, 72 + g).reshape(n, g, 3).copy()
+    en[::5, 0] = en[::5, -1]
+    en[::7, g // 2] = np.nan
+    en[::9, 0] = st[::9]
+    en[3::11] = np.float32(1e4)
+    en[4::13, : max(1, g // 3)] = en[4::13, -1:]
+    en = np.ascontiguousarray(en)
+    wd, wi, _, _ = ref.find_path_multigoal_batch(st, en, 0, 4)
+    assert np.isfinite(wd).any() and np.isinf(wd).any()
+    for pruned in (0, 1):
+        dist = np.zeros(n, np.float32)
+        idx = np.zeros(n, np.int32)
+        searched = C.c_long()
+        emu.emu_find_path_multigoal(h, P(st, f32p), P(en, f32p), C.c_long(n), g, P(dist, f32p), P(idx, i32p), pruned,
+                                    C.byref(searched))
+        assert beq(dist, wd).all() and (idx == wi).all(), pruned
+    emu.emu_destroy(h)
+
+
 @pytest.mark.parametrize("seed", [11, 12, 13])
 def test_hostemu_fuzz_random_scenes(seed):
     """Fresh procedural scenes (not the cached benchmark ones): a seeded multi-room floor plan and a
