@@ -165,6 +165,41 @@ void emu_find_path(void* h, const float* starts, const float* ends, long n, int 
   }
 }
 
+// Node-key numbering of the flattener (PolyRec::key0, LinkRec::neiKey): out[0] = numKeys,
+// out[1] = 1 if the per-poly key ranges tile [0, numKeys) without overlap and every link's key
+// lies in its neighbour's range, out[2] = links counted, out[3] = sum over links of
+// |key0(poly) - neiKey| / 16 (distance in 32 B sectors of the node table: the locality the
+// numbering is chosen for).
+void emu_key_stats(void* h, long* out) {
+  Emu* e = static_cast<Emu*>(h);
+  const FlatNav& f = e->flat;
+  const size_t np = f.polys.size();
+  std::vector<uint8_t> sides(np, 1);
+  for (const LinkRec& lr : f.links)
+    if (lr.nei != kNoPoly) sides[lr.nei] |= static_cast<uint8_t>(1u << ((lr.meta >> kLinkStateShift) & 3u));
+  std::vector<uint8_t> seen(f.numKeys, 0);
+  bool ok = true;
+  for (size_t g = 0; g < np; ++g) {
+    const int cnt = __builtin_popcount(sides[g]);
+    for (int k = 0; k < cnt; ++k) {
+      const uint32_t key = f.polys[g].key0 + static_cast<uint32_t>(k);
+      if (key >= f.numKeys || seen[key]) ok = false; else seen[key] = 1;
+    }
+  }
+  for (uint32_t k = 0; k < f.numKeys; ++k) if (!seen[k]) ok = false;
+  long links = 0, dist = 0;
+  for (size_t g = 0; g < np; ++g)
+    for (uint32_t l = f.polys[g].linkStart; l < f.polys[g].linkStart + f.polys[g].linkCount; ++l) {
+      const LinkRec& lr = f.links[l];
+      if (lr.nei == kNoPoly) continue;
+      const uint32_t k0 = f.polys[lr.nei].key0;
+      if (lr.neiKey < k0 || lr.neiKey >= k0 + static_cast<uint32_t>(__builtin_popcount(sides[lr.nei]))) ok = false;
+      links++;
+      dist += labs(static_cast<long>(f.polys[g].key0 / 16) - static_cast<long>(lr.neiKey / 16));
+    }
+  out[0] = f.numKeys; out[1] = ok ? 1 : 0; out[2] = links; out[3] = dist;
+}
+
 // The lane-per-query search (hbn_astar_lane.h, the state machine k_astar_lane runs in every
 // lane) on ONE lane slot reused by all n queries, so table generations wrap and get wiped.
 // out_info [n,4]: {findPath status (0 = no search), corridor length, nodes allocated, event};

@@ -403,6 +403,29 @@ def test_hostemu_multigoal_odd_goal_sets(g):
     emu.emu_destroy(h)
 
 
+@pytest.mark.parametrize("name", ["c2_apartment", "c3_multiroom", "t_building", "c4_building"])
+def test_node_key_numbering(name, monkeypatch):
+    """The flattener numbers the A* node keys along a space-filling curve (height layers, Morton
+    order within a layer).  Whatever the order, the per-poly key ranges must tile [0, numKeys) and
+    every link must carry a key of its neighbour's range; and the curve must put the two ends of
+    a link closer together in the node table than poly order does (HBN_KEY_ORDER=0)."""
+    emu = hostemu()
+    img = navmesh_image(name)
+    stats = {}
+    for order in ("1", "0"):
+        monkeypatch.setenv("HBN_KEY_ORDER", order)
+        h = C.c_void_p(emu.emu_create(img, C.c_long(len(img))))
+        out = (C.c_long * 4)()
+        emu.emu_key_stats(h, out)
+        emu.emu_destroy(h)
+        assert out[1] == 1, "key ranges do not tile [0, numKeys)"
+        stats[order] = (out[0], out[3] / max(1, out[2]))
+    assert stats["1"][0] == stats["0"][0]
+    assert stats["1"][1] <= stats["0"][1], stats
+    if name in ("t_building", "c4_building"):  # tiled, multi-storey: poly order interleaves the storeys of a tile
+        assert stats["1"][1] < 0.5 * stats["0"][1], stats
+
+
 @pytest.mark.parametrize("seed", [11, 12, 13])
 def test_hostemu_fuzz_random_scenes(seed):
     """Fresh procedural scenes (not the cached benchmark ones): a seeded multi-room floor plan and a

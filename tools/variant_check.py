@@ -37,8 +37,9 @@ def as_u32(a):
 
 img = navmesh_bytes("c4_building")
 base = None
-for cfg in (os.environ.get("VARIANT_CFGS") or "0,17,22,20,21,18,19,23,1,8,10,13,15").split(","):
-    os.environ["HBN_LANE_CFG"] = cfg
+for cfg in (os.environ.get("VARIANT_CFGS") or "0,0k0,17,22,20,21,18,19,23,1,8,10,13,15").split(","):
+    os.environ["HBN_LANE_CFG"] = cfg.replace("k0", "")
+    os.environ["HBN_KEY_ORDER"] = "0" if cfg.endswith("k0") else "1"  # k0: node keys in poly order
     pf = PathFinder(0)
     assert pf.load_nav_mesh_bytes(img)
     pf.set_profiling(True)
@@ -55,6 +56,7 @@ for cfg in (os.environ.get("VARIANT_CFGS") or "0,17,22,20,21,18,19,23,1,8,10,13,
     del pf
     gc.collect()
 os.environ.pop("HBN_LANE_CFG")
+os.environ.pop("HBN_KEY_ORDER")
 
 img2 = navmesh_bytes("c2_apartment")
 base = None
