@@ -148,6 +148,8 @@ struct LaneSearch {
   static constexpr bool kSiftPrefetch = V == 5;
   // V = 6: 1 + the modify scan looks through the shared part of the heap before the HBM part
   static constexpr bool kScanSharedFirst = V == 6;
+  // V = 7: 1 + node-table loads and stores carry an L2 evict_last policy
+  static constexpr bool kTabEvictLast = V == 7;
   static_assert((TS & 1) == 1, "TS must be odd");
   // memory of this lane
   float* K;        // shared: heap keys
@@ -172,6 +174,32 @@ struct LaneSearch {
   uint32_t xcur;
   LaneRecB xB;
 
+  // Node-table accesses.  V = 7 marks them evict_last in L2: with the keys numbered along the
+  // space-filling curve the table working set of a search is a few KB, which is worth keeping
+  // against the record stream (device only; a hint, the values are the same).
+  HBN_HD uint32_t tabLoad(const uint32_t key) const {
+#if defined(__CUDA_ARCH__)
+    if constexpr (kTabEvictLast) {
+      unsigned long long pol;
+      unsigned short v;
+      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+      asm volatile("ld.global.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(tab + key), "l"(pol) : "memory");
+      return v;
+    }
+#endif
+    return tab[key];
+  }
+  HBN_HD void tabStore(const uint32_t key, const uint32_t v) const {
+#if defined(__CUDA_ARCH__)
+    if constexpr (kTabEvictLast) {
+      unsigned long long pol;
+      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+      asm volatile("st.global.L2::cache_hint.u16 [%0], %1, %2;" ::"l"(tab + key), "h"(static_cast<unsigned short>(v)), "l"(pol) : "memory");
+      return;
+    }
+#endif
+    tab[key] = static_cast<uint16_t>(v);
+  }
   HBN_HD LaneRecA* recA(uint32_t s) const { return reinterpret_cast<LaneRecA*>(rec + static_cast<size_t>(s) * 32); }
   HBN_HD LaneRecB* recB(uint32_t s) const { return reinterpret_cast<LaneRecB*>(rec + static_cast<size_t>(s) * 32 + 16); }
 
@@ -409,7 +437,7 @@ struct LaneSearch {
     const float stotal = vdist(sp, ep) * kHScale;
     *recA(0) = LaneRecA{sp[0], sp[1], sp[2], 0.f};
     *recB(0) = LaneRecB{startG, kLaneNoParent, slnk, 0u};
-    tab[spoly->key0] = static_cast<uint16_t>(gen << kLaneSlotBits);
+    tabStore(spoly->key0, gen << kLaneSlotBits);
     hset(0, stotal, 0u);
     size = 1;
     nodeCount = 1;
@@ -448,7 +476,7 @@ struct LaneSearch {
                    const bool fastFail, int* stop, float* opKey, uint32_t* opSlot) {
     const uint32_t nei = lo.nei;
     if ((hi.meta & kLinkDupBit) != 0) {  // an earlier link of this poly may just have created the node
-      te = tab[hi.neiKey];
+      te = tabLoad(hi.neiKey);
       if ((te >> kLaneSlotBits) == gen) ra = *recA(te & kLaneSlotMask);
     }
     const bool found = (te >> kLaneSlotBits) == gen;
@@ -485,7 +513,7 @@ struct LaneSearch {
     *recA(slot) = LaneRecA{npos[0], npos[1], npos[2], cost};
     *recB(slot) = LaneRecB{nei, bestG | (viaJ << 24), hi.neiLinkStart | ((hi.meta >> kLinkNeiCountShift) << 27),
                            bslot | (1u << 12)};
-    if (!found) tab[hi.neiKey] = static_cast<uint16_t>((gen << kLaneSlotBits) | slot);
+    if (!found) tabStore(hi.neiKey, (gen << kLaneSlotBits) | slot);
     if (heuristic < lastBestCost) {  // DQ.cpp:1154-1159
       lastBestCost = heuristic;
       lastBest = slot;
@@ -624,7 +652,7 @@ struct LaneSearch {
       for (int k = 0; k < kLaneChunk; ++k) {
         if (lo[k].nei != kNoPoly) nNeigh++;
         cand[k] = lo[k].nei != kNoPoly && lo[k].nei != parentG && (hi[k].meta & kLinkPassBit) != 0;
-        te[k] = cand[k] ? tab[hi[k].neiKey] : 0u;
+        te[k] = cand[k] ? tabLoad(hi[k].neiKey) : 0u;
       }
 #if defined(__CUDA_ARCH__)
 #pragma unroll

@@ -181,6 +181,8 @@ const void* laneKernel(int cfg, size_t* shared) {
     // modify scan looks through the shared part of the heap first (V = 6)
     HBN_LANE_CASE(20, 63, k_astar_lane<63, 16, 4, 6>)
     HBN_LANE_CASE(21, 63, k_astar_lane_r<63, 112, 4, 6>)
+    // node-table accesses with an L2 evict_last policy (V = 7)
+    HBN_LANE_CASE(24, 63, k_astar_lane<63, 16, 4, 7>)
     // 95 entries (85 % of the pops find the whole open list in shared memory) at 11 warps per SM
     HBN_LANE_CASE(23, 95, k_astar_lane<95, 11, 4>)
     default: *shared = laneSharedBytes<kLaneTS>(); return reinterpret_cast<const void*>(&k_astar_lane<kLaneTS, kLaneMinB, 4>);

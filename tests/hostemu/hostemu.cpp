@@ -584,7 +584,7 @@ long emu_lane_heap_fuzz(int ts, int v, unsigned seed, long ops, int keyLevels) {
 long emu_lane_lockstep(void* h, int ts, int v, const float* starts, const float* ends, long n, int fastFail) {
 #define HBN_EMU_LOCK(T, VV) if (ts == T && v == VV) return laneLockstep<T, VV>(h, starts, ends, n, fastFail);
   HBN_EMU_LOCK(3, 1) HBN_EMU_LOCK(3, 2) HBN_EMU_LOCK(7, 2) HBN_EMU_LOCK(31, 2) HBN_EMU_LOCK(63, 2)
-  HBN_EMU_LOCK(47, 1) HBN_EMU_LOCK(47, 2) HBN_EMU_LOCK(55, 1) HBN_EMU_LOCK(39, 1) HBN_EMU_LOCK(63, 3) HBN_EMU_LOCK(47, 4) HBN_EMU_LOCK(63, 5) HBN_EMU_LOCK(63, 6) HBN_EMU_LOCK(59, 1) HBN_EMU_LOCK(95, 1)
+  HBN_EMU_LOCK(47, 1) HBN_EMU_LOCK(47, 2) HBN_EMU_LOCK(55, 1) HBN_EMU_LOCK(39, 1) HBN_EMU_LOCK(63, 3) HBN_EMU_LOCK(47, 4) HBN_EMU_LOCK(63, 5) HBN_EMU_LOCK(63, 6) HBN_EMU_LOCK(59, 1) HBN_EMU_LOCK(95, 1) HBN_EMU_LOCK(63, 7)
 #undef HBN_EMU_LOCK
   return -1;
 }

@@ -305,7 +305,7 @@ def test_hostemu_lane_heap_fuzz(ts, v):
             assert emu.emu_lane_heap_fuzz(ts, v, seed, C.c_long(8000), levels) == 0, (levels, seed)
 
 
-@pytest.mark.parametrize("ts,v", [(3, 1), (3, 2), (7, 2), (31, 2), (39, 1), (47, 1), (47, 2), (47, 4), (55, 1), (63, 2), (59, 1), (63, 3), (63, 5), (63, 6), (95, 1)])
+@pytest.mark.parametrize("ts,v", [(3, 1), (3, 2), (7, 2), (31, 2), (39, 1), (47, 1), (47, 2), (47, 4), (55, 1), (63, 2), (59, 1), (63, 3), (63, 5), (63, 6), (63, 7), (95, 1)])
 @pytest.mark.parametrize("name", ["c3_multiroom", "c4_building"])
 def test_hostemu_lane_variants_lockstep(name, ts, v):
     """Every variant in lock step with the shipped one: same heap entries, node count, best node

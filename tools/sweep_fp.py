@@ -5,10 +5,10 @@ n = sys.argv[1] if len(sys.argv) > 1 else "400000"
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # lane:N = HBN_LANE_CFG (hbn_capi.cu laneKernel): 0 shipped, 1-4 shared-heap / occupancy variants,
 # 5-7, 11 heap code variant 2 (two heap levels per HBM round trip), 8-10 47 / 55 shared entries at 19-21 warps/SM
-variants = (("lane", None), ("lane:17", None), ("lane:22", None), ("lane:20", None), ("lane:21", None),
+variants = (("lane", None), ("lane:24", None), ("lane:17", None), ("lane:22", None), ("lane:20", None), ("lane:21", None),
             ("lane:18", None), ("lane:23", None), ("lane:1", None))
 if os.environ.get("SWEEP_LANE_ALL"):
-    variants = (("lane", None),) + tuple((f"lane:{c}", None) for c in range(1, 24))
+    variants = (("lane", None),) + tuple((f"lane:{c}", None) for c in range(1, 25))
 os.environ.setdefault("HBN_QUERY_CACHE", "/tmp/hbn_queries")  # bench.py generates the pairs once
 if os.environ.get("SWEEP_ALL"):
     variants += (("8", None), ("32", None), ("4", None))
