@@ -144,8 +144,10 @@ HBN_HD float mnDist(const float* a, const float* b) {
   return fsqrt(out);
 }
 
-// Counter-based uniform stream in [0,1] (1.0 reachable, like rand()/RAND_MAX, trap T7).
-// This is this library's definition (include/hbn.h: hbn_uniform); the oracle restates it.
+// Counter-based uniform stream in [0,1], in the form of the reference's frand() (PF.cpp:1232-1234):
+// float(r) / float(RAND_MAX) with r a 31-bit value, so that the reference's own code, fed r through
+// rand(), computes the identical float (1.0 is reachable: float(2^31 - 1) rounds to 2^31; trap T7).
+// This is this library's definition (include/hbn.h: hbn_uniform).
 HBN_HD uint32_t mix32(uint32_t x) {
   x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
   return x;
@@ -156,7 +158,7 @@ HBN_HD float uniform01(uint64_t seed, uint64_t query, uint32_t draw) {
   h = mix32(h ^ static_cast<uint32_t>(query));
   h = mix32(h ^ static_cast<uint32_t>(query >> 32) ^ 0x85ebca6bU);
   h = mix32(h ^ draw);
-  return static_cast<float>(h >> 8) / 16777215.0f;
+  return static_cast<float>(static_cast<int>(h >> 1)) / 2147483648.0f;
 }
 
 }  // namespace hbn

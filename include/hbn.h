@@ -159,6 +159,9 @@ int hbn_random_points_dev(hbn_navmesh_t nm, uint64_t seed, uint64_t query0, int6
 int hbn_random_points_near_dev(hbn_navmesh_t nm, uint64_t seed, uint64_t query0, int64_t n,
                                const float* centers, float radius, const int32_t* islands, int max_tries,
                                float* out_pts, void* stream);
+/* The stream: u = float(r) / float(RAND_MAX) with r = the top 31 bits of a 32-bit hash of
+ * (seed, query, draw) -- the form of the reference's frand() (PF.cpp:1232-1234), so the
+ * reference's own code driven by rand() := r sees bit-identical uniforms. */
 float hbn_uniform(uint64_t seed, uint64_t query, uint32_t draw);
 /* order[0..n) <- the permutation std::sort (libstdc++ introsort, unstable) leaves when sorting 0..n-1
  * by key: the goal order of findPath(MultiGoalShortestPath&), PF.cpp:1542-1548.  Host function. */

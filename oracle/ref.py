@@ -1,10 +1,12 @@
 """ctypes binding of oracle/_ref/libhbn_ref.so -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 
-The library is the reference's own Detour + Recast (compiled from
-/root/reference/src/deps/recastnavigation by oracle/Makefile) plus the restated
-esp::nav::PathFinder layer in oracle/ref_pathfinder.cpp.  Only tests/,
-__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs (and
-the navmesh *input* builders they use) may import this module.
+The library is the reference's own, unmodified src/esp/nav/PathFinder.cpp + Detour + Recast,
+compiled where they lie under /root/reference by oracle/Makefile (SURVEY.md 8c recipe), behind
+the C ABI of oracle/ref_esp.cpp.  `RefPathFinder(restated=True)` binds the round-1 restatement
+of the PathFinder layer instead (oracle/_ref/libhbn_restated.so); it exists only so that
+tests/test_oracle.py can compare the two bit for bit.  Only tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs (and the navmesh *input* builders they use) may
+import this module.
 """
 from __future__ import annotations
 
@@ -16,7 +18,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_ref", "libhbn_ref.so")
-_lib = None
+_SO_RESTATED = os.path.join(_HERE, "_ref", "libhbn_restated.so")
+_libs = {}
 
 f32p = C.POINTER(C.c_float)
 u32p = C.POINTER(C.c_uint32)
@@ -27,7 +30,7 @@ u8p = C.POINTER(C.c_uint8)
 
 def build(force: bool = False) -> str:
     """Compile the oracle library (needs /root/reference); returns the .so path."""
-    if force or not os.path.exists(_SO):
+    if force or not os.path.exists(_SO) or not os.path.exists(_SO_RESTATED):
         if not os.path.isdir("/root/reference/src/deps/recastnavigation"):
             raise RuntimeError(
                 "oracle/_ref/libhbn_ref.so is missing and /root/reference is not present to build it")
@@ -35,19 +38,25 @@ def build(force: bool = False) -> str:
     return _SO
 
 
-def lib():
-    global _lib
-    if _lib is None:
+def lib(restated: bool = False):
+    l = _libs.get(restated)
+    if l is None:
         build()
-        _lib = C.CDLL(_SO)
-        _lib.ref_create.restype = C.c_void_p
-        _lib.ref_multigoal_create.restype = C.c_void_p
-        _lib.ref_save_memory.restype = C.c_int64
-        _lib.ref_poly_islands.restype = C.c_int64
-        _lib.ref_navigable_area.restype = C.c_float
-        _lib.ref_island_radius.restype = C.c_float
-        _lib.ref_uniform.restype = C.c_float
-    return _lib
+        l = C.CDLL(_SO_RESTATED if restated else _SO)
+        l.ref_create.restype = C.c_void_p
+        l.ref_multigoal_create.restype = C.c_void_p
+        l.ref_save_memory.restype = C.c_int64
+        l.ref_poly_islands.restype = C.c_int64
+        l.ref_navigable_area.restype = C.c_float
+        l.ref_island_radius.restype = C.c_float
+        l.ref_uniform.restype = C.c_float
+        if not restated:
+            assert l.ref_is_reference_pathfinder() == 1
+            l.ref_frand_of_stream.restype = C.c_float
+            l.ref_topdown_view.restype = C.c_int64
+            l.ref_navmesh_vertices.restype = C.c_int64
+        _libs[restated] = l
+    return l
 
 
 def _f32(a, shape_last=3):
@@ -60,10 +69,12 @@ def _p(a, typ):
 
 
 class RefPathFinder:
-    """Reference PathFinder (real Detour, restated esp::nav layer) on the CPU."""
+    """The reference's esp::nav::PathFinder on the CPU (restated=True: the round-1 restatement of
+    that layer over the same Detour, kept for the cross-check only)."""
 
-    def __init__(self):
-        self._l = lib()
+    def __init__(self, restated: bool = False):
+        self.restated = restated
+        self._l = lib(restated)
         self._h = C.c_void_p(self._l.ref_create())
 
     def __del__(self):
@@ -313,12 +324,34 @@ class RefPathFinder:
         return out
 
 
+    # ---- only the reference's own PathFinder has these --------------------------------
+    def topdown_view(self, meters_per_pixel: float, height: float, eps: float = 0.5, islands: bool = False):
+        """get_topdown_view (bool [H, W]) / get_topdown_island_view (int32 [H, W]), PF.cpp:1833-1896."""
+        dims = np.zeros(2, np.int32)
+        args = (self._h, C.c_float(meters_per_pixel), C.c_float(height), C.c_float(eps), C.c_int(1 if islands else 0))
+        n = self._l.ref_topdown_view(*args, None, C.c_int64(0), _p(dims, i32p))
+        out = np.zeros(max(int(n), 1), np.int32)
+        self._l.ref_topdown_view(*args, _p(out, i32p), C.c_int64(n), _p(dims, i32p))
+        g = out[:n].reshape(int(dims[0]), int(dims[1]))
+        return g if islands else g.astype(bool)
+
+    def navmesh_vertices(self, island: int = -1):
+        """build_navmesh_vertices / build_navmesh_vertex_indices (getNavMeshData, PF.cpp:1898-1944)."""
+        n = self._l.ref_navmesh_vertices(self._h, C.c_int(island), None, None, C.c_int64(0))
+        if n < 0:
+            raise ValueError(f"{island} not a valid index for this island system.")
+        v = np.zeros((max(int(n), 1), 3), np.float32)
+        idx = np.zeros(max(int(n), 1), np.uint32)
+        self._l.ref_navmesh_vertices(self._h, C.c_int(island), _p(v, f32p), _p(idx, u32p), C.c_int64(n))
+        return v[:n], idx[:n]
+
+
 class RefMultiGoal:
     """Stateful MultiGoalShortestPath twin (PF.cpp:95-123) for cache / trap-T4 tests."""
 
     def __init__(self, pf: RefPathFinder):
         self._pf = pf
-        self._l = lib()
+        self._l = pf._l
         self._m = C.c_void_p(self._l.ref_multigoal_create())
 
     def __del__(self):
@@ -345,6 +378,12 @@ class RefMultiGoal:
 
 def uniform(seed: int, query: int, draw: int) -> float:
     return float(lib().ref_uniform(C.c_uint64(seed), C.c_uint64(query), C.c_uint32(draw)))
+
+
+def frand_of_stream(seed: int, query: int, draw: int) -> float:
+    """What the reference's unmodified frand() (PF.cpp:1232-1234) returns when the oracle's
+    interposed rand() serves draw `draw` of the counter-based stream."""
+    return float(lib().ref_frand_of_stream(C.c_uint64(seed), C.c_uint64(query), C.c_uint32(draw)))
 
 
 def random_point_in_convex_poly(pts, s: float, t: float):

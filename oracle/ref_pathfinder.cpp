@@ -1,24 +1,13 @@
 // =============================================================================
-// oracle/ref_pathfinder.cpp  --  TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+// oracle/ref_pathfinder.cpp  --  TEST INFRASTRUCTURE, NOT PRODUCT CODE, NOT THE ORACLE.
 //
-// CPU oracle for the navmesh query path.  It links the reference's OWN,
-// unmodified Detour + Recast sources (compiled where they lie under
-// /root/reference/src/deps/recastnavigation by oracle/Makefile into
-// oracle/_ref/) and restates, on top of them, the thin esp::nav::PathFinder::Impl
-// layer (src/esp/nav/PathFinder.cpp, "PF.cpp" below) that habitat-sim wraps
-// around dtNavMeshQuery.  PathFinder.cpp itself needs Corrade/Magnum built by
-// cmake plus generated configure headers, so it is restated here line by line
-// (each function cites the PF.cpp range it follows) instead of being compiled.
-//
-// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
-// reference legs may load this library.  bench.py and the test fixtures also use
-// its Recast entry points to BUILD navmesh inputs (the north star keeps navmesh
-// construction on the host in the reference's own Recast path).
-//
-// Parity pinning: all Detour arithmetic here IS the reference (same sources).
-// The PF-layer restatement is pinned by tests/test_oracle.py properties that
-// mirror src/tests/NavTest.cpp / PathFinderTest.cpp and by
-// Tests/Detour/Tests_Detour.cpp known answers.
+// The round-1 RESTATEMENT of the thin esp::nav::PathFinder::Impl layer (src/esp/nav/PathFinder.cpp,
+// "PF.cpp" below; each function cites the range it follows) over the reference's own Detour + Recast.
+// Since round 2 the oracle is the reference's PathFinder.cpp itself (oracle/ref_esp.cpp ->
+// oracle/_ref/libhbn_ref.so).  This file is built into oracle/_ref/libhbn_restated.so and loaded by
+// exactly one test, tests/test_oracle.py::test_restatement_equals_reference_pathfinder, which shows
+// the two agree bit for bit on the five scenes -- i.e. that what round 1 checked against this
+// restatement also held against the reference.  No parity test, smoke() or bench leg uses it.
 // =============================================================================
 #include <algorithm>
 #include <atomic>
@@ -44,7 +33,10 @@
 #include "DetourNode.h"
 #include "Recast.h"
 
+#include "tiled_recast.h"
+
 namespace {
+using namespace hbnoracle;
 
 // ---- Magnum::Vector3 operations used by PF.cpp, same operation order --------
 // (src/deps/magnum/src/Magnum/Math/Vector.h:106-111 dot, :997 length,
@@ -86,59 +78,9 @@ inline bool mnFuzzyEq(const V3& a, const V3& b) {
 const float kNaN = std::numeric_limits<float>::quiet_NaN();
 const float kInf = std::numeric_limits<float>::infinity();
 
-// PF.h:137-299 (56 bytes, written raw into .navmesh files, PF.cpp:1204)
-struct NavMeshSettings {
-  float cellSize = 0.05f, cellHeight = 0.2f, agentHeight = 1.5f, agentRadius = 0.1f,
-        agentMaxClimb = 0.2f, agentMaxSlope = 45.0f, regionMinSize = 20.f,
-        regionMergeSize = 20.f, edgeMaxLen = 12.0f, edgeMaxError = 1.3f,
-        vertsPerPoly = 6.0f, detailSampleDist = 6.0f, detailSampleMaxError = 1.0f;
-  bool filterLowHangingObstacles = true, filterLedgeSpans = true,
-       filterWalkableLowHeightSpans = true, includeStaticObjects = false;
-};
-static_assert(sizeof(NavMeshSettings) == 56, "NavMeshSettings layout");
 
-// PF.cpp:590-600
-enum PolyAreas { POLYAREA_GROUND, POLYAREA_DOOR };
-enum PolyFlags {
-  POLYFLAGS_WALK = 0x01,
-  POLYFLAGS_DOOR = 0x02,
-  POLYFLAGS_DISABLED = 0x04,
-  POLYFLAGS_OFF_ISLAND = 0x08,
-  POLYFLAGS_ALL = 0xffff
-};
 const int ID_UNDEFINED = -1;  // core/Esp.h:100
 
-// PF.cpp:978-991
-const int NAVMESHSET_MAGIC = 'M' << 24 | 'S' << 16 | 'E' << 8 | 'T';
-const int NAVMESHSET_VERSION = 2;
-struct NavMeshSetHeader {
-  int magic;
-  int version;
-  int numTiles;
-  dtNavMeshParams params;
-};
-struct NavMeshTileHeader {
-  dtTileRef tileRef;
-  int dataSize;
-};
-
-// ---- random stream ---------------------------------------------------------
-// PF.cpp:1225-1234 uses glibc srand/rand.  For GPU parity the same uniforms must
-// be fed to both sides (SURVEY trap T7), so the oracle can also draw from the
-// counter-based stream hbn_uniform(seed, query, draw) that include/hbn.h defines.
-inline uint32_t mix32(uint32_t x) {
-  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
-  return x;
-}
-inline float hbnUniform(uint64_t seed, uint64_t query, uint32_t draw) {
-  uint32_t h = mix32(static_cast<uint32_t>(seed) ^ 0x9e3779b9U);
-  h = mix32(h ^ static_cast<uint32_t>(seed >> 32));
-  h = mix32(h ^ static_cast<uint32_t>(query));
-  h = mix32(h ^ static_cast<uint32_t>(query >> 32) ^ 0x85ebca6bU);
-  h = mix32(h ^ draw);
-  // 24 random bits -> [0, 1]; 1.0 is reachable like rand()/RAND_MAX (T7)
-  return static_cast<float>(h >> 8) / 16777215.0f;
-}
 struct RandStream {
   int mode = 0;  // 0 = glibc rand(), 1 = counter based
   uint64_t seed = 0, query = 0;
@@ -359,145 +301,6 @@ struct HitRecord {
   float hitDist;
 };
 
-// ---- one Recast tile / solo build: PF.cpp:612-896 ---------------------------
-struct BuildOut {
-  unsigned char* navData = nullptr;
-  int navDataSize = 0;
-  int npolys = 0;
-};
-
-// Steps 1-8 of PathFinder::Impl::build.  tiled=false follows PF.cpp exactly;
-// tiled=true adds what RecastDemo/Source/Sample_TileMesh.cpp:794-1160 adds for a
-// tile (tileSize/borderSize config, expanded bounds, borderSize passed to
-// rcBuildRegions, tileX/tileY in the create params).
-bool recastBuildOne(const NavMeshSettings& bs, const float* verts, int nverts,
-                    const int* tris, int ntris, const float* bmin, const float* bmax,
-                    bool tiled, int tileSize, int tx, int ty, BuildOut& out) {
-  rcContext ctx(false);
-  rcConfig cfg{};
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.cs = bs.cellSize;
-  cfg.ch = bs.cellHeight;
-  cfg.walkableSlopeAngle = bs.agentMaxSlope;
-  cfg.walkableHeight = static_cast<int>(ceilf(bs.agentHeight / cfg.ch));
-  cfg.walkableClimb = static_cast<int>(floorf(bs.agentMaxClimb / cfg.ch));
-  cfg.walkableRadius = static_cast<int>(ceilf(bs.agentRadius / cfg.cs));
-  cfg.maxEdgeLen = static_cast<int>(bs.edgeMaxLen / bs.cellSize);
-  cfg.maxSimplificationError = bs.edgeMaxError;
-  cfg.minRegionArea = static_cast<int>(rcSqr(bs.regionMinSize));
-  cfg.mergeRegionArea = static_cast<int>(rcSqr(bs.regionMergeSize));
-  cfg.maxVertsPerPoly = static_cast<int>(bs.vertsPerPoly);
-  cfg.detailSampleDist = bs.detailSampleDist < 0.9f ? 0 : bs.cellSize * bs.detailSampleDist;
-  cfg.detailSampleMaxError = bs.cellHeight * bs.detailSampleMaxError;
-  rcVcopy(cfg.bmin, bmin);
-  rcVcopy(cfg.bmax, bmax);
-  if (tiled) {
-    cfg.tileSize = tileSize;
-    cfg.borderSize = cfg.walkableRadius + 3;
-    cfg.width = cfg.tileSize + cfg.borderSize * 2;
-    cfg.height = cfg.tileSize + cfg.borderSize * 2;
-    cfg.bmin[0] -= cfg.borderSize * cfg.cs;
-    cfg.bmin[2] -= cfg.borderSize * cfg.cs;
-    cfg.bmax[0] += cfg.borderSize * cfg.cs;
-    cfg.bmax[2] += cfg.borderSize * cfg.cs;
-  } else {
-    rcCalcGridSize(cfg.bmin, cfg.bmax, cfg.cs, &cfg.width, &cfg.height);
-  }
-
-  struct Workspace {
-    rcHeightfield* solid = nullptr;
-    unsigned char* triareas = nullptr;
-    rcCompactHeightfield* chf = nullptr;
-    rcContourSet* cset = nullptr;
-    rcPolyMesh* pmesh = nullptr;
-    rcPolyMeshDetail* dmesh = nullptr;
-    ~Workspace() {
-      rcFreeHeightField(solid);
-      delete[] triareas;
-      rcFreeCompactHeightfield(chf);
-      rcFreeContourSet(cset);
-      rcFreePolyMesh(pmesh);
-      rcFreePolyMeshDetail(dmesh);
-    }
-  } ws;
-
-  ws.solid = rcAllocHeightfield();
-  if (!rcCreateHeightfield(&ctx, *ws.solid, cfg.width, cfg.height, cfg.bmin, cfg.bmax,
-                           cfg.cs, cfg.ch))
-    return false;
-  ws.triareas = new unsigned char[ntris > 0 ? ntris : 1];
-  memset(ws.triareas, 0, ntris * sizeof(unsigned char));
-  rcMarkWalkableTriangles(&ctx, cfg.walkableSlopeAngle, verts, nverts, tris, ntris,
-                          ws.triareas);
-  if (!rcRasterizeTriangles(&ctx, verts, nverts, tris, ws.triareas, ntris, *ws.solid,
-                            cfg.walkableClimb))
-    return false;
-  if (bs.filterLowHangingObstacles)
-    rcFilterLowHangingWalkableObstacles(&ctx, cfg.walkableClimb, *ws.solid);
-  if (bs.filterLedgeSpans)
-    rcFilterLedgeSpans(&ctx, cfg.walkableHeight, cfg.walkableClimb, *ws.solid);
-  if (bs.filterWalkableLowHeightSpans)
-    rcFilterWalkableLowHeightSpans(&ctx, cfg.walkableHeight, *ws.solid);
-  ws.chf = rcAllocCompactHeightfield();
-  if (!rcBuildCompactHeightfield(&ctx, cfg.walkableHeight, cfg.walkableClimb, *ws.solid,
-                                 *ws.chf))
-    return false;
-  if (!rcErodeWalkableArea(&ctx, cfg.walkableRadius, *ws.chf)) return false;
-  if (!rcBuildDistanceField(&ctx, *ws.chf)) return false;
-  if (!rcBuildRegions(&ctx, *ws.chf, tiled ? cfg.borderSize : 0, cfg.minRegionArea,
-                      cfg.mergeRegionArea))
-    return false;
-  ws.cset = rcAllocContourSet();
-  if (!rcBuildContours(&ctx, *ws.chf, cfg.maxSimplificationError, cfg.maxEdgeLen, *ws.cset))
-    return false;
-  ws.pmesh = rcAllocPolyMesh();
-  if (!rcBuildPolyMesh(&ctx, *ws.cset, cfg.maxVertsPerPoly, *ws.pmesh)) return false;
-  ws.dmesh = rcAllocPolyMeshDetail();
-  if (!rcBuildPolyMeshDetail(&ctx, *ws.pmesh, *ws.chf, cfg.detailSampleDist,
-                             cfg.detailSampleMaxError, *ws.dmesh))
-    return false;
-  if (cfg.maxVertsPerPoly > DT_VERTS_PER_POLYGON) return false;
-  out.npolys = ws.pmesh->npolys;
-  if (tiled && ws.pmesh->npolys == 0) return true;  // empty tile: no data
-
-  for (int i = 0; i < ws.pmesh->npolys; ++i) {
-    if (ws.pmesh->areas[i] == RC_WALKABLE_AREA) ws.pmesh->areas[i] = POLYAREA_GROUND;
-    if (ws.pmesh->areas[i] == POLYAREA_GROUND) {
-      ws.pmesh->flags[i] = POLYFLAGS_WALK;
-    } else if (ws.pmesh->areas[i] == POLYAREA_DOOR) {
-      ws.pmesh->flags[i] = POLYFLAGS_WALK | POLYFLAGS_DOOR;
-    }
-  }
-  dtNavMeshCreateParams params{};
-  memset(&params, 0, sizeof(params));
-  params.verts = ws.pmesh->verts;
-  params.vertCount = ws.pmesh->nverts;
-  params.polys = ws.pmesh->polys;
-  params.polyAreas = ws.pmesh->areas;
-  params.polyFlags = ws.pmesh->flags;
-  params.polyCount = ws.pmesh->npolys;
-  params.nvp = ws.pmesh->nvp;
-  params.detailMeshes = ws.dmesh->meshes;
-  params.detailVerts = ws.dmesh->verts;
-  params.detailVertsCount = ws.dmesh->nverts;
-  params.detailTris = ws.dmesh->tris;
-  params.detailTriCount = ws.dmesh->ntris;
-  params.walkableHeight = bs.agentHeight;
-  params.walkableRadius = bs.agentRadius;
-  params.walkableClimb = bs.agentMaxClimb;
-  rcVcopy(params.bmin, ws.pmesh->bmin);
-  rcVcopy(params.bmax, ws.pmesh->bmax);
-  params.cs = cfg.cs;
-  params.ch = cfg.ch;
-  params.buildBvTree = true;
-  if (tiled) {
-    params.tileX = tx;
-    params.tileY = ty;
-    params.tileLayer = 0;
-  }
-  if (!dtCreateNavMeshData(&params, &out.navData, &out.navDataSize)) return false;
-  return true;
-}
 
 // ---- the PathFinder restatement ----------------------------------------------
 class RefPathFinder {
@@ -540,97 +343,13 @@ class RefPathFinder {
     return true;
   }
 
-  // Tiled host build (not a PathFinder method).  The result is what
-  // PathFinder::loadNavMesh (PF.cpp:1091-1175) ingests after save().
+  // Tiled host build (not a PathFinder method): oracle/tiled_recast.h makes the
+  // MSET image, which is then loaded like any .navmesh file (PF.cpp:1091-1175).
   bool buildTiled(const NavMeshSettings& bs, const float* verts, int nverts,
                   const int* tris, int ntris, int tileSize, int nthreads) {
-    float bmin[3], bmax[3];
-    rcCalcBounds(verts, nverts, bmin, bmax);
-    int gw = 0, gh = 0;
-    rcCalcGridSize(bmin, bmax, bs.cellSize, &gw, &gh);
-    const int tw = (gw + tileSize - 1) / tileSize;
-    const int th = (gh + tileSize - 1) / tileSize;
-    const float tcs = tileSize * bs.cellSize;
-    const int walkableRadius = static_cast<int>(ceilf(bs.agentRadius / bs.cellSize));
-    const float border = (walkableRadius + 3) * bs.cellSize;
-
-    // triangle xz bounds for the per-tile geometry query
-    std::vector<float> tb(static_cast<size_t>(ntris) * 4);
-    for (int i = 0; i < ntris; ++i) {
-      float x0 = FLT_MAX, x1 = -FLT_MAX, z0 = FLT_MAX, z1 = -FLT_MAX;
-      for (int k = 0; k < 3; ++k) {
-        const float* v = &verts[static_cast<size_t>(tris[i * 3 + k]) * 3];
-        x0 = std::min(x0, v[0]); x1 = std::max(x1, v[0]);
-        z0 = std::min(z0, v[2]); z1 = std::max(z1, v[2]);
-      }
-      tb[i * 4 + 0] = x0; tb[i * 4 + 1] = x1; tb[i * 4 + 2] = z0; tb[i * 4 + 3] = z1;
-    }
-    std::vector<BuildOut> outs(static_cast<size_t>(tw) * th);
-    std::atomic<int> next(0);
-    std::atomic<bool> ok(true);
-    auto worker = [&]() {
-      std::vector<int> ltris;
-      for (;;) {
-        const int t = next.fetch_add(1);
-        if (t >= tw * th) break;
-        const int tx = t % tw, ty = t / tw;
-        float tbmin[3] = {bmin[0] + tx * tcs, bmin[1], bmin[2] + ty * tcs};
-        float tbmax[3] = {bmin[0] + (tx + 1) * tcs, bmax[1], bmin[2] + (ty + 1) * tcs};
-        const float qx0 = tbmin[0] - border, qx1 = tbmax[0] + border;
-        const float qz0 = tbmin[2] - border, qz1 = tbmax[2] + border;
-        ltris.clear();
-        for (int i = 0; i < ntris; ++i) {
-          if (tb[i * 4 + 0] > qx1 || tb[i * 4 + 1] < qx0 || tb[i * 4 + 2] > qz1 ||
-              tb[i * 4 + 3] < qz0)
-            continue;
-          ltris.push_back(tris[i * 3]);
-          ltris.push_back(tris[i * 3 + 1]);
-          ltris.push_back(tris[i * 3 + 2]);
-        }
-        if (ltris.empty()) continue;
-        if (!recastBuildOne(bs, verts, nverts, ltris.data(),
-                            static_cast<int>(ltris.size() / 3), tbmin, tbmax, true, tileSize,
-                            tx, ty, outs[t]))
-          ok = false;
-      }
-    };
-    std::vector<std::thread> pool;
-    for (int i = 0; i < std::max(1, nthreads); ++i) pool.emplace_back(worker);
-    for (auto& th_ : pool) th_.join();
-    if (!ok) {
-      for (auto& o : outs) if (o.navData) dtFree(o.navData);
-      return false;
-    }
-    int numTiles = 0, maxPolysInTile = 0;
-    for (auto& o : outs)
-      if (o.navData) {
-        ++numTiles;
-        maxPolysInTile = std::max(maxPolysInTile, o.npolys);
-      }
-    if (numTiles == 0) return false;
-    reset();
-    dtNavMeshParams params;
-    rcVcopy(params.orig, bmin);
-    params.tileWidth = tcs;
-    params.tileHeight = tcs;
-    params.maxTiles = numTiles;  // trap T10: must equal the tile count
-    const int tileBits = dtIlog2(dtNextPow2(static_cast<unsigned int>(numTiles)));
-    const int polyBits = std::min(22 - tileBits, 16);
-    params.maxPolys = 1 << polyBits;
-    if (maxPolysInTile > params.maxPolys) return false;
-    navMesh_ = dtAllocNavMesh();
-    if (dtStatusFailed(navMesh_->init(&params))) return false;
-    for (auto& o : outs) {
-      if (!o.navData) continue;
-      if (dtStatusFailed(navMesh_->addTile(o.navData, o.navDataSize, DT_TILE_FREE_DATA, 0,
-                                           nullptr))) {
-        dtFree(o.navData);
-        return false;
-      }
-    }
-    settings_ = bs;
-    computeBoundsFromTiles();
-    return initNavQuery();
+    std::vector<unsigned char> image;
+    if (!buildTiledImage(bs, verts, nverts, tris, ntris, tileSize, nthreads, image)) return false;
+    return loadFromMemory(image.data(), image.size());
   }
 
   // PF.cpp:1091-1175
@@ -824,7 +543,7 @@ class RefPathFinder {
     if (raw) {
       raw->astarStatus = status;
       raw->numPolys = numPolys;
-      raw->nodesUsed = q->getNodePool()->getNodeCount();
+      raw->nodesUsed = startRef == endRef ? 0 : q->getNodePool()->getNodeCount();  // (same poly: findPath returns before clearing the pool)
     }
     if (status != DT_SUCCESS || numPolys == 0) return false;
     int numPoints = 0;

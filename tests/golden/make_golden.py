@@ -1,4 +1,5 @@
-"""Regenerates tests/golden/*.npz: oracle (reference Detour) outputs on seeded inputs.
+"""Regenerates tests/golden/*.npz: outputs of the reference's own PathFinder.cpp + Detour (compiled in
+place by oracle/Makefile, bound by oracle/ref.py) on seeded inputs.
 
 Run here (the container with /root/reference): python tests/golden/make_golden.py
 The MSET navmesh image each vector set belongs to is stored inside the .npz, so the vectors
@@ -62,6 +63,12 @@ def make(name: str, n: int, seed: int, image: bytes | None = None):
     mg_ends = (geom.sample(n // 4 * g, rng) + rng.normal(0, 0.2, (n // 4 * g, 3))).astype(np.float32).reshape(n // 4, g, 3)
     mg_d, mg_i, mg_n, _ = pf.find_path_multigoal_batch(starts[: n // 4], mg_ends)
     refs_all, isl_all = pf.poly_islands()
+    # the reference's own top-down views and navmesh geometry (PF.cpp:1833-1896, :1898-1944)
+    td_h = float(snap_pts[np.isfinite(snap_pts[:, 0])][0, 1])
+    td = pf.topdown_view(0.25, td_h)
+    tdi = pf.topdown_view(0.25, td_h, islands=True)
+    nv_all, _ = pf.navmesh_vertices(-1)
+    nv_last, _ = pf.navmesh_vertices(pf.num_islands - 1)
     np.savez_compressed(
         os.path.join(HERE, name + ".npz"), image=np.frombuffer(image, np.uint8), starts=starts, ends=ends,
         snap_pts=snap_pts, snap_refs=snap_refs, snap_isl=snap_isl, dist=raw["dist"],
@@ -70,6 +77,8 @@ def make(name: str, n: int, seed: int, image: bytes | None = None):
         step_targets=tgt, step_sliding=step_s, step_nosliding=step_n, hit_pos=hp, hit_normal=hn,
         hit_dist=hd, rand_islands=isl, rand_pts=rp, rand_refs=rr, mg_ends=mg_ends, mg_dist=mg_d,
         mg_idx=mg_i, mg_npts=mg_n, poly_refs=refs_all, poly_islands=isl_all,
+        topdown_height=np.float32(td_h), topdown=td, topdown_islands=tdi, nav_verts_all=nv_all,
+        nav_verts_last_island=nv_last,
         seed=np.int32(seed), num_islands=np.int32(pf.num_islands), area=np.float32(pf.navigable_area()),
         island_radius=np.array([pf.island_radius(i) for i in range(pf.num_islands)], np.float32),
         island_area=np.array([pf.navigable_area(i) for i in range(pf.num_islands)], np.float32))
