@@ -62,6 +62,8 @@ SYMBOLS = [
     "hbn_random_points_dev", "hbn_uniform", "hbn_snap_point", "hbn_is_navigable",
     "hbn_find_path", "hbn_find_path_multigoal", "hbn_try_step", "hbn_closest_obstacle",
     "hbn_random_points", "hbn_random_points_near_dev", "hbn_random_points_near", "hbn_std_sort_order",
+    "hbn_navmesh_set_settings", "hbn_navmesh_save_mset", "hbn_navmesh_set_option", "hbn_navmesh_reserve",
+    "hbn_navmesh_scratch_bytes", "hbn_env_step_dev", "hbn_env_step",
 ]
 
 
@@ -86,14 +88,23 @@ def lib():
         l.hbn_navmesh_triangles.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]
         l.hbn_navmesh_create_from_mset.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]
         l.hbn_navmesh_create_from_tiles.argtypes = [C.POINTER(TileBlob), C.c_int, f32p, C.c_int, C.c_int,
-                                                    C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+                                                    C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                                    C.POINTER(C.c_void_p)]
         l.hbn_navmesh_destroy.argtypes = [C.c_void_p]
         l.hbn_navmesh_destroy.restype = None
         l.hbn_navmesh_get_info.argtypes = [C.c_void_p, C.POINTER(NavMeshInfo)]
         l.hbn_navmesh_island_info.argtypes = [C.c_void_p, C.c_int, f32p, f32p]
         l.hbn_navmesh_get_settings.argtypes = [C.c_void_p, C.c_void_p]
+        l.hbn_navmesh_set_settings.argtypes = [C.c_void_p, C.c_void_p]
+        l.hbn_navmesh_save_mset.restype = C.c_int64
+        l.hbn_navmesh_save_mset.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        l.hbn_navmesh_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
+        l.hbn_navmesh_reserve.argtypes = [C.c_void_p, C.c_int64]
+        l.hbn_navmesh_scratch_bytes.restype = C.c_int64
+        l.hbn_navmesh_scratch_bytes.argtypes = [C.c_void_p]
         vp = C.c_void_p
         for suffix, extra in (("_dev", [vp]), ("", [])):
+            getattr(l, "hbn_env_step" + suffix).argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int, vp, vp] + extra
             getattr(l, "hbn_snap_point" + suffix).argtypes = [vp, vp, vp, C.c_int64, vp, vp, vp] + extra
             getattr(l, "hbn_is_navigable" + suffix).argtypes = [vp, vp, C.c_int64, C.c_float, vp] + extra
             getattr(l, "hbn_find_path" + suffix).argtypes = [vp, vp, vp, C.c_int64, vp, vp, vp, C.c_int,

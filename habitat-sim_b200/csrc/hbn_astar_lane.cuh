@@ -2,12 +2,12 @@
 // machine is hbn_astar_lane.h).  Persistent one-warp blocks pull queries from the search list
 // of k_fp_classify with a warp-aggregated atomic; a lane whose query ends takes the next one
 // in the same iteration, so the lanes of a warp stay busy until the list is empty.
-// Outputs are the ones of k_astar_g: status word and corridor ring (the heap continues in HBM,
-// so no query overflows to another tier); the funnel runs in k_fp_funnel.
+// Outputs: status word and corridor ring per query (the heap continues in HBM, so no query
+// overflows to another tier); the funnel runs in k_fp_funnel.
 #pragma once
 #include <cuda_runtime.h>
 
-#include "hbn_astar_group.cuh"  // AStarGArgs, kSearchOverflow
+#include "hbn_findpath.cuh"  // SearchArgs
 #include "hbn_astar_lane.h"
 
 namespace hbn {
@@ -26,7 +26,7 @@ __host__ __device__ constexpr size_t laneSharedBytes() { return static_cast<size
 // TS: heap entries per lane in shared memory; MINB: resident one-warp blocks per SM the
 // register allocation must allow; CH: links per load stage; V: heap code variant (LaneSearch).
 template <int TS, int CH, int V>
-__device__ __forceinline__ void astarLaneBody(const NavView& nav, const AStarGArgs& a, const LaneScratch& sc) {
+__device__ __forceinline__ void astarLaneBody(const NavView& nav, const SearchArgs& a, const LaneScratch& sc) {
   constexpr uint32_t FULL = 0xffffffffu;
   extern __shared__ __align__(16) char smem[];
   const int lane = threadIdx.x;
@@ -108,14 +108,14 @@ __device__ __forceinline__ void astarLaneBody(const NavView& nav, const AStarGAr
 }
 
 template <int TS, int MINB, int CH, int V = 1>
-__global__ void __launch_bounds__(32, MINB) k_astar_lane(NavView nav, AStarGArgs a, LaneScratch sc) {
+__global__ void __launch_bounds__(32, MINB) k_astar_lane(NavView nav, SearchArgs a, LaneScratch sc) {
   astarLaneBody<TS, CH, V>(nav, a, sc);
 }
 
 // The same with the register budget given directly: ptxas turns "MINB one-warp blocks" into 96
 // registers for 17-20 blocks and 80 for 21-25, although 18 blocks would allow 112 and 19 blocks 104.
 template <int TS, int REGS, int CH, int V = 1>
-__global__ void __maxnreg__(REGS) k_astar_lane_r(NavView nav, AStarGArgs a, LaneScratch sc) {
+__global__ void __maxnreg__(REGS) k_astar_lane_r(NavView nav, SearchArgs a, LaneScratch sc) {
   astarLaneBody<TS, CH, V>(nav, a, sc);
 }
 

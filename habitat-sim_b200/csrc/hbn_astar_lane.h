@@ -114,8 +114,20 @@ HBN_HD size_t laneScratchBytes(uint32_t numKeys) {
 enum { kLIdle = 0, kLSearch = 1, kLExtract = 2, kLDone = 3 };
 enum { kLEvNone = 0, kLEvFinished = 1, kLEvFault = 3, kLEvPoolExhausted = 4 /* internal */ };
 
+// KEEP: the link records are the read-only, L2-sized part of the working set (a few MB against GBs of
+// per-query search state streaming through L2): one 32 B load, evict_last in L1 and L2 (device only).
+template <bool KEEP = false>
 HBN_HD void laneLoadLink(const LinkRec* p, LaneLinkLo& lo, LaneLinkHi& hi) {
 #if defined(__CUDA_ARCH__)
+  if constexpr (KEEP) {
+    uint32_t w[8];
+    asm volatile("ld.global.nc.L1::evict_last.L2::evict_last.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                 : "l"(p));
+    lo.mx = __uint_as_float(w[0]); lo.my = __uint_as_float(w[1]); lo.mz = __uint_as_float(w[2]); lo.nei = w[3];
+    hi.neiLinkStart = w[4]; hi.meta = w[5]; hi.neiRef = w[6]; hi.neiKey = w[7];
+    return;
+  }
   const float4 a = __ldg(reinterpret_cast<const float4*>(p));
   const uint4 b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
   lo.mx = a.x; lo.my = a.y; lo.mz = a.z; lo.nei = __float_as_uint(a.w);
@@ -149,7 +161,20 @@ struct LaneSearch {
   // V = 6: 1 + the modify scan looks through the shared part of the heap before the HBM part
   static constexpr bool kScanSharedFirst = V == 6;
   // V = 7: 1 + node-table loads and stores carry an L2 evict_last policy
-  static constexpr bool kTabEvictLast = V == 7;
+  static constexpr bool kTabEvictLast = V == 7 || V >= 10;
+  // V >= 8: L2 residency by kind of data (profiles/r2_summary.md: with every access at normal priority
+  // the 126 MB L2 keeps nothing from one step to the next; 60 % of the read sectors go to DRAM).  Node
+  // records are write-once / read-once-much-later: 32 B accesses, no L1 allocation, L2 evict_first.
+  // Link records (read-only, a few MB, read by every search): evict_last.
+  static constexpr bool kRecStream = V >= 8;
+  static constexpr bool kLinkKeep = V >= 8;
+  // V >= 9: no closed flag.  The flag only matters when a better path to an allocated node turns up
+  // (DQ.cpp:1124-1153: open -> modify, closed -> push again); the modify scan that looks for the node in
+  // the heap answers that, so the store of the flag at every pop (a DRAM write-back) is dropped.
+  static constexpr bool kNoClosedStore = V >= 9;
+  // V >= 11: the heap entries beyond the shared levels (a few hundred bytes per search, touched at
+  // nearly every pop and push) are kept in L2 with evict_last as well
+  static constexpr bool kHeapKeep = V >= 11;
   static_assert((TS & 1) == 1, "TS must be odd");
   // memory of this lane
   float* K;        // shared: heap keys
@@ -202,23 +227,126 @@ struct LaneSearch {
   }
   HBN_HD LaneRecA* recA(uint32_t s) const { return reinterpret_cast<LaneRecA*>(rec + static_cast<size_t>(s) * 32); }
   HBN_HD LaneRecB* recB(uint32_t s) const { return reinterpret_cast<LaneRecB*>(rec + static_cast<size_t>(s) * 32 + 16); }
+  HBN_HD void loadRec(const uint32_t s, LaneRecA& a, LaneRecB& b) const {
+#if defined(__CUDA_ARCH__)
+    if constexpr (kRecStream) {
+      uint32_t w[8];
+      asm volatile("ld.global.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                   : "l"(rec + static_cast<size_t>(s) * 32)
+                   : "memory");
+      a = LaneRecA{__uint_as_float(w[0]), __uint_as_float(w[1]), __uint_as_float(w[2]), __uint_as_float(w[3])};
+      b = LaneRecB{w[4], w[5], w[6], w[7]};
+      return;
+    }
+#endif
+    a = *recA(s);
+    b = *recB(s);
+  }
+  HBN_HD void storeRec(const uint32_t s, const LaneRecA& a, const LaneRecB& b) const {
+#if defined(__CUDA_ARCH__)
+    if constexpr (kRecStream) {
+      asm volatile("st.global.L1::no_allocate.L2::evict_first.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(
+                       rec + static_cast<size_t>(s) * 32),
+                   "r"(__float_as_uint(a.px)), "r"(__float_as_uint(a.py)), "r"(__float_as_uint(a.pz)),
+                   "r"(__float_as_uint(a.cost)), "r"(b.poly), "r"(b.w1), "r"(b.lnk), "r"(b.w3)
+                   : "memory");
+      return;
+    }
+#endif
+    *recA(s) = a;
+    *recB(s) = b;
+  }
+  HBN_HD LaneRecA loadRecA(const uint32_t s) const {  // what a revisit reads
+#if defined(__CUDA_ARCH__)
+    if constexpr (kRecStream) {
+      unsigned long long pol;
+      LaneRecA a;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+      asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                   : "=f"(a.px), "=f"(a.py), "=f"(a.pz), "=f"(a.cost)
+                   : "l"(rec + static_cast<size_t>(s) * 32), "l"(pol)
+                   : "memory");
+      return a;
+    }
+#endif
+    return *recA(s);
+  }
+  HBN_HD LaneRecB loadRecB(const uint32_t s) const {  // corridor extraction
+#if defined(__CUDA_ARCH__)
+    if constexpr (kRecStream) {
+      unsigned long long pol;
+      LaneRecB b;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+      asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                   : "=r"(b.poly), "=r"(b.w1), "=r"(b.lnk), "=r"(b.w3)
+                   : "l"(rec + static_cast<size_t>(s) * 32 + 16), "l"(pol)
+                   : "memory");
+      return b;
+    }
+#endif
+    return *recB(s);
+  }
+  HBN_HD void storeClosed(const uint32_t s, const float cost) const {  // the flag of DQ.cpp:1037-1038
+    if constexpr (kNoClosedStore) return;
+#if defined(__CUDA_ARCH__)
+    if constexpr (kRecStream) {
+      unsigned long long pol;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+      asm volatile("st.global.L1::no_allocate.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(&recA(s)->cost),
+                   "f"(laneSetClosed(cost)), "l"(pol)
+                   : "memory");
+      return;
+    }
+#endif
+    recA(s)->cost = laneSetClosed(cost);
+  }
 
   HBN_HD void hget(int i, float& k, uint32_t& s) const {
     if (i < TS) {
       k = K[i * HS];
       s = S[i * HS];
     } else {
-      const LaneHeapEnt e = G[i - TS];
+      const LaneHeapEnt e = gLoad(&G[i - TS]);
       k = e.key;
       s = e.slot;
     }
+  }
+  // global part of the heap, optionally with an L2 evict_last policy (device only; same values)
+  static HBN_HD LaneHeapEnt gLoad(const LaneHeapEnt* p) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (kHeapKeep) {
+      unsigned long long pol;
+      LaneHeapEnt e;
+      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+      asm volatile("ld.global.L2::cache_hint.v2.b32 {%0,%1}, [%2], %3;"
+                   : "=r"(*reinterpret_cast<uint32_t*>(&e.key)), "=r"(e.slot)
+                   : "l"(p), "l"(pol)
+                   : "memory");
+      return e;
+    }
+#endif
+    return *p;
+  }
+  static HBN_HD void gStore(LaneHeapEnt* p, const float k, const uint32_t s) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (kHeapKeep) {
+      unsigned long long pol;
+      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+      asm volatile("st.global.L2::cache_hint.v2.b32 [%0], {%1,%2}, %3;" ::"l"(p), "r"(__float_as_uint(k)), "r"(s),
+                   "l"(pol)
+                   : "memory");
+      return;
+    }
+#endif
+    *p = LaneHeapEnt{k, s};
   }
   HBN_HD void hset(int i, float k, uint32_t s) const {
     if (i < TS) {
       K[i * HS] = k;
       S[i * HS] = static_cast<uint16_t>(s);
     } else {
-      G[i - TS] = LaneHeapEnt{k, s};
+      gStore(&G[i - TS], k, s);
     }
   }
   static HBN_HD bool warpAny(bool p) {
@@ -325,7 +453,22 @@ struct LaneSearch {
     }
     hset(i, key, slot);
   }
-  static HBN_HD LaneHeapPair loadPair(const LaneHeapEnt* p) { return *reinterpret_cast<const LaneHeapPair*>(p); }
+  static HBN_HD LaneHeapPair loadPair(const LaneHeapEnt* p) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (kHeapKeep) {
+      unsigned long long pol;
+      LaneHeapPair r;
+      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+      asm volatile("ld.global.L2::cache_hint.v4.b32 {%0,%1,%2,%3}, [%4], %5;"
+                   : "=r"(*reinterpret_cast<uint32_t*>(&r.a.key)), "=r"(r.a.slot),
+                     "=r"(*reinterpret_cast<uint32_t*>(&r.b.key)), "=r"(r.b.slot)
+                   : "l"(p), "l"(pol)
+                   : "memory");
+      return r;
+    }
+#endif
+    return *reinterpret_cast<const LaneHeapPair*>(p);
+  }
   // dtNodeQueue::pop's trickleDown (DNode.cpp:169-184) for a heap that has `n` entries left
   HBN_HD void heapPopSift(const int n) const {
     float lk;
@@ -408,7 +551,7 @@ struct LaneSearch {
         s0 = S[child * HS];
         s1 = S[(child + 1) * HS];
       } else {
-        const LaneHeapPair p = *reinterpret_cast<const LaneHeapPair*>(&G[child - TS]);
+        const LaneHeapPair p = loadPair(&G[child - TS]);
         c0 = p.a.key; s0 = p.a.slot;
         c1 = p.b.key; s1 = p.b.slot;
       }
@@ -435,8 +578,7 @@ struct LaneSearch {
     const PolyRec* spoly = &nav.polys[startG];
     const uint32_t slnk = spoly->linkStart | (static_cast<uint32_t>(spoly->linkCount) << 27);
     const float stotal = vdist(sp, ep) * kHScale;
-    *recA(0) = LaneRecA{sp[0], sp[1], sp[2], 0.f};
-    *recB(0) = LaneRecB{startG, kLaneNoParent, slnk, 0u};
+    storeRec(0, LaneRecA{sp[0], sp[1], sp[2], 0.f}, LaneRecB{startG, kLaneNoParent, slnk, 0u});
     tabStore(spoly->key0, gen << kLaneSlotBits);
     hset(0, stotal, 0u);
     size = 1;
@@ -460,7 +602,7 @@ struct LaneSearch {
     if (status == kDtSuccess || allCorridors) {
       mode = kLExtract;
       xcur = lastBest;
-      xB = *recB(lastBest);
+      xB = loadRecB(lastBest);
       return kLEvNone;
     }
     mode = kLIdle;
@@ -477,7 +619,7 @@ struct LaneSearch {
     const uint32_t nei = lo.nei;
     if ((hi.meta & kLinkDupBit) != 0) {  // an earlier link of this poly may just have created the node
       te = tabLoad(hi.neiKey);
-      if ((te >> kLaneSlotBits) == gen) ra = *recA(te & kLaneSlotMask);
+      if ((te >> kLaneSlotBits) == gen) ra = loadRecA(te & kLaneSlotMask);
     }
     const bool found = (te >> kLaneSlotBits) == gen;
     uint32_t slot;
@@ -509,10 +651,12 @@ struct LaneSearch {
     // DQ.cpp:1124-1130: an allocated node is open or closed, and its total was formed as its
     // cost + the same heuristic
     if (found && total >= laneCost(ra.cost) + heuristic) return kOpNone;
-    const bool wasOpen = found && !laneIsClosed(ra.cost);
-    *recA(slot) = LaneRecA{npos[0], npos[1], npos[2], cost};
-    *recB(slot) = LaneRecB{nei, bestG | (viaJ << 24), hi.neiLinkStart | ((hi.meta >> kLinkNeiCountShift) << 27),
-                           bslot | (1u << 12)};
+    // without the closed flag every improved node is looked for in the heap; the replay pushes it
+    // when it is not there (it was closed)
+    const bool wasOpen = found && (kNoClosedStore || !laneIsClosed(ra.cost));
+    storeRec(slot, LaneRecA{npos[0], npos[1], npos[2], cost},
+             LaneRecB{nei, bestG | (viaJ << 24), hi.neiLinkStart | ((hi.meta >> kLinkNeiCountShift) << 27),
+                      bslot | (1u << 12)});
     if (!found) tabStore(hi.neiKey, (gen << kLaneSlotBits) | slot);
     if (heuristic < lastBestCost) {  // DQ.cpp:1154-1159
       lastBestCost = heuristic;
@@ -545,7 +689,7 @@ struct LaneSearch {
         uint32_t via = kNoPoly;
         if (hasParent) {
           const uint32_t ps = xB.w3 & 0xfffu;
-          const LaneRecB pb = *recB(ps);
+          const LaneRecB pb = loadRecB(ps);
           via = (pb.lnk & 0x07ffffffu) + ((xB.w1 >> 24) & 31u);
           xB = pb;
           xcur = ps;
@@ -567,8 +711,9 @@ struct LaneSearch {
       } else {
         // ---- pop (DQ.cpp:1027-1040) ------------------------------------------------------
         bslot = S[0];
-        const LaneRecA ba = *recA(bslot);
-        const LaneRecB bb = *recB(bslot);
+        LaneRecA ba;
+        LaneRecB bb;
+        loadRec(bslot, ba, bb);
         size--;
 #if defined(__CUDA_ARCH__)
         {  // the popped poly's link records are needed right after the sift: start them towards L1 now
@@ -592,7 +737,7 @@ struct LaneSearch {
         }
 #endif
         heapPopSift(size);
-        recA(bslot)->cost = laneSetClosed(ba.cost);
+        storeClosed(bslot, ba.cost);
 #if defined(__CUDA_ARCH__)
         // The next pop takes the new top unless one of this poly's neighbours (whose records are
         // written below, so they are in L2) overtakes it: pull its record into L2 meanwhile.
@@ -644,7 +789,7 @@ struct LaneSearch {
         lo[k].nei = kNoPoly;
         lo[k].mx = lo[k].my = lo[k].mz = 0.f;
         hi[k] = LaneLinkHi{0u, 0u, 0u, 0u};
-        if (act && base + k < ln) laneLoadLink(&nav.links[l0 + base + k], lo[k], hi[k]);
+        if (act && base + k < ln) laneLoadLink<kLinkKeep>(&nav.links[l0 + base + k], lo[k], hi[k]);
       }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -659,7 +804,7 @@ struct LaneSearch {
 #endif
       for (int k = 0; k < kLaneChunk; ++k) {
         ra[k] = LaneRecA{0.f, 0.f, 0.f, 0.f};
-        if (cand[k] && (te[k] >> kLaneSlotBits) == gen) ra[k] = *recA(te[k] & kLaneSlotMask);
+        if (cand[k] && (te[k] >> kLaneSlotBits) == gen) ra[k] = loadRecA(te[k] & kLaneSlotMask);
       }
       // cost tests and record updates; the heap operations are queued in link order
       float qKey[kLaneChunk];
@@ -728,11 +873,11 @@ struct LaneSearch {
           continue;
         }
         if (mine) {
-          if (isModify) {
+          if (isModify && (hp >= 0 || !kNoClosedStore)) {
             if (hp < 0) stop = kLEvFault;  // an open node that is not in the heap would be a bug
             else heapUp(hp, qKey[j], slot);
             pkValid = false;
-          } else {
+          } else {  // push (with kNoClosedStore also: the improved node was closed, DQ.cpp:1147-1152)
             // bubbleUp's first comparison against the prefetched parent key: valid as long as
             // no earlier operation of this expansion has moved an entry
             if (pkValid && pushed < 2 && !((pushed == 0 ? pk0 : pk1) > qKey[j])) {

@@ -1,6 +1,7 @@
 // C ABI of libhbn.so (include/hbn.h): navmesh upload, kernel orchestration, host-buffer
 // wrappers.  No CPU query path exists in this library.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -11,7 +12,7 @@
 #include "../../include/hbn.h"
 #include "hbn_host.h"
 #include "hbn_kernels.cuh"
-#include "hbn_astar_group.cuh"
+#include "hbn_findpath.cuh"
 #include "hbn_astar_lane.cuh"
 #include "hbn_snap.cuh"
 #include <cub/device/device_scan.cuh>
@@ -36,28 +37,34 @@ int fail(int code, const std::string& msg) {
 constexpr int kCapL = 2048;   // reference pool size: heap+hash shared, nodes in L2
 constexpr int kWallCapS = 128;
 constexpr int kFpWarps = 4;   // warps per block of the wall-distance kernels
-// find_path (hbn_astar_warp.cuh): open-list capacity of the two tiers, warps per block
-constexpr int kOpenS = 256;
-constexpr int kOpenL = 2048;
-constexpr int kFpWpb = 1;
 // per chunk of a find_path call: 16 counters, then the class histogram and the scatter cursors (k_fp_classify)
 constexpr size_t kFpCounterBytes = (16 + 2 * 32) * 4;
 constexpr int kLaneTS = 63;    // lane-per-query search: heap entries per lane kept in shared memory (6 levels)
 constexpr int kLaneMinB = 16;  // ... and resident warps per SM its register budget must allow
+constexpr int kLaneV = 10;     // ... and its code variant: L2 residency by kind of data, no closed flag (hbn_astar_lane.h)
 constexpr int kSnapW = 8;     // lanes per point in k_snap
 constexpr int kRandW = 8;
 
+// Scratch buffer that grows on demand.  Growing frees and allocates (a device-wide implicit
+// synchronisation, illegal during stream capture): hbn_navmesh_reserve sizes every buffer up front so
+// that the *_dev entry points only enqueue.  `epoch` counts reallocations of any buffer of the process
+// (cached CUDA graphs bake the pointers in and are rebuilt when it moves).
+uint64_t g_scratchEpoch = 0;
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
-  int ensure(size_t bytes) {
+  int ensure(size_t bytes, bool slack = true) {
     if (bytes <= cap) return HBN_OK;
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
-    size_t want = bytes + bytes / 4 + 256;
+    g_scratchEpoch++;
+    const size_t want = slack ? bytes + bytes / 4 + 256 : bytes;
     cudaError_t e = cudaMalloc(&p, want);
-    if (e != cudaSuccess) return fail(HBN_ERR_CUDA, std::string("cudaMalloc scratch: ") + cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(HBN_ERR_CUDA, std::string("cudaMalloc scratch: ") + cudaGetErrorString(e));
+    }
     cap = want;
     return HBN_OK;
   }
@@ -65,47 +72,88 @@ struct DevBuf {
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
+    g_scratchEpoch++;
   }
+};
+
+// Tuning knobs of a handle.  Defaults come from the environment ONCE, at creation (HBN_LANE_CFG,
+// HBN_LANE_SPREAD, HBN_SNAP_SPREAD, HBN_SNAP_DUAL, HBN_SNAP_GROUP, HBN_SNAP_CAP, HBN_FP_BLOCKS_PER_SM,
+// HBN_LANE_SCRATCH_MB); hbn_navmesh_set_option changes them afterwards.  Nothing on a query path reads
+// the environment.
+struct Options {
+  int laneCfg = 0;          // k_astar_lane instantiation (0 = shipped)
+  int laneSpread = 1;       // batches smaller than the grid use fewer lanes per warp
+  int snapSpread = 1;       // small snap batches: one lane group per warp
+  int snapDual = 1;         // independent small snap batches share a launch
+  int snapGroup = 0;        // testing: the lane-group snap kernel for every batch size
+  int64_t snapCap = 0;      // testing: candidate scratch entries of the snap pipeline (0 = default)
+  int blocksPerSm = 0;      // cap on resident one-warp blocks per SM of the search (0 = occupancy)
+  int64_t laneScratchBytes = 0;  // cap on the per-lane search state in HBM (0 = half of the free memory)
+  int nvtx = 1;             // NVTX range around every batched call
+};
+
+struct NvtxRange {
+  bool on;
+  NvtxRange(bool enable, const char* name) : on(enable) { if (on) nvtxRangePushA(name); }
+  ~NvtxRange() { if (on) nvtxRangePop(); }
 };
 
 }  // namespace
 
 struct hbn_navmesh {
   int device = 0;
+  HostNavMesh host;  // the tiles as ingested + finished (kept for hbn_navmesh_save_mset)
   FlatNav flat;
   NavView view{};
+  Options opt;
   std::vector<void*> devArrays;
   int64_t deviceBytes = 0;
   cudaStream_t stream = nullptr;  // for the host-buffer entry points
   int smCount = 0;
   int64_t launches = 0;
   std::recursive_mutex mu;
+  // All scratch belongs to the handle, so calls on different streams must not overlap: every *_dev
+  // entry point makes its stream wait for the event the previous call recorded on ITS stream (a no-op
+  // for the same stream) and records a new one when it has enqueued its work.
+  cudaEvent_t lastDone = nullptr;
+  cudaStream_t lastStream = nullptr;
+  bool lastValid = false;
   // scratch (device)
-  DevBuf sG, eG, e2G, sPt, ePt, epPt, lastPoly, lists, counters, wsL, wsFp, io, work, mgDist, mgBounds, mgOrder, mgEnd, mgMask;
-  // lock-step find_path (hbn_astar_group.cuh): class, search list, status, corridor rings, node records
-  DevBuf fpCls, fpBucket, fpWork, fpStat, fpLen, fpCorr, wsFpG;
-  int fpG = 1;          // lanes per query of k_astar_g; 0 = one query per warp (k_findpath_w tiers only);
-                        // 1 = one query per LANE (k_astar_lane, hbn_astar_lane.cuh)
-  int blocksFpG = 0;
-  // lane-per-query search: per-lane node table + records in HBM, allocated on first use
+  DevBuf sG, eG, e2G, sPt, ePt, epPt, e2Pt, lastPoly, lists, counters, wsL, io, work, mgDist, mgBounds, mgOrder, mgEnd, mgMask;
+  DevBuf envG, envPt, envFlag, envPos;  // env step: find_path's start projection, fix-up flags, the goals' polys
+  // find_path pipeline: class, cost class, search list, status, corridor rings
+  DevBuf fpCls, fpBucket, fpWork, fpStat, fpLen, fpCorr;
   DevBuf snapCnt, snapOff, snapG, snapQ, snapD, snapOut, snapBest, snapTmp, snapTodo;  // candidate-list snap (hbn_snap.cuh)
+  // lane-per-query search: per-lane node table + records + heap tail in HBM, sized from the batch
   DevBuf wsLane, laneGen;
-  int blocksFpLane = 0;
-  int laneCfg = 0;      // HBN_LANE_CFG: shared heap levels / warps per SM variant (tuning)
-  bool laneSpread = true;   // batches smaller than the grid use fewer lanes per warp (HBN_LANE_SPREAD=0: always 32)
+  int64_t laneSlots = 0;    // lane slots the scratch holds (tables zeroed, generations 0 when allocated)
+  int blocksFpLane = 0;     // resident one-warp blocks of the search kernel (occupancy x SMs)
   // pinned staging for the host-buffer entry points
   void* pinned = nullptr;
   size_t pinnedCap = 0;
-  int blocksFpS = 0, blocksFpL = 0, blocksWallS = 0, blocksWallL = 0;
-  // optional phase timing of hbn_find_path_dev (hbn_navmesh_set_profiling)
+  int blocksWallS = 0, blocksWallL = 0;
   unsigned int* faultHost = nullptr;  // mapped pinned memory the kernels report bugs through
   unsigned int* faultDev = nullptr;
+  // optional phase timing of hbn_find_path_dev (hbn_navmesh_set_profiling)
   bool profile = false;
   struct PhaseEv { cudaEvent_t e[3]; };
   std::vector<PhaseEv> phaseEvents;
+  // cached CUDA graphs of the host-buffer env step, keyed by (n, allow_sliding)
+  struct StepGraph { int64_t n; int sliding; uint64_t epoch; cudaGraphExec_t exec; size_t offs[5]; };
+  std::vector<StepGraph> stepGraphs;
 };
 
 namespace {
+
+struct DeviceGuard {
+  int prev = 0;
+  bool ok;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() { cudaSetDevice(prev); }
+};
 
 template <class T>
 int upload(hbn_navmesh* nm, const std::vector<T>& v, const T** out) {
@@ -119,24 +167,45 @@ int upload(hbn_navmesh* nm, const std::vector<T>& v, const T** out) {
   return HBN_OK;
 }
 
-// Per-lane node tables + records of k_astar_lane: blocksFpLane * 32 slots, allocated (and zeroed:
-// generation 0, empty tables) on first use.  Shrinks the grid when HBM is short.
-int laneScratch(hbn_navmesh* nm, cudaStream_t st, LaneScratch* out) {
+// Per-lane search state of k_astar_lane (node table + node records + heap tail per lane slot) for a
+// grid of `blocks` one-warp blocks.  Sized from what the batch needs, grown on demand (new tables are
+// zeroed, generations reset), capped by Options::laneScratchBytes or half of the free device memory:
+// under the cap the grid shrinks and every lane serves more queries.  On any failure both buffers are
+// released, so a later call starts from a clean state.
+int laneScratch(hbn_navmesh* nm, cudaStream_t st, int* blocks, LaneScratch* out) {
   const size_t tabB = laneTabBytes(nm->view.numKeys);
   const size_t per = laneScratchBytes(nm->view.numKeys);
-  if (!nm->wsLane.p) {
-    size_t freeB = 0, totalB = 0;
-    CK(cudaMemGetInfo(&freeB, &totalB));
-    const size_t maxBlocks = (freeB / 2) / (per * 32);
-    if (maxBlocks < 1) return fail(HBN_ERR_CUDA, "not enough device memory for the find_path node tables");
-    if (static_cast<size_t>(nm->blocksFpLane) > maxBlocks) nm->blocksFpLane = static_cast<int>(maxBlocks);
-    const size_t lanes = static_cast<size_t>(nm->blocksFpLane) * 32;
-    int rc;
-    if ((rc = nm->wsLane.ensure(lanes * per)) || (rc = nm->laneGen.ensure(lanes * 4))) return rc;
-    CK(cudaMemsetAsync(nm->wsLane.p, 0, lanes * tabB, st));  // the tables come first
-    CK(cudaMemsetAsync(nm->laneGen.p, 0, lanes * 4, st));
+  int64_t want = static_cast<int64_t>(*blocks) * 32;
+  if (want > nm->laneSlots) {
+    size_t budget = nm->opt.laneScratchBytes > 0 ? static_cast<size_t>(nm->opt.laneScratchBytes) : 0;
+    if (!budget) {
+      size_t freeB = 0, totalB = 0;
+      CK(cudaMemGetInfo(&freeB, &totalB));
+      budget = (freeB + nm->wsLane.cap) / 2;
+    }
+    const int64_t maxSlots = static_cast<int64_t>(budget / per) / 32 * 32;
+    if (maxSlots < 32) return fail(HBN_ERR_CUDA, "not enough device memory for the find_path search state");
+    if (want > maxSlots) want = maxSlots;
+    if (want > nm->laneSlots) {
+      nm->laneSlots = 0;
+      int rc;
+      if ((rc = nm->wsLane.ensure(static_cast<size_t>(want) * per, false)) ||
+          (rc = nm->laneGen.ensure(static_cast<size_t>(want) * 4, false))) {
+        nm->wsLane.release();
+        nm->laneGen.release();
+        return rc;
+      }
+      if (cudaMemsetAsync(nm->wsLane.p, 0, static_cast<size_t>(want) * tabB, st) != cudaSuccess ||  // the tables come first
+          cudaMemsetAsync(nm->laneGen.p, 0, static_cast<size_t>(want) * 4, st) != cudaSuccess) {
+        nm->wsLane.release();
+        nm->laneGen.release();
+        return fail(HBN_ERR_CUDA, "cudaMemsetAsync(search state)");
+      }
+      nm->laneSlots = want;
+    }
   }
-  const size_t lanes = static_cast<size_t>(nm->blocksFpLane) * 32;
+  if (static_cast<int64_t>(*blocks) * 32 > nm->laneSlots) *blocks = static_cast<int>(nm->laneSlots / 32);
+  const size_t lanes = static_cast<size_t>(nm->laneSlots);
   char* p = static_cast<char*>(nm->wsLane.p);
   out->tab = p;
   out->rec = p + lanes * tabB;
@@ -146,79 +215,68 @@ int laneScratch(hbn_navmesh* nm, cudaStream_t st, LaneScratch* out) {
   return HBN_OK;
 }
 
-// lane-per-query search instantiations (HBN_LANE_CFG; 0 = shipped).  Template arguments: heap
-// entries in shared memory, resident warps per SM (or registers for k_astar_lane_r), links per
-// load stage, code variant V of LaneSearch.  All are bit-exact (tests/test_zz_tuning_variants.py);
-// times of the find_path phase on 200 k C4 queries are in profiles/r1_summary.md.
+// lane-per-query search instantiations (Options::laneCfg; 0 = shipped).  Template arguments: heap
+// entries in shared memory, resident warps per SM, links per load stage, code variant V of LaneSearch.
+// All are bit-exact (tests/test_zz_tuning_variants.py); the measurements that picked the shipped one are in
+// profiles/r2_summary.md (and profiles/r1_summary.md for the variants deleted since).
 const void* laneKernel(int cfg, size_t* shared) {
 #define HBN_LANE_CASE(N, TS, ...) \
   case N: *shared = laneSharedBytes<TS>(); return reinterpret_cast<const void*>(&__VA_ARGS__);
   switch (cfg) {
-    // measured in round 1, none faster than the shipped one
-    HBN_LANE_CASE(1, 63, k_astar_lane<63, 17, 3>)      // 150.5 ms per 1 M (shipped 153.7 in that run)
-    HBN_LANE_CASE(2, 31, k_astar_lane<31, 20, 2>)      // 158.7
-    HBN_LANE_CASE(3, 63, k_astar_lane<63, 18, 2>)      // 169.6
-    HBN_LANE_CASE(4, 31, k_astar_lane<31, 17, 3>)      // 202.0
-    HBN_LANE_CASE(5, 63, k_astar_lane<63, 16, 4, 2>)   // heap code variant 2: 38.97 ms per 200 k (shipped 37.22)
-    HBN_LANE_CASE(6, 31, k_astar_lane<31, 16, 4, 2>)   // 49.92
-    HBN_LANE_CASE(7, 31, k_astar_lane<31, 20, 2, 2>)   // 46.20
-    HBN_LANE_CASE(8, 47, k_astar_lane<47, 20, 3>)      // 38.13 (shipped 37.00 in that run)
-    HBN_LANE_CASE(12, 39, k_astar_lane<39, 24, 2>)     // 46.52
-    HBN_LANE_CASE(13, 63, k_astar_lane<63, 16, 4, 3>)  // node-table prefetch before the sift-down: 37.93
-    HBN_LANE_CASE(15, 63, k_astar_lane<63, 16, 4, 5>)  // + grandchildren prefetch in the sift-down: 37.59
-    HBN_LANE_CASE(16, 47, k_astar_lane<47, 20, 3, 5>)  // 38.92
-    // built and host-tested, not measured yet
-    HBN_LANE_CASE(9, 47, k_astar_lane<47, 20, 2>)
-    HBN_LANE_CASE(10, 55, k_astar_lane<55, 19, 3>)
-    HBN_LANE_CASE(11, 47, k_astar_lane<47, 20, 3, 2>)
-    HBN_LANE_CASE(14, 47, k_astar_lane<47, 20, 3, 3>)
-    // register budgets ptxas does not pick by itself ("17-20 one-warp blocks" become 96 registers):
-    // 112 = 17 warps at 63 entries (12 KB + 1 KB reserved per block), 18 at 59; 104 = 19 warps
-    HBN_LANE_CASE(17, 63, k_astar_lane_r<63, 112, 4>)
-    HBN_LANE_CASE(18, 55, k_astar_lane_r<55, 104, 4>)
-    HBN_LANE_CASE(19, 55, k_astar_lane_r<55, 104, 3>)
-    HBN_LANE_CASE(22, 59, k_astar_lane_r<59, 112, 4>)
-    // modify scan looks through the shared part of the heap first (V = 6)
-    HBN_LANE_CASE(20, 63, k_astar_lane<63, 16, 4, 6>)
-    HBN_LANE_CASE(21, 63, k_astar_lane_r<63, 112, 4, 6>)
-    // node-table accesses with an L2 evict_last policy (V = 7)
-    HBN_LANE_CASE(24, 63, k_astar_lane<63, 16, 4, 7>)
-    // 95 entries (85 % of the pops find the whole open list in shared memory) at 11 warps per SM
-    HBN_LANE_CASE(23, 95, k_astar_lane<95, 11, 4>)
-    default: *shared = laneSharedBytes<kLaneTS>(); return reinterpret_cast<const void*>(&k_astar_lane<kLaneTS, kLaneMinB, 4>);
+    HBN_LANE_CASE(1, 63, k_astar_lane<63, 16, 4, 1>)    // round 1's kernel: every access at normal L2 priority
+    HBN_LANE_CASE(30, 63, k_astar_lane<63, 16, 4, 8>)   // records evict_first (32 B accesses), links evict_last
+    HBN_LANE_CASE(31, 63, k_astar_lane<63, 16, 4, 9>)   // + no closed-flag store
+    HBN_LANE_CASE(35, 63, k_astar_lane<63, 16, 4, 11>)  // + heap tail evict_last (slower)
+    HBN_LANE_CASE(23, 95, k_astar_lane<95, 11, 4, 1>)   // 95 shared heap entries at 11 warps per SM
+    HBN_LANE_CASE(34, 95, k_astar_lane<95, 11, 4, 10>)
+    default: *shared = laneSharedBytes<kLaneTS>(); return reinterpret_cast<const void*>(&k_astar_lane<kLaneTS, kLaneMinB, 4, kLaneV>);
   }
 #undef HBN_LANE_CASE
 }
 
-const void* groupKernel(int g) {
-  switch (g) {
-    case 4: return reinterpret_cast<const void*>(&k_astar_g<4, kOpenS>);
-    case 16: return reinterpret_cast<const void*>(&k_astar_g<16, kOpenS>);
-    case 32: return reinterpret_cast<const void*>(&k_astar_g<32, kOpenS>);
-    default: return reinterpret_cast<const void*>(&k_astar_g<8, kOpenS>);
-  }
+int envInt(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
 }
 
-int finishCreate(HostNavMesh& mesh, const int32_t* islands, int device, hbn_navmesh_t* out) {
+// (re)select the search kernel of Options::laneCfg: shared-memory opt-in, occupancy, grid size
+int laneConfigure(hbn_navmesh* nm) {
+  size_t smLane = 0;
+  const void* fn = laneKernel(nm->opt.laneCfg, &smLane);
+  CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smLane)));
+  CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32, smLane));
+  occ = std::max(1, occ);
+  if (nm->opt.blocksPerSm > 0) occ = std::min(occ, nm->opt.blocksPerSm);
+  nm->blocksFpLane = occ * nm->smCount;
+  return HBN_OK;
+}
+
+int finishCreate(HostNavMesh& meshIn, const int32_t* islands, const float* radii, int numRadii, int device,
+                 hbn_navmesh_t* out) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
     return fail(HBN_ERR_NO_DEVICE, "no CUDA device available (libhbn has no CPU path)");
   if (device < 0 || device >= ndev) return fail(HBN_ERR_INVALID, "bad device index");
-  CK(cudaSetDevice(device));
-  hbn_navmesh* nm = new hbn_navmesh();
+  DeviceGuard devGuard(device);  // the caller's current device is restored on every return path
+  if (!devGuard.ok) return fail(HBN_ERR_CUDA, "cudaSetDevice failed");
+  // every failure below releases the handle and what was uploaded so far
+  struct Cleanup {
+    hbn_navmesh* nm;
+    ~Cleanup() { if (nm) hbn_navmesh_destroy(nm); }
+  } guard{new hbn_navmesh()};
+  hbn_navmesh* nm = guard.nm;
   nm->device = device;
-  mesh.finish(islands);
+  nm->host = std::move(meshIn);
+  HostNavMesh& mesh = nm->host;
+  mesh.finish(islands, radii, numRadii);
   mesh.flatten(nm->flat);
   const FlatNav& f = nm->flat;
-  if (f.polys.size() >= (1u << 24) || f.links.size() >= (1u << 27)) {
-    delete nm;
+  if (f.polys.size() >= (1u << 24) || f.links.size() >= (1u << 27))
     return fail(HBN_ERR_LIMIT, "navmesh exceeds 2^24 polys or 2^27 links");
-  }
   for (const PolyRec& p : f.polys)
-    if (p.linkCount > 31) {
-      delete nm;
-      return fail(HBN_ERR_LIMIT, "a polygon has more than 31 links");
-    }
+    if (p.linkCount > 31) return fail(HBN_ERR_LIMIT, "a polygon has more than 31 links");
   NavView v = f.view();
   int rc = HBN_OK;
   auto up = [&](auto& vec, auto** dst) { if (rc == HBN_OK) rc = upload(nm, vec, dst); };
@@ -237,68 +295,46 @@ int finishCreate(HostNavMesh& mesh, const int32_t* islands, int device, hbn_navm
   up(f.tileIslId, &v.tileIslId);
   up(f.tileIslWin, &v.tileIslWin);
   up(f.tileIslCnt, &v.tileIslCnt);
-  if (rc != HBN_OK) {
-    hbn_navmesh_destroy(nm);
-    return rc;
-  }
+  if (rc != HBN_OK) return rc;
   nm->view = v;
+  if (const char* e = getenv("HBN_L2_FETCH")) {  // experiment: L2 fetch granularity (32 / 64 / 128 B)
+    CK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, static_cast<size_t>(atoi(e))));
+    size_t got = 0;
+    cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+    fprintf(stderr, "[hbn] L2 fetch granularity %zu\n", got);
+  }
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   nm->smCount = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&nm->stream, cudaStreamNonBlocking));
 
+  // knobs: environment defaults, read once
+  nm->opt.laneCfg = envInt("HBN_LANE_CFG", 0);
+  nm->opt.laneSpread = envInt("HBN_LANE_SPREAD", 1);
+  nm->opt.snapSpread = envInt("HBN_SNAP_SPREAD", 1);
+  nm->opt.snapDual = envInt("HBN_SNAP_DUAL", 1);
+  nm->opt.snapGroup = getenv("HBN_SNAP_GROUP") ? 1 : 0;
+  nm->opt.snapCap = envInt("HBN_SNAP_CAP", 0);
+  nm->opt.blocksPerSm = envInt("HBN_FP_BLOCKS_PER_SM", 0);
+  nm->opt.laneScratchBytes = static_cast<int64_t>(envInt("HBN_LANE_SCRATCH_MB", 0)) << 20;
+  nm->opt.nvtx = envInt("HBN_NVTX", 1);
+  CK(cudaEventCreateWithFlags(&nm->lastDone, cudaEventDisableTiming));
+
   // opt in to large dynamic shared memory and size the persistent grids from occupancy
   const int threads = kFpWarps * 32;
   const size_t smL = kFpWarps * wsSharedBytes(kCapL, kWsHybrid);
   const size_t smW = kFpWarps * wsSharedBytes(kWallCapS, kWsShared);
-  const size_t smFpS = kFpWpb * WarpWs<kOpenS>::sharedBytes();
-  const size_t smFpL = kFpWpb * WarpWs<kOpenL>::sharedBytes();
-  CK(cudaFuncSetAttribute(k_findpath_w<kOpenS, kFpWpb>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smFpS)));
-  CK(cudaFuncSetAttribute(k_findpath_w<kOpenL, kFpWpb>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smFpL)));
-  CK(cudaFuncSetAttribute(k_findpath_w<kOpenS, kFpWpb>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   CK(cudaFuncSetAttribute(k_wall<kWallCapS, kWsShared>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smW)));
   CK(cudaFuncSetAttribute(k_wall<kCapL, kWsHybrid>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smL)));
   int occ = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_findpath_w<kOpenS, kFpWpb>, 32 * kFpWpb, smFpS));
-  nm->blocksFpS = std::max(1, occ) * nm->smCount;
-  if (const char* e = getenv("HBN_FP_BLOCKS_PER_SM")) nm->blocksFpS = std::max(1, std::min(occ, atoi(e))) * nm->smCount;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_findpath_w<kOpenL, kFpWpb>, 32 * kFpWpb, smFpL));
-  nm->blocksFpL = std::max(1, occ) * nm->smCount;
-  // lock-step search: group width from HBN_FP_G (4, 8, 16, 32; "warp" = the one-query-per-warp tiers)
-  if (const char* e = getenv("HBN_FP_G"))
-    nm->fpG = (strcmp(e, "warp") == 0) ? 0 : (strcmp(e, "lane") == 0) ? 1 : atoi(e);
-  if (nm->fpG != 0 && nm->fpG != 1 && nm->fpG != 4 && nm->fpG != 8 && nm->fpG != 16 && nm->fpG != 32) nm->fpG = 8;
-  {
-    if (const char* e = getenv("HBN_LANE_CFG")) nm->laneCfg = atoi(e);
-    if (const char* e = getenv("HBN_LANE_SPREAD")) nm->laneSpread = atoi(e) != 0;
-    size_t smLane = 0;
-    const void* fn = laneKernel(nm->laneCfg, &smLane);
-    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smLane)));
-    CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32, smLane));
-    nm->blocksFpLane = std::max(1, occ) * nm->smCount;
-    if (const char* e = getenv("HBN_FP_BLOCKS_PER_SM")) nm->blocksFpLane = std::max(1, std::min(occ, atoi(e))) * nm->smCount;
-  }
-  if (nm->fpG > 1) {
-    const size_t smG = (32 / nm->fpG) * gGroupSharedBytes<kOpenS>();
-    const void* fn = groupKernel(nm->fpG);
-    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smG)));
-    CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32, smG));
-    nm->blocksFpG = std::max(1, occ) * nm->smCount;
-    if (const char* e = getenv("HBN_FP_BLOCKS_PER_SM")) nm->blocksFpG = std::max(1, std::min(occ, atoi(e))) * nm->smCount;
-  }
+  int rcLane = HBN_OK;
+  if ((rcLane = laneConfigure(nm))) return rcLane;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wall<kWallCapS, kWsShared>, threads, smW));
   nm->blocksWallS = std::max(1, occ) * nm->smCount;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wall<kCapL, kWsHybrid>, threads, smL));
   nm->blocksWallL = std::max(1, occ) * nm->smCount;
   // global scratch: one slot per resident warp
   rc = nm->wsL.ensure(static_cast<size_t>(nm->blocksWallL) * kFpWarps * wsGlobalBytes(kCapL, kWsHybrid));
-  if (rc == HBN_OK)
-    rc = nm->wsFp.ensure(static_cast<size_t>(std::max(nm->blocksFpS, nm->blocksFpL)) * kFpWpb *
-                         WarpWs<kOpenS>::globalBytes());
-  if (rc == HBN_OK && nm->fpG > 1)
-    rc = nm->wsFpG.ensure(static_cast<size_t>(nm->blocksFpG) * (32 / nm->fpG) * gGroupGlobalBytes());
   if (rc == HBN_OK) rc = nm->counters.ensure(64);
   if (rc == HBN_OK) rc = nm->work.ensure(64);
   if (rc == HBN_OK) {
@@ -309,10 +345,8 @@ int finishCreate(HostNavMesh& mesh, const int32_t* islands, int device, hbn_navm
       memset(nm->faultHost, 0, 64);
   }
   if (rc == HBN_OK && cudaMemset(nm->work.p, 0, 64) != cudaSuccess) rc = fail(HBN_ERR_CUDA, "cudaMemset");
-  if (rc != HBN_OK) {
-    hbn_navmesh_destroy(nm);
-    return rc;
-  }
+  if (rc != HBN_OK) return rc;
+  guard.nm = nullptr;
   *out = nm;
   return HBN_OK;
 }
@@ -330,36 +364,46 @@ int checkFault(hbn_navmesh* nm) {
   return HBN_OK;
 }
 
-struct DeviceGuard {
-  int prev = 0;
-  bool ok;
-  explicit DeviceGuard(int dev) {
-    cudaGetDevice(&prev);
-    ok = cudaSetDevice(dev) == cudaSuccess;
-  }
-  ~DeviceGuard() { cudaSetDevice(prev); }
-};
-
 constexpr int64_t kSnapChunk = 1 << 18;   // points per pass of the candidate-list pipeline
 constexpr int64_t kSnapSmall = 4096;      // below this one k_snap<8> launch is cheaper than five kernels + a scan
 
-// Two small independent projectToPoly batches in one k_snap_dual launch (HBN_SNAP_DUAL=0: off).
-// Returns false when the pair does not qualify (the caller then launches them one after the
-// other).  1024 C2 points: find_path's snap phase 71 -> 38 us, with spreading 28 us.
-bool snapDualLaunch(hbn_navmesh* nm, const float* ptsA, int64_t nA, float* outPtsA, uint32_t* outGA,
-                    const float* ptsB, int64_t nB, float* outPtsB, uint32_t* outGB, cudaStream_t st, int* rc) {
+// Stream order between calls on one handle (see hbn_navmesh::lastDone).  During a stream capture the
+// caller owns the ordering (an event recorded outside the capture cannot be waited on inside it).
+struct CallOrder {
+  hbn_navmesh* nm;
+  cudaStream_t st;
+  bool capturing = false;
+  CallOrder(hbn_navmesh* n, cudaStream_t s) : nm(n), st(s) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) == cudaSuccess) capturing = cs != cudaStreamCaptureStatusNone;
+    else cudaGetLastError();
+    if (!capturing && nm->lastValid && nm->lastStream != st) cudaStreamWaitEvent(st, nm->lastDone, 0);
+  }
+  ~CallOrder() {
+    if (capturing) return;
+    if (cudaEventRecord(nm->lastDone, st) == cudaSuccess) {
+      nm->lastStream = st;
+      nm->lastValid = true;
+    } else {
+      cudaGetLastError();
+    }
+  }
+};
+
+// Up to three small independent projectToPoly batches in one k_snap_dual launch (Options::snapDual).
+// Returns false when the batches do not qualify (the caller then launches them one after the other).
+// 1024 C2 points: find_path's snap phase 71 -> 38 us, with spreading 28 us.
+bool snapDualLaunch(hbn_navmesh* nm, SnapJob a, SnapJob b, SnapJob c, cudaStream_t st, int* rc) {
   *rc = HBN_OK;
-  const char* e = getenv("HBN_SNAP_DUAL");
-  if ((e && atoi(e) == 0) || nA <= 0 || nB <= 0 || nA >= kSnapSmall || nB >= kSnapSmall || getenv("HBN_SNAP_GROUP"))
+  if (!nm->opt.snapDual || nm->opt.snapGroup || a.n <= 0 || b.n <= 0 || a.n >= kSnapSmall || b.n >= kSnapSmall ||
+      c.n >= kSnapSmall)
     return false;
-  const char* sp = getenv("HBN_SNAP_SPREAD");
-  const bool spread = !sp || atoi(sp) != 0;
-  const int64_t n = nA + nB;
-  const unsigned threads = spread ? kSnapW : 256;
+  const int64_t n = a.n + b.n + std::max<int64_t>(c.n, 0);
+  const unsigned threads = nm->opt.snapSpread ? kSnapW : 256;
   const int64_t gpb = threads / kSnapW;
   const int64_t blocks = (n + gpb - 1) / gpb;
-  k_snap_dual<kSnapW><<<static_cast<unsigned>(blocks), threads, 0, st>>>(nm->view, SnapJob{ptsA, nA, outPtsA, outGA},
-                                                                        SnapJob{ptsB, nB, outPtsB, outGB});
+  if (c.n < 0) c.n = 0;
+  k_snap_dual<kSnapW><<<static_cast<unsigned>(blocks), threads, 0, st>>>(nm->view, a, b, c);
   nm->launches++;
   const cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) *rc = fail(HBN_ERR_CUDA, std::string("k_snap_dual: ") + cudaGetErrorString(ce));
@@ -374,16 +418,14 @@ int snapLaunch(hbn_navmesh* nm, const float* pts, const int32_t* islands, int64_
   if (n <= 0) return HBN_OK;
   const int groupsPerBlock = 256 / kSnapW;
   const int64_t maxBlocks = static_cast<int64_t>(nm->smCount) * 64;
-  const bool forceGroup = getenv("HBN_SNAP_GROUP") != nullptr;  // testing: the lane-group kernel only
+  const bool forceGroup = nm->opt.snapGroup != 0;  // testing: the lane-group kernel only
   if (n < kSnapSmall || forceGroup) {
     int64_t blocks = std::min(maxBlocks, (n + groupsPerBlock - 1) / groupsPerBlock);
     unsigned threads = 256;
     // one lane group per warp (blocks of 8 threads): the groups of a small batch neither share a
     // warp's issue slots nor diverge against each other, and 1024 points cover the SMs instead
     // of 32 blocks (HBN_SNAP_SPREAD=0: blocks of 256 threads)
-    const char* sp = getenv("HBN_SNAP_SPREAD");
-    const bool spread = !sp || atoi(sp) != 0;
-    if (spread && n < kSnapSmall) {
+    if (nm->opt.snapSpread && n < kSnapSmall) {
       threads = kSnapW;
       blocks = n;
     }
@@ -395,7 +437,7 @@ int snapLaunch(hbn_navmesh* nm, const float* pts, const int32_t* islands, int64_
   }
   const int64_t cmax = std::min(n, kSnapChunk);
   size_t cap = static_cast<size_t>(cmax) * kSnapAvgCap;
-  if (const char* e = getenv("HBN_SNAP_CAP")) cap = static_cast<size_t>(std::max(1, atoi(e)));  // testing: force the fallback
+  if (nm->opt.snapCap > 0) cap = static_cast<size_t>(nm->opt.snapCap);  // testing: force the fallback
   size_t tmpBytes = 0;
   CK(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr),
                                    static_cast<int>(cmax + 1), st));
@@ -467,12 +509,12 @@ int hbn_navmesh_create_from_mset(const void* bytes, size_t len, int device, hbn_
   HostNavMesh mesh;
   std::string err;
   if (!mesh.loadMSET(static_cast<const uint8_t*>(bytes), len, err)) return fail(HBN_ERR_FORMAT, err);
-  return finishCreate(mesh, nullptr, device, out);
+  return finishCreate(mesh, nullptr, nullptr, 0, device, out);
 }
 
 int hbn_navmesh_create_from_tiles(const hbn_tile_blob* tiles, int n_tiles, const float* params5,
                                   int max_tiles, int max_polys, const int32_t* poly_islands,
-                                  int device, hbn_navmesh_t* out) {
+                                  const float* island_radii, int n_islands, int device, hbn_navmesh_t* out) {
   if (!tiles || n_tiles <= 0 || !params5 || !out) return fail(HBN_ERR_INVALID, "null argument");
   *out = nullptr;
   HostNavMesh mesh;
@@ -488,21 +530,25 @@ int hbn_navmesh_create_from_tiles(const hbn_tile_blob* tiles, int n_tiles, const
     if (!mesh.addFinalisedTile(static_cast<const uint8_t*>(tiles[i].data), tiles[i].size,
                                tiles[i].tile_ref, err))
       return fail(HBN_ERR_FORMAT, err);
-  return finishCreate(mesh, poly_islands, device, out);
+  return finishCreate(mesh, poly_islands, poly_islands ? island_radii : nullptr, n_islands, device, out);
 }
 
 void hbn_navmesh_destroy(hbn_navmesh_t nm) {
   if (!nm) return;
   DeviceGuard g(nm->device);
   for (void* d : nm->devArrays) cudaFree(d);
-  for (DevBuf* b : {&nm->sG, &nm->eG, &nm->e2G, &nm->sPt, &nm->ePt, &nm->epPt, &nm->lastPoly,
-                    &nm->lists, &nm->counters, &nm->wsL, &nm->wsFp, &nm->io, &nm->work, &nm->mgDist,
-                    &nm->mgBounds, &nm->mgOrder, &nm->mgEnd, &nm->mgMask, &nm->fpCls, &nm->fpWork, &nm->fpStat,
-                    &nm->fpLen, &nm->fpCorr, &nm->fpBucket, &nm->wsFpG, &nm->wsLane, &nm->laneGen, &nm->snapCnt, &nm->snapOff,
+  for (auto& sg : nm->stepGraphs)
+    if (sg.exec) cudaGraphExecDestroy(sg.exec);
+  for (DevBuf* b : {&nm->sG, &nm->eG, &nm->e2G, &nm->sPt, &nm->ePt, &nm->epPt, &nm->e2Pt, &nm->lastPoly,
+                    &nm->lists, &nm->counters, &nm->wsL, &nm->io, &nm->work, &nm->mgDist,
+                    &nm->mgBounds, &nm->mgOrder, &nm->mgEnd, &nm->mgMask, &nm->envG, &nm->envPt, &nm->envFlag, &nm->envPos,
+                    &nm->fpCls, &nm->fpWork, &nm->fpStat,
+                    &nm->fpLen, &nm->fpCorr, &nm->fpBucket, &nm->wsLane, &nm->laneGen, &nm->snapCnt, &nm->snapOff,
                     &nm->snapG, &nm->snapQ, &nm->snapD, &nm->snapOut, &nm->snapBest, &nm->snapTmp, &nm->snapTodo})
     b->release();
   if (nm->pinned) cudaFreeHost(nm->pinned);
   if (nm->faultHost) cudaFreeHost(nm->faultHost);
+  if (nm->lastDone) cudaEventDestroy(nm->lastDone);
   if (nm->stream) cudaStreamDestroy(nm->stream);
   delete nm;
 }
@@ -537,6 +583,98 @@ int hbn_navmesh_island_info(hbn_navmesh_t nm, int island, float* radius, float* 
   if (radius) *radius = nm->flat.islandRadius[island];
   if (area) *area = nm->flat.islandArea[island];
   return HBN_OK;
+}
+
+int hbn_navmesh_set_settings(hbn_navmesh_t nm, const void* in56) {
+  if (!nm || !in56) return fail(HBN_ERR_INVALID, "null argument");
+  std::lock_guard<std::recursive_mutex> lk(nm->mu);
+  nm->host.setSettings(static_cast<const uint8_t*>(in56));
+  memcpy(nm->flat.settings, in56, 56);
+  nm->flat.hasSettings = true;
+  return HBN_OK;
+}
+
+static int envStepReserve(hbn_navmesh* nm, int64_t n);
+
+int hbn_navmesh_set_option(hbn_navmesh_t nm, const char* key, int64_t value) {
+  if (!nm || !key) return fail(HBN_ERR_INVALID, "null argument");
+  DeviceGuard g(nm->device);
+  std::lock_guard<std::recursive_mutex> lk(nm->mu);
+  const std::string k(key);
+  g_scratchEpoch++;  // cached graphs were captured under the old options
+  if (k == "lane_cfg") {
+    nm->opt.laneCfg = static_cast<int>(value);
+    return laneConfigure(nm);
+  } else if (k == "blocks_per_sm") {
+    nm->opt.blocksPerSm = static_cast<int>(value);
+    return laneConfigure(nm);
+  } else if (k == "lane_spread") nm->opt.laneSpread = value != 0;
+  else if (k == "snap_spread") nm->opt.snapSpread = value != 0;
+  else if (k == "snap_dual") nm->opt.snapDual = value != 0;
+  else if (k == "snap_group") nm->opt.snapGroup = value != 0;
+  else if (k == "snap_cap") nm->opt.snapCap = value;
+  else if (k == "nvtx") nm->opt.nvtx = value != 0;
+  else if (k == "lane_scratch_bytes") {
+    // a smaller cap takes effect at once: the search state is released and re-made on the next call
+    nm->opt.laneScratchBytes = value;
+    CK(cudaDeviceSynchronize());
+    nm->wsLane.release();
+    nm->laneGen.release();
+    nm->laneSlots = 0;
+  } else {
+    return fail(HBN_ERR_INVALID, "unknown option: " + k);
+  }
+  return HBN_OK;
+}
+
+int64_t hbn_navmesh_scratch_bytes(hbn_navmesh_t nm) {
+  if (!nm) return -1;
+  std::lock_guard<std::recursive_mutex> lk(nm->mu);
+  int64_t total = 0;
+  for (const DevBuf* b : {&nm->sG, &nm->eG, &nm->e2G, &nm->sPt, &nm->ePt, &nm->epPt, &nm->e2Pt, &nm->lastPoly,
+                          &nm->lists, &nm->counters, &nm->wsL, &nm->io, &nm->work, &nm->mgDist, &nm->mgBounds,
+                          &nm->mgOrder, &nm->mgEnd, &nm->mgMask, &nm->envG, &nm->envPt, &nm->envFlag, &nm->envPos,
+                          &nm->fpCls, &nm->fpWork, &nm->fpStat, &nm->fpLen, &nm->fpCorr, &nm->fpBucket, &nm->wsLane,
+                          &nm->laneGen, &nm->snapCnt, &nm->snapOff, &nm->snapG, &nm->snapQ, &nm->snapD, &nm->snapOut,
+                          &nm->snapBest, &nm->snapTmp, &nm->snapTodo})
+    total += static_cast<int64_t>(b->cap);
+  return total;
+}
+
+int hbn_navmesh_reserve(hbn_navmesh_t nm, int64_t n) {
+  if (!nm || n <= 0) return fail(HBN_ERR_INVALID, "bad argument");
+  if (n >= (1ll << 31)) return fail(HBN_ERR_INVALID, "batch too large");
+  DeviceGuard g(nm->device);
+  std::lock_guard<std::recursive_mutex> lk(nm->mu);
+  int rc;
+  if ((rc = envStepReserve(nm, n)) || (rc = nm->lists.ensure(n * 4))) return rc;
+  if (n >= kSnapSmall) {  // the candidate-list snap pipeline's scratch
+    const int64_t cmax = std::min(n, kSnapChunk);
+    const size_t cap = nm->opt.snapCap > 0 ? static_cast<size_t>(nm->opt.snapCap) : static_cast<size_t>(cmax) * kSnapAvgCap;
+    size_t tmpBytes = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr),
+                                     static_cast<int>(cmax + 1), nm->stream));
+    if ((rc = nm->snapCnt.ensure((cmax + 1) * 4)) || (rc = nm->snapOff.ensure((cmax + 1) * 4)) ||
+        (rc = nm->snapG.ensure(cap * 4)) || (rc = nm->snapQ.ensure(cap * 4)) || (rc = nm->snapD.ensure(cap * 4)) ||
+        (rc = nm->snapOut.ensure(cap * 4)) || (rc = nm->snapBest.ensure(cmax * 8)) || (rc = nm->snapTmp.ensure(tmpBytes)) ||
+        (rc = nm->snapTodo.ensure(16)))
+      return rc;
+  }
+  CK(cudaStreamSynchronize(nm->stream));  // the zeroing of new search state
+  return HBN_OK;
+}
+
+int64_t hbn_navmesh_save_mset(hbn_navmesh_t nm, void* out, int64_t cap) {
+  if (!nm) return -1;
+  std::lock_guard<std::recursive_mutex> lk(nm->mu);
+  std::vector<uint8_t> image;
+  std::string err;
+  if (!nm->host.saveMSET(image, err)) {
+    fail(HBN_ERR_FORMAT, err);
+    return -1;
+  }
+  if (out && cap >= static_cast<int64_t>(image.size())) memcpy(out, image.data(), image.size());
+  return static_cast<int64_t>(image.size());
 }
 
 int hbn_navmesh_get_settings(hbn_navmesh_t nm, void* out56) {
@@ -578,11 +716,6 @@ int hbn_navmesh_work_counters(hbn_navmesh_t nm, uint64_t* out8, int reset) {
   if (!nm || !out8) return fail(HBN_ERR_INVALID, "null argument");
   DeviceGuard g(nm->device);
   CK(cudaDeviceSynchronize());
-  if (getenv("HBN_DEBUG_SLOW") && nm->faultHost) {
-    fprintf(stderr, "[hbn] slowest find_path query: %u kcycles, q=%u, expansions=%u, tier OC=%u\n",
-            nm->faultHost[4], nm->faultHost[5], nm->faultHost[6], nm->faultHost[7]);
-    nm->faultHost[4] = 0;
-  }
   CK(cudaMemcpy(out8, nm->work.p, 64, cudaMemcpyDeviceToHost));
   if (reset) CK(cudaMemset(nm->work.p, 0, 64));
   return checkFault(nm);
@@ -592,9 +725,9 @@ int64_t hbn_navmesh_triangles(hbn_navmesh_t nm, int island, float* out, int64_t 
   if (!nm) return -1;
   const FlatNav& f = nm->flat;
   int64_t n = 0;
+  // getNavMeshData (PF.cpp:1898-1944): the detail triangles of EVERY poly of the island (all polys for
+  // island -1) in tile-table, poly order -- disabled zero-area polys and non-walkable ones included
   for (const PolyRec& p : f.polys) {
-    if ((p.areaType >> 6) == 1) continue;
-    if ((p.flags & kFlagWalk) == 0) continue;
     if (island >= 0 && p.island != island) continue;
     for (int j = 0; j < p.detTriCount; ++j) {
       const uint8_t* t = &f.detTris[static_cast<size_t>(p.detTriBase + j) * 4];
@@ -615,6 +748,9 @@ int hbn_snap_point_dev(hbn_navmesh_t nm, const float* pts, const int32_t* island
                        float* out_pts, uint32_t* out_refs, int32_t* out_islands, void* stream) {
   if (!nm || (n > 0 && !pts)) return fail(HBN_ERR_INVALID, "null argument");
   DeviceGuard g(nm->device);
+  std::lock_guard<std::recursive_mutex> lk(nm->mu);
+  NvtxRange nv(nm->opt.nvtx, "hbn_snap_point");
+  CallOrder order(nm, static_cast<cudaStream_t>(stream));
   return snapLaunch(nm, pts, islands, n, out_pts, nullptr, out_refs, out_islands, nullptr, 0.f,
                     static_cast<cudaStream_t>(stream));
 }
@@ -623,79 +759,85 @@ int hbn_is_navigable_dev(hbn_navmesh_t nm, const float* pts, int64_t n, float ma
                          uint8_t* out, void* stream) {
   if (!nm || (n > 0 && (!pts || !out))) return fail(HBN_ERR_INVALID, "null argument");
   DeviceGuard g(nm->device);
+  std::lock_guard<std::recursive_mutex> lk(nm->mu);
+  NvtxRange nv(nm->opt.nvtx, "hbn_is_navigable");
+  CallOrder order(nm, static_cast<cudaStream_t>(stream));
   return snapLaunch(nm, pts, nullptr, n, nullptr, nullptr, nullptr, nullptr, out, max_y_delta,
                     static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"
 
-// one-query-per-warp tiers (hbn_astar_warp.cuh) over `work` (nullptr: all n queries): search +
-// funnel + outputs in one kernel.  cnt: 4 zeroed counters.
-static int warpTierLaunch(hbn_navmesh_t nm, FindPathArgs a, bool smallTier, uint32_t* cnt, cudaStream_t st) {
-  a.counter = cnt + 0;
-  a.overflow = static_cast<uint32_t*>(nm->lists.p);
-  a.overflowCount = cnt + 1;
-  a.scratch = static_cast<char*>(nm->wsFp.p);
-  if (smallTier) {
-    int64_t blocks = std::min<int64_t>(nm->blocksFpS, (a.n + kFpWpb - 1) / kFpWpb);
-    k_findpath_w<kOpenS, kFpWpb><<<static_cast<unsigned>(blocks), 32 * kFpWpb,
-                                   kFpWpb * WarpWs<kOpenS>::sharedBytes(), st>>>(nm->view, a);
-    nm->launches++;
-    CK(cudaGetLastError());
-    // large tier over the overflow list (its length stays on the device)
-    a.work = a.overflow;
-    a.workCount = a.overflowCount;
-    a.counter = cnt + 2;
-    a.overflowCount = cnt + 3;  // cannot overflow: open list <= kMaxNodes
-  }
-  k_findpath_w<kOpenL, kFpWpb><<<nm->blocksFpL, 32 * kFpWpb, kFpWpb * WarpWs<kOpenL>::sharedBytes(), st>>>(nm->view, a);
-  nm->launches++;
-  CK(cudaGetLastError());
+constexpr int64_t kFpChunk = 1 << 20;  // queries per pass of the pipeline (1 KB corridor ring each)
+
+// scratch of a find_path over n pairs (nStarts distinct starts)
+static int findPathReserve(hbn_navmesh* nm, int64_t n, int64_t nStarts, int startDiv) {
+  const int64_t chunk = startDiv > 1 ? std::max<int64_t>(1, kFpChunk / startDiv) * startDiv : kFpChunk;
+  const int64_t nChunks = (n + chunk - 1) / chunk;
+  const int64_t cmax = std::min(n, chunk);
+  int rc;
+  if ((rc = nm->sG.ensure(nStarts * 4)) || (rc = nm->eG.ensure(n * 4)) || (rc = nm->sPt.ensure(nStarts * 12)) ||
+      (rc = nm->ePt.ensure(n * 12)) || (rc = nm->counters.ensure(static_cast<size_t>(nChunks) * kFpCounterBytes)) ||
+      (rc = nm->fpCls.ensure(cmax)) || (rc = nm->fpBucket.ensure(cmax)) || (rc = nm->fpWork.ensure(cmax * 4)) ||
+      (rc = nm->fpStat.ensure(cmax * 4)) || (rc = nm->fpLen.ensure(cmax * 4)) ||
+      (rc = nm->fpCorr.ensure(static_cast<size_t>(cmax) * kMaxPathPolys * 4)))
+    return rc;
   return HBN_OK;
 }
 
-constexpr int64_t kFpChunk = 1 << 20;  // queries per pass of the lock-step pipeline (1 KB corridor ring each)
+// grid of the search kernel for cn queries: lanes per warp (spreading) and one-warp blocks
+static void laneGrid(const hbn_navmesh* nm, int64_t cn, int* lanes, int* blocks) {
+  int64_t l = 32;
+  if (nm->opt.laneSpread) l = std::max<int64_t>(1, std::min<int64_t>(32, (cn + nm->blocksFpLane - 1) / nm->blocksFpLane));
+  *lanes = static_cast<int>(l);
+  *blocks = static_cast<int>(std::min<int64_t>(nm->blocksFpLane, (cn + l - 1) / l));
+}
 
 // n (start, end) pairs; startDiv > 1: pair q uses start q / startDiv (multi-goal layout)
-// pairMask (lock-step pipeline only): queries with a zero byte are skipped -- their outputs are left
-// alone, or get an infinite distance with kFpFillSkipped.  kFpReuseSnaps: the projectToPoly results
-// of the previous call on the same points are still in the scratch.
-enum { kFpReuseSnaps = 1 << 16, kFpFillSkipped = 1 << 17 };
+// pairMask: queries with a zero byte are skipped -- their outputs are left alone, or get an infinite
+// distance with kFpFillSkipped.  kFpReuseSnaps: the projectToPoly results of the previous call on the
+// same points are still in the scratch.  snapS / snapE (kFpGivenSnaps): projections supplied by the
+// caller (the env step hands over the ones tryStep made).
+enum { kFpReuseSnaps = 1 << 16, kFpFillSkipped = 1 << 17, kFpGivenSnaps = 1 << 18 };
+struct GivenSnaps {
+  const uint32_t* sG; const float* sPt; const uint32_t* eG; const float* ePt;
+};
 static int findPathLaunch(hbn_navmesh_t nm, const float* starts, const float* ends, int64_t n,
                           int startDiv, float* out_dist, int32_t* out_npts, float* out_pts, int max_pts,
                           uint32_t* out_corridor, int32_t* out_ncorridor, uint32_t* out_status,
-                          int flags, void* stream, const uint8_t* pairMask = nullptr) {
+                          int flags, cudaStream_t st, const uint8_t* pairMask = nullptr,
+                          const GivenSnaps* given = nullptr) {
   if (!nm || (n > 0 && (!starts || !ends || !out_dist))) return fail(HBN_ERR_INVALID, "null argument");
   if (n <= 0) return HBN_OK;
   const int64_t nStarts = startDiv > 1 ? n / startDiv : n;
   if (n >= (1ll << 31)) return fail(HBN_ERR_INVALID, "batch too large");
   if (out_pts && max_pts <= 0) return fail(HBN_ERR_INVALID, "max_pts must be positive");
-  DeviceGuard g(nm->device);
-  std::lock_guard<std::recursive_mutex> lk(nm->mu);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc;
   if ((rc = checkFault(nm))) return rc;  // reported by an earlier launch
   const int64_t chunk = startDiv > 1 ? std::max<int64_t>(1, kFpChunk / startDiv) * startDiv : kFpChunk;
-  const int64_t nChunks = nm->fpG ? (n + chunk - 1) / chunk : 1;
-  const int64_t cmax = std::min(n, chunk);
-  if ((rc = nm->sG.ensure(nStarts * 4)) || (rc = nm->eG.ensure(n * 4)) || (rc = nm->sPt.ensure(nStarts * 12)) ||
-      (rc = nm->ePt.ensure(n * 12)) || (rc = nm->lists.ensure(cmax * 4)) ||
-      (rc = nm->counters.ensure(static_cast<size_t>(nChunks) * kFpCounterBytes)))
-    return rc;
-  if (nm->fpG &&
-      ((rc = nm->fpCls.ensure(cmax)) || (rc = nm->fpBucket.ensure(cmax)) || (rc = nm->fpWork.ensure(cmax * 4)) || (rc = nm->fpStat.ensure(cmax * 4)) ||
-       (rc = nm->fpLen.ensure(cmax * 4)) || (rc = nm->fpCorr.ensure(static_cast<size_t>(cmax) * kMaxPathPolys * 4))))
-    return rc;
+  const int64_t nChunks = (n + chunk - 1) / chunk;
+  if ((rc = findPathReserve(nm, n, nStarts, startDiv))) return rc;
   CK(cudaMemsetAsync(nm->counters.p, 0, static_cast<size_t>(nChunks) * kFpCounterBytes, st));
   hbn_navmesh::PhaseEv pe{};
-  if (nm->profile) {
+  bool profile = nm->profile;
+  if (profile) {  // not inside a stream capture
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) profile = false;
+  }
+  if (profile) {
     for (auto& e : pe.e) CK(cudaEventCreate(&e));
     CK(cudaEventRecord(pe.e[0], st));
   }
-  if (pairMask && !nm->fpG) return fail(HBN_ERR_INVALID, "pair masks need the lock-step find_path pipeline");
-  if ((flags & kFpReuseSnaps) == 0) {
-    if (snapDualLaunch(nm, starts, nStarts, static_cast<float*>(nm->sPt.p), static_cast<uint32_t*>(nm->sG.p), ends, n,
-                       static_cast<float*>(nm->ePt.p), static_cast<uint32_t*>(nm->eG.p), st, &rc)) {
+  const uint32_t* sGp = static_cast<uint32_t*>(nm->sG.p);
+  const float* sPtp = static_cast<float*>(nm->sPt.p);
+  const uint32_t* eGp = static_cast<uint32_t*>(nm->eG.p);
+  const float* ePtp = static_cast<float*>(nm->ePt.p);
+  if (flags & kFpGivenSnaps) {
+    sGp = given->sG; sPtp = given->sPt; eGp = given->eG; ePtp = given->ePt;
+  } else if ((flags & kFpReuseSnaps) == 0) {
+    if (snapDualLaunch(nm, SnapJob{starts, nStarts, static_cast<float*>(nm->sPt.p), static_cast<uint32_t*>(nm->sG.p)},
+                       SnapJob{ends, n, static_cast<float*>(nm->ePt.p), static_cast<uint32_t*>(nm->eG.p)},
+                       SnapJob{nullptr, 0, nullptr, nullptr}, st, &rc)) {
       if (rc) return rc;
     } else {
       if ((rc = snapLaunch(nm, starts, nullptr, nStarts, static_cast<float*>(nm->sPt.p),
@@ -706,104 +848,71 @@ static int findPathLaunch(hbn_navmesh_t nm, const float* starts, const float* en
         return rc;
     }
   }
-  if (nm->profile) CK(cudaEventRecord(pe.e[1], st));
+  if (profile) CK(cudaEventRecord(pe.e[1], st));
   unsigned long long* workCtr = (flags & HBN_FP_COUNT_WORK) ? static_cast<unsigned long long*>(nm->work.p) : nullptr;
   for (int64_t ci = 0; ci < nChunks; ++ci) {
-    const int64_t c0 = nm->fpG ? ci * chunk : 0;
-    const int64_t cn = nm->fpG ? std::min(chunk, n - c0) : n;
+    const int64_t c0 = ci * chunk;
+    const int64_t cn = std::min(chunk, n - c0);
     const int64_t s0 = startDiv > 1 ? c0 / startDiv : c0;
     uint32_t* cnt = static_cast<uint32_t*>(nm->counters.p) + ci * (kFpCounterBytes / 4);
-    FindPathArgs a{};
-    a.starts = starts + 3 * s0; a.ends = ends + 3 * c0;
-    a.sG = static_cast<uint32_t*>(nm->sG.p) + s0; a.sPt = static_cast<float*>(nm->sPt.p) + 3 * s0;
-    a.eG = static_cast<uint32_t*>(nm->eG.p) + c0; a.ePt = static_cast<float*>(nm->ePt.p) + 3 * c0;
-    a.n = cn;
-    a.work = nullptr; a.workCount = nullptr;
-    a.out_dist = out_dist + c0;
-    a.out_npts = out_npts ? out_npts + c0 : nullptr;
-    a.out_pts = out_pts ? out_pts + static_cast<size_t>(c0) * max_pts * 3 : nullptr;
-    a.max_pts = max_pts;
-    a.out_corridor = out_corridor ? out_corridor + static_cast<size_t>(c0) * kMaxPathPolys : nullptr;
-    a.out_ncorridor = out_ncorridor ? out_ncorridor + c0 : nullptr;
-    a.out_status = out_status ? out_status + 2 * c0 : nullptr;
-    a.fault = nm->faultDev;
-    a.startDiv = startDiv;
-    a.fastFail = (flags & HBN_FP_EXACT_STATUS) ? 0 : 1;
-    a.workCtr = workCtr;
-    if (!nm->fpG) {
-      if ((rc = warpTierLaunch(nm, a, true, cnt, st))) return rc;
-      continue;
-    }
-    // lock-step pipeline: classify -> search -> funnel (+ the 2048-entry tier for overflows)
+    // classify -> search list -> search -> funnel
     uint8_t* cls = static_cast<uint8_t*>(nm->fpCls.p);
     uint32_t* work = static_cast<uint32_t*>(nm->fpWork.p);
     uint8_t* bucket = static_cast<uint8_t*>(nm->fpBucket.p);
     k_fp_classify<<<static_cast<unsigned>((cn + 255) / 256), 256, 0, st>>>(
-        nm->view, a.sG, a.sPt, a.eG, a.ePt, cn, startDiv, pairMask ? pairMask + c0 : nullptr, cls, bucket, cnt + 16,
-        cnt + 4);
+        nm->view, sGp + s0, sPtp + 3 * s0, eGp + c0, ePtp + 3 * c0, cn, startDiv, pairMask ? pairMask + c0 : nullptr,
+        cls, bucket, cnt + 16, cnt + 4);
     k_fp_scatter<<<static_cast<unsigned>((cn + 255) / 256), 256, 0, st>>>(bucket, cn, cnt + 16, cnt + 16 + kFpBuckets,
                                                                          work);
     nm->launches += 2;
     CK(cudaGetLastError());
-    AStarGArgs ga{};
-    ga.sG = a.sG; ga.sPt = a.sPt; ga.eG = a.eG; ga.ePt = a.ePt;
+    SearchArgs ga{};
+    ga.sG = sGp + s0; ga.sPt = sPtp + 3 * s0; ga.eG = eGp + c0; ga.ePt = ePtp + 3 * c0;
     ga.work = work; ga.workCount = cnt + 4;
     ga.counter = cnt + 5;
-    ga.overflow = static_cast<uint32_t*>(nm->lists.p);
-    ga.overflowCount = cnt + 6;
     ga.astat = static_cast<uint32_t*>(nm->fpStat.p);
     ga.fullLen = static_cast<int32_t*>(nm->fpLen.p);
     ga.corrVia = static_cast<uint32_t*>(nm->fpCorr.p);
-    ga.scratch = static_cast<char*>(nm->wsFpG.p);
     ga.startDiv = startDiv;
-    ga.fastFail = a.fastFail;
+    ga.fastFail = (flags & HBN_FP_EXACT_STATUS) ? 0 : 1;
     ga.allCorridors = (out_corridor || out_ncorridor) ? 1 : 0;
     ga.workCtr = workCtr;
     ga.fault = nm->faultDev;
-    if (nm->fpG == 1) {
+    {
+      int lanes = 32, blocks = 1;
+      laneGrid(nm, cn, &lanes, &blocks);
       LaneScratch sc{};
-      if ((rc = laneScratch(nm, st, &sc))) return rc;
-      int64_t lanes = 32;  // queries per warp
-      if (nm->laneSpread) lanes = std::max<int64_t>(1, std::min<int64_t>(32, (cn + nm->blocksFpLane - 1) / nm->blocksFpLane));
-      ga.laneLimit = static_cast<int>(lanes);
-      const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(nm->blocksFpLane, (cn + lanes - 1) / lanes));
+      if ((rc = laneScratch(nm, st, &blocks, &sc))) return rc;
+      // fewer lane slots than the grid wanted (memory cap): every active lane takes more queries
+      if (static_cast<int64_t>(blocks) * lanes < std::min<int64_t>(cn, static_cast<int64_t>(nm->blocksFpLane) * 32) && lanes < 32)
+        lanes = static_cast<int>(std::min<int64_t>(32, (cn + blocks - 1) / blocks));
+      ga.laneLimit = lanes;
       size_t smLane = 0;
-      const void* fn = laneKernel(nm->laneCfg, &smLane);
+      const void* fn = laneKernel(nm->opt.laneCfg, &smLane);
       void* kargs[] = {&nm->view, &ga, &sc};
-      CK(cudaLaunchKernel(fn, dim3(blocks), dim3(32), kargs, smLane, st));
-      nm->launches++;
-      CK(cudaGetLastError());
-    } else {
-      const int qpw = 32 / nm->fpG;
-      const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(nm->blocksFpG, (cn + qpw - 1) / qpw));
-      const size_t sm = qpw * gGroupSharedBytes<kOpenS>();
-      switch (nm->fpG) {
-        case 4: k_astar_g<4, kOpenS><<<blocks, 32, sm, st>>>(nm->view, ga); break;
-        case 16: k_astar_g<16, kOpenS><<<blocks, 32, sm, st>>>(nm->view, ga); break;
-        case 32: k_astar_g<32, kOpenS><<<blocks, 32, sm, st>>>(nm->view, ga); break;
-        default: k_astar_g<8, kOpenS><<<blocks, 32, sm, st>>>(nm->view, ga); break;
-      }
+      CK(cudaLaunchKernel(fn, dim3(static_cast<unsigned>(blocks)), dim3(32), kargs, smLane, st));
       nm->launches++;
       CK(cudaGetLastError());
     }
     FpFunnelArgs fa{};
-    fa.starts = a.starts; fa.ends = a.ends;
-    fa.sG = a.sG; fa.sPt = a.sPt; fa.eG = a.eG; fa.ePt = a.ePt;
+    fa.starts = starts + 3 * s0; fa.ends = ends + 3 * c0;
+    fa.sG = ga.sG; fa.sPt = ga.sPt; fa.eG = ga.eG; fa.ePt = ga.ePt;
     fa.cls = cls; fa.astat = ga.astat; fa.fullLen = ga.fullLen; fa.corrVia = ga.corrVia;
     fa.n = cn; fa.startDiv = startDiv;
-    fa.out_dist = a.out_dist; fa.out_npts = a.out_npts; fa.out_pts = a.out_pts; fa.max_pts = max_pts;
-    fa.out_corridor = a.out_corridor; fa.out_ncorridor = a.out_ncorridor; fa.out_status = a.out_status;
+    fa.out_dist = out_dist + c0;
+    fa.out_npts = out_npts ? out_npts + c0 : nullptr;
+    fa.out_pts = out_pts ? out_pts + static_cast<size_t>(c0) * max_pts * 3 : nullptr;
+    fa.max_pts = max_pts;
+    fa.out_corridor = out_corridor ? out_corridor + static_cast<size_t>(c0) * kMaxPathPolys : nullptr;
+    fa.out_ncorridor = out_ncorridor ? out_ncorridor + c0 : nullptr;
+    fa.out_status = out_status ? out_status + 2 * c0 : nullptr;
     fa.workCtr = workCtr;
     fa.fillSkipped = (flags & kFpFillSkipped) ? 1 : 0;
     k_fp_funnel<<<static_cast<unsigned>((cn + 127) / 128), 128, 0, st>>>(nm->view, fa);
     nm->launches++;
     CK(cudaGetLastError());
-    // queries whose open list outgrew kOpenS: one query per warp with a 2048-entry heap
-    a.work = ga.overflow;
-    a.workCount = ga.overflowCount;
-    if ((rc = warpTierLaunch(nm, a, false, cnt, st))) return rc;
   }
-  if (nm->profile) {
+  if (profile) {
     CK(cudaEventRecord(pe.e[2], st));
     nm->phaseEvents.push_back(pe);
   }
@@ -815,8 +924,13 @@ extern "C" int hbn_find_path_dev(hbn_navmesh_t nm, const float* starts, const fl
                                  float* out_dist, int32_t* out_npts, float* out_pts, int max_pts,
                                  uint32_t* out_corridor, int32_t* out_ncorridor, uint32_t* out_status,
                                  int flags, void* stream) {
+  if (!nm) return fail(HBN_ERR_INVALID, "null navmesh");
+  DeviceGuard g(nm->device);
+  std::lock_guard<std::recursive_mutex> lk(nm->mu);
+  NvtxRange nv(nm->opt.nvtx, "hbn_find_path");
+  CallOrder order(nm, static_cast<cudaStream_t>(stream));
   return findPathLaunch(nm, starts, ends, n, 1, out_dist, out_npts, out_pts, max_pts, out_corridor,
-                        out_ncorridor, out_status, flags, stream);
+                        out_ncorridor, out_status, flags & 0xffff, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" {
@@ -833,12 +947,14 @@ int hbn_find_path_multigoal_dev(hbn_navmesh_t nm, const float* starts, const flo
   DeviceGuard gd(nm->device);
   std::lock_guard<std::recursive_mutex> lk(nm->mu);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  NvtxRange nv(nm->opt.nvtx, "hbn_find_path_multigoal");
+  CallOrder order(nm, st);
   int rc;
   const bool wantPts = out_npts || out_pts;
   if ((rc = nm->mgDist.ensure(pairs * 4)) || (rc = nm->mgBounds.ensure(pairs * 4)) ||
       (rc = nm->mgOrder.ensure(pairs * 4)) || (wantPts && (rc = nm->mgEnd.ensure(n * 12))))
     return rc;
-  if (g > kMultiGoalFirst && nm->fpG) {
+  if (g > kMultiGoalFirst) {
     // two rounds of pair searches: the kMultiGoalFirst goals of smallest bound of every start, then
     // the later goals the reference would not skip (hbn_query.h); bounds / order in the select's scratch
     if ((rc = nm->mgMask.ensure(pairs))) return rc;
@@ -849,7 +965,7 @@ int hbn_find_path_multigoal_dev(hbn_navmesh_t nm, const float* starts, const flo
     nm->launches++;
     CK(cudaGetLastError());
     if ((rc = findPathLaunch(nm, starts, ends, pairs, g, static_cast<float*>(nm->mgDist.p), nullptr, nullptr, 0,
-                             nullptr, nullptr, nullptr, kFpFillSkipped, stream, mask)))
+                             nullptr, nullptr, nullptr, kFpFillSkipped, st, mask)))
       return rc;
     k_multigoal_round2<<<sb, 128, 0, st>>>(static_cast<uint32_t*>(nm->sG.p), static_cast<uint32_t*>(nm->eG.p),
                                            static_cast<float*>(nm->mgDist.p), n, g,
@@ -858,10 +974,10 @@ int hbn_find_path_multigoal_dev(hbn_navmesh_t nm, const float* starts, const flo
     nm->launches++;
     CK(cudaGetLastError());
     if ((rc = findPathLaunch(nm, starts, ends, pairs, g, static_cast<float*>(nm->mgDist.p), nullptr, nullptr, 0,
-                             nullptr, nullptr, nullptr, kFpReuseSnaps, stream, mask)))
+                             nullptr, nullptr, nullptr, kFpReuseSnaps, st, mask)))
       return rc;
   } else if ((rc = findPathLaunch(nm, starts, ends, pairs, g, static_cast<float*>(nm->mgDist.p), nullptr, nullptr,
-                                  0, nullptr, nullptr, nullptr, 0, stream))) {
+                                  0, nullptr, nullptr, nullptr, 0, st))) {
     // every (start, goal) pair's findPathInternal, in parallel ...
     return rc;
   }
@@ -877,10 +993,45 @@ int hbn_find_path_multigoal_dev(hbn_navmesh_t nm, const float* starts, const flo
     if ((rc = nm->mgDist.ensure(std::max<int64_t>(pairs, n) * 4))) return rc;
     if ((rc = findPathLaunch(nm, starts, static_cast<float*>(nm->mgEnd.p), n, 1,
                              static_cast<float*>(nm->mgDist.p), out_npts, out_pts, max_pts, nullptr, nullptr,
-                             nullptr, 0, stream)))
+                             nullptr, 0, st)))
       return rc;
   }
   return HBN_OK;
+}
+
+// scratch of try_step / env step over n queries
+static int tryStepReserve(hbn_navmesh* nm, int64_t n) {
+  int rc;
+  if ((rc = nm->sG.ensure(n * 4)) || (rc = nm->eG.ensure(n * 4)) || (rc = nm->e2G.ensure(n * 4)) ||
+      (rc = nm->sPt.ensure(n * 12)) || (rc = nm->epPt.ensure(n * 12)) || (rc = nm->lastPoly.ensure(n * 4)))
+    return rc;
+  return HBN_OK;
+}
+
+// tryStep up to, not including, phase B: projections of start and end (+ an optional third batch in
+// the same launch), moveAlongSurface / the no-sliding ray, projection of the end point
+static int tryStepFront(hbn_navmesh* nm, const float* starts, const float* ends, int64_t n, int allow_sliding,
+                        SnapJob third, float* e2Pt, cudaStream_t st) {
+  int rc;
+  uint32_t* sG = static_cast<uint32_t*>(nm->sG.p);
+  uint32_t* eG = static_cast<uint32_t*>(nm->eG.p);
+  float* sPt = static_cast<float*>(nm->sPt.p);
+  float* ep = static_cast<float*>(nm->epPt.p);
+  uint32_t* last = static_cast<uint32_t*>(nm->lastPoly.p);
+  if (snapDualLaunch(nm, SnapJob{starts, n, sPt, sG}, SnapJob{ends, n, nullptr, eG}, third, st, &rc)) {
+    if (rc) return rc;
+  } else {
+    if ((rc = snapLaunch(nm, starts, nullptr, n, sPt, sG, nullptr, nullptr, nullptr, 0.f, st))) return rc;
+    if ((rc = snapLaunch(nm, ends, nullptr, n, nullptr, eG, nullptr, nullptr, nullptr, 0.f, st))) return rc;
+    if (third.n > 0 &&
+        (rc = snapLaunch(nm, third.pts, nullptr, third.n, third.out_pts, third.out_g, nullptr, nullptr, nullptr, 0.f, st)))
+      return rc;
+  }
+  k_trystep_a<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(nm->view, ends, sG, sPt, eG, n,
+                                                                      allow_sliding, ep, last);
+  nm->launches++;
+  CK(cudaGetLastError());
+  return snapLaunch(nm, ep, nullptr, n, e2Pt, static_cast<uint32_t*>(nm->e2G.p), nullptr, nullptr, nullptr, 0.f, st);
 }
 
 int hbn_try_step_dev(hbn_navmesh_t nm, const float* starts, const float* ends, int64_t n,
@@ -890,31 +1041,78 @@ int hbn_try_step_dev(hbn_navmesh_t nm, const float* starts, const float* ends, i
   DeviceGuard g(nm->device);
   std::lock_guard<std::recursive_mutex> lk(nm->mu);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  NvtxRange nv(nm->opt.nvtx, "hbn_try_step");
+  CallOrder order(nm, st);
   int rc;
-  if ((rc = nm->sG.ensure(n * 4)) || (rc = nm->eG.ensure(n * 4)) || (rc = nm->e2G.ensure(n * 4)) ||
-      (rc = nm->sPt.ensure(n * 12)) || (rc = nm->epPt.ensure(n * 12)) || (rc = nm->lastPoly.ensure(n * 4)))
+  if ((rc = tryStepReserve(nm, n))) return rc;
+  if ((rc = tryStepFront(nm, starts, ends, n, allow_sliding, SnapJob{nullptr, 0, nullptr, nullptr}, nullptr, st)))
     return rc;
-  uint32_t* sG = static_cast<uint32_t*>(nm->sG.p);
-  uint32_t* eG = static_cast<uint32_t*>(nm->eG.p);
-  uint32_t* e2G = static_cast<uint32_t*>(nm->e2G.p);
-  float* sPt = static_cast<float*>(nm->sPt.p);
-  float* ep = static_cast<float*>(nm->epPt.p);
-  uint32_t* last = static_cast<uint32_t*>(nm->lastPoly.p);
-  if (snapDualLaunch(nm, starts, n, sPt, sG, ends, n, nullptr, eG, st, &rc)) {
-    if (rc) return rc;
-  } else {
-    if ((rc = snapLaunch(nm, starts, nullptr, n, sPt, sG, nullptr, nullptr, nullptr, 0.f, st))) return rc;
-    if ((rc = snapLaunch(nm, ends, nullptr, n, nullptr, eG, nullptr, nullptr, nullptr, 0.f, st))) return rc;
-  }
-  k_trystep_a<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(nm->view, ends, sG, sPt, eG, n,
-                                                                      allow_sliding, ep, last);
-  nm->launches++;
-  CK(cudaGetLastError());
-  if ((rc = snapLaunch(nm, ep, nullptr, n, nullptr, e2G, nullptr, nullptr, nullptr, 0.f, st))) return rc;
-  k_trystep_b<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(nm->view, starts, sG, e2G, last, ep, n, out_pts);
+  k_trystep_b<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
+      nm->view, starts, static_cast<uint32_t*>(nm->sG.p), static_cast<uint32_t*>(nm->e2G.p),
+      static_cast<uint32_t*>(nm->lastPoly.p), static_cast<float*>(nm->epPt.p), n, out_pts);
   nm->launches++;
   CK(cudaGetLastError());
   return HBN_OK;
+}
+
+static int envStepReserve(hbn_navmesh* nm, int64_t n) {
+  int rc;
+  if ((rc = tryStepReserve(nm, n)) || (rc = nm->e2Pt.ensure(n * 12)) || (rc = nm->envG.ensure(n * 4)) ||
+      (rc = nm->envPt.ensure(n * 12)) || (rc = nm->envFlag.ensure(n)) || (rc = nm->ePt.ensure(n * 12)) ||
+      (rc = nm->envPos.ensure(n * 4)) || (rc = findPathReserve(nm, n, n, 1)))
+    return rc;
+  int lanes = 32, blocks = 1;
+  laneGrid(nm, n, &lanes, &blocks);
+  LaneScratch sc{};
+  return laneScratch(nm, nm->stream, &blocks, &sc);
+}
+
+// One environment step of the PointNav loop (simulator.py:660-673 + the geodesic reward): tryStep from
+// `starts` towards `targets`, then find_path from the new position to `goals`.  Equivalent to
+// hbn_try_step_dev followed by hbn_find_path_dev (bit for bit), with the projections shared: goals are
+// projected in the same launch as starts and targets, and the new position is not projected again
+// (k_envstep_b hands find_path the projection phase B already made; nudged positions are redone by
+// k_snap_flagged).  9 launches instead of 13.
+int hbn_env_step_dev(hbn_navmesh_t nm, const float* starts, const float* targets, const float* goals, int64_t n,
+                     int allow_sliding, float* out_pos, float* out_dist, void* stream) {
+  if (!nm || (n > 0 && (!starts || !targets || !goals || !out_pos || !out_dist)))
+    return fail(HBN_ERR_INVALID, "null argument");
+  if (n <= 0) return HBN_OK;
+  if (n >= (1ll << 31)) return fail(HBN_ERR_INVALID, "batch too large");
+  DeviceGuard g(nm->device);
+  std::lock_guard<std::recursive_mutex> lk(nm->mu);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  NvtxRange nv(nm->opt.nvtx, "hbn_env_step");
+  CallOrder order(nm, st);
+  int rc;
+  if ((rc = tryStepReserve(nm, n)) || (rc = nm->e2Pt.ensure(n * 12)) || (rc = nm->envG.ensure(n * 4)) ||
+      (rc = nm->envPt.ensure(n * 12)) || (rc = nm->envFlag.ensure(n)) || (rc = nm->ePt.ensure(n * 12)) ||
+      (rc = nm->envPos.ensure(n * 4)))
+    return rc;
+  // the goals' projections: points where find_path keeps its end projections (ePt is free during a
+  // try_step), polys in a slot of their own (eG holds try_step's end projection)
+  uint32_t* gG = static_cast<uint32_t*>(nm->envPos.p);
+  float* gPt = static_cast<float*>(nm->ePt.p);
+  float* e2Pt = static_cast<float*>(nm->e2Pt.p);
+  if ((rc = tryStepFront(nm, starts, targets, n, allow_sliding, SnapJob{goals, n, gPt, gG}, e2Pt, st))) return rc;
+  uint32_t* fpG = static_cast<uint32_t*>(nm->envG.p);
+  float* fpPt = static_cast<float*>(nm->envPt.p);
+  uint8_t* flag = static_cast<uint8_t*>(nm->envFlag.p);
+  k_envstep_b<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
+      nm->view, starts, static_cast<uint32_t*>(nm->sG.p), static_cast<float*>(nm->sPt.p),
+      static_cast<uint32_t*>(nm->e2G.p), e2Pt, static_cast<uint32_t*>(nm->lastPoly.p),
+      static_cast<float*>(nm->epPt.p), n, out_pos, fpG, fpPt, flag);
+  {
+    const unsigned threads = (nm->opt.snapSpread && n < kSnapSmall) ? kSnapW : 256;
+    const int64_t gpb = threads / kSnapW;
+    const int64_t blocks = std::min<int64_t>((n + gpb - 1) / gpb, static_cast<int64_t>(nm->smCount) * 64 * (256 / threads));
+    k_snap_flagged<kSnapW><<<static_cast<unsigned>(blocks), threads, 0, st>>>(nm->view, out_pos, flag, n, fpPt, fpG);
+  }
+  nm->launches += 2;
+  CK(cudaGetLastError());
+  const GivenSnaps given{fpG, fpPt, gG, gPt};
+  return findPathLaunch(nm, out_pos, goals, n, 1, out_dist, nullptr, nullptr, 0, nullptr, nullptr, nullptr,
+                        kFpGivenSnaps, st, nullptr, &given);
 }
 
 int hbn_closest_obstacle_dev(hbn_navmesh_t nm, const float* pts, int64_t n, float max_radius,
@@ -926,6 +1124,8 @@ int hbn_closest_obstacle_dev(hbn_navmesh_t nm, const float* pts, int64_t n, floa
   DeviceGuard g(nm->device);
   std::lock_guard<std::recursive_mutex> lk(nm->mu);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  NvtxRange nv(nm->opt.nvtx, "hbn_closest_obstacle");
+  CallOrder order(nm, st);
   int rc;
   if ((rc = nm->sG.ensure(n * 4)) || (rc = nm->sPt.ensure(n * 12)) || (rc = nm->lists.ensure(n * 4))) return rc;
   uint32_t* cnt = static_cast<uint32_t*>(nm->counters.p);
@@ -968,6 +1168,9 @@ int hbn_random_points_dev(hbn_navmesh_t nm, uint64_t seed, uint64_t query0, int6
   if (nm->flat.totalArea <= 0.0f)
     return fail(HBN_ERR_NO_AREA, "NavMesh has no navigable area, this indicates an issue with the NavMesh");
   DeviceGuard g(nm->device);
+  std::lock_guard<std::recursive_mutex> lk(nm->mu);
+  NvtxRange nv(nm->opt.nvtx, "hbn_random_points");
+  CallOrder order(nm, static_cast<cudaStream_t>(stream));
   const int groupsPerBlock = 256 / kRandW;
   int64_t blocks = std::min<int64_t>((n + groupsPerBlock - 1) / groupsPerBlock,
                                      static_cast<int64_t>(nm->smCount) * 64);
@@ -986,6 +1189,9 @@ int hbn_random_points_near_dev(hbn_navmesh_t nm, uint64_t seed, uint64_t query0,
   if (nm->flat.totalArea <= 0.0f)
     return fail(HBN_ERR_NO_AREA, "NavMesh has no navigable area, this indicates an issue with the NavMesh");
   DeviceGuard g(nm->device);
+  std::lock_guard<std::recursive_mutex> lk(nm->mu);
+  NvtxRange nv(nm->opt.nvtx, "hbn_random_points_near");
+  CallOrder order(nm, static_cast<cudaStream_t>(stream));
   const int groupsPerBlock = 256 / kRandW;
   int64_t blocks = std::min<int64_t>((n + groupsPerBlock - 1) / groupsPerBlock,
                                      static_cast<int64_t>(nm->smCount) * 64);
@@ -1023,28 +1229,43 @@ struct IoPlan {
       nm->pinnedCap = 0;
       CK(cudaMallocHost(&nm->pinned, off + off / 4));
       nm->pinnedCap = off + off / 4;
+      g_scratchEpoch++;
     }
     return HBN_OK;
   }
   template <class T> T* dev(size_t o) { return reinterpret_cast<T*>(static_cast<char*>(nm->io.p) + o); }
-  int h2d() {
+  void stage() {  // user buffers -> pinned
     for (auto& it : items)
-      if (it.src) {
-        memcpy(static_cast<char*>(nm->pinned) + it.off, it.src, it.bytes);
+      if (it.src) memcpy(static_cast<char*>(nm->pinned) + it.off, it.src, it.bytes);
+  }
+  int enqueueH2D() {
+    for (auto& it : items)
+      if (it.src)
         CK(cudaMemcpyAsync(static_cast<char*>(nm->io.p) + it.off, static_cast<char*>(nm->pinned) + it.off,
                            it.bytes, cudaMemcpyHostToDevice, nm->stream));
-      }
     return HBN_OK;
   }
-  int d2h() {
+  int enqueueD2H() {
     for (auto& it : items)
       if (it.dst)
         CK(cudaMemcpyAsync(static_cast<char*>(nm->pinned) + it.off, static_cast<char*>(nm->io.p) + it.off,
                            it.bytes, cudaMemcpyDeviceToHost, nm->stream));
+    return HBN_OK;
+  }
+  int finish() {  // wait, pinned -> user buffers
     CK(cudaStreamSynchronize(nm->stream));
     for (auto& it : items)
       if (it.dst) memcpy(it.dst, static_cast<char*>(nm->pinned) + it.off, it.bytes);
     return checkFault(nm);
+  }
+  int h2d() {
+    stage();
+    return enqueueH2D();
+  }
+  int d2h() {
+    int rc = enqueueD2H();
+    if (rc) return rc;
+    return finish();
   }
 };
 }  // namespace
@@ -1141,6 +1362,70 @@ int hbn_try_step(hbn_navmesh_t nm, const float* starts, const float* ends, int64
   if ((rc = hbn_try_step_dev(nm, io.dev<float>(oS), io.dev<float>(oE), n, allow_sliding, io.dev<float>(oO), nm->stream)))
     return rc;
   return io.d2h();
+}
+
+// Host-buffer env step.  The whole step -- H2D of the three inputs, the 9 kernels of hbn_env_step_dev,
+// D2H of the two outputs -- is captured ONCE per (batch size, sliding mode) into a CUDA graph and
+// replayed: a PointNav step at 1024 envs is a chain of small kernels whose launch overheads and
+// inter-kernel gaps are a third of its wall time.  The graph is rebuilt when any scratch buffer or
+// option it baked in has changed (g_scratchEpoch).
+int hbn_env_step(hbn_navmesh_t nm, const float* starts, const float* targets, const float* goals, int64_t n,
+                 int allow_sliding, float* out_pos, float* out_dist) {
+  HOST_PROLOGUE
+  if (!starts || !targets || !goals || !out_pos || !out_dist) return fail(HBN_ERR_INVALID, "null argument");
+  NvtxRange nv(nm->opt.nvtx, "hbn_env_step(host)");
+  const size_t oS = io.add(n * 12, starts, nullptr);
+  const size_t oT = io.add(n * 12, targets, nullptr);
+  const size_t oG = io.add(n * 12, goals, nullptr);
+  const size_t oP = io.add(n * 12, nullptr, out_pos);
+  const size_t oD = io.add(n * 4, nullptr, out_dist);
+  if ((rc = checkFault(nm))) return rc;
+  hbn_navmesh::StepGraph* sg = nullptr;
+  for (auto& c : nm->stepGraphs)
+    if (c.n == n && c.sliding == (allow_sliding != 0)) sg = &c;
+  if (!sg || sg->epoch != g_scratchEpoch) {
+    // everything the step will touch exists before the capture starts
+    if ((rc = io.prepare()) || (rc = envStepReserve(nm, n))) return rc;
+    CK(cudaStreamSynchronize(nm->stream));
+    if (sg && sg->exec) cudaGraphExecDestroy(sg->exec);
+    if (!sg) {
+      nm->stepGraphs.push_back(hbn_navmesh::StepGraph{n, allow_sliding != 0, 0, nullptr, {0, 0, 0, 0, 0}});
+      sg = &nm->stepGraphs.back();
+    }
+    sg->exec = nullptr;
+    const int64_t l0 = nm->launches;
+    const uint64_t epoch = g_scratchEpoch;
+    CK(cudaStreamBeginCapture(nm->stream, cudaStreamCaptureModeThreadLocal));
+    rc = io.enqueueH2D();
+    if (!rc)
+      rc = hbn_env_step_dev(nm, io.dev<float>(oS), io.dev<float>(oT), io.dev<float>(oG), n, allow_sliding,
+                            io.dev<float>(oP), io.dev<float>(oD), nm->stream);
+    if (!rc) rc = io.enqueueD2H();
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(nm->stream, &graph);
+    if (rc || ce != cudaSuccess || epoch != g_scratchEpoch) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      if (!rc) rc = fail(HBN_ERR_CUDA, epoch != g_scratchEpoch ? "scratch moved during the env step capture"
+                                                                 : std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+      return rc;
+    }
+    const cudaError_t ie = cudaGraphInstantiate(&sg->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) return fail(HBN_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie));
+    sg->epoch = epoch;
+    sg->offs[0] = static_cast<size_t>(nm->launches - l0);  // kernels per replay
+    nm->launches = l0;
+  }
+  io.stage();
+  if (nm->lastValid && nm->lastStream != nm->stream) CK(cudaStreamWaitEvent(nm->stream, nm->lastDone, 0));
+  CK(cudaGraphLaunch(sg->exec, nm->stream));
+  nm->launches += static_cast<int64_t>(sg->offs[0]);
+  if (cudaEventRecord(nm->lastDone, nm->stream) == cudaSuccess) {
+    nm->lastStream = nm->stream;
+    nm->lastValid = true;
+  }
+  return io.finish();
 }
 
 int hbn_closest_obstacle(hbn_navmesh_t nm, const float* pts, int64_t n, float max_radius,

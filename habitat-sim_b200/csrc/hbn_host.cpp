@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <unordered_map>
 
 namespace hbn {
 namespace {
@@ -392,6 +393,43 @@ bool HostNavMesh::loadMSET(const uint8_t* buf, size_t len, std::string& err) {
   return true;
 }
 
+// PathFinder::Impl::saveNavMesh, PathFinder.cpp:1177-1223
+bool HostNavMesh::saveMSET(std::vector<uint8_t>& out, std::string& err) const {
+  if (!hasSettings_) {
+    err = "NavMeshSettings weren't set. Either build or load a navmesh before saving";
+    return false;
+  }
+  struct { int32_t magic, version, numTiles; DtNavMeshParams params; } header;
+  header.magic = kMsetMagic;
+  header.version = 2;
+  header.numTiles = 0;
+  for (const HostTile& t : tiles_)
+    if (t.present && !t.data.empty()) ++header.numTiles;
+  header.params = params_;
+  out.clear();
+  auto wr = [&](const void* p, size_t n) {
+    const uint8_t* c = static_cast<const uint8_t*>(p);
+    out.insert(out.end(), c, c + n);
+  };
+  wr(&header, sizeof(header));
+  wr(settings_, 56);
+  for (size_t i = 0; i < tiles_.size(); ++i) {
+    const HostTile& t = tiles_[i];
+    if (!t.present || t.data.empty()) continue;
+    struct { uint32_t tileRef; int32_t dataSize; } th;
+    th.tileRef = polyRefBase(static_cast<int>(i));  // dtNavMesh::getTileRef: poly 0 of the tile
+    th.dataSize = static_cast<int32_t>(t.data.size());
+    wr(&th, sizeof(th));
+    wr(t.data.data(), t.data.size());
+  }
+  return true;
+}
+
+void HostNavMesh::setSettings(const uint8_t* raw56) {
+  memcpy(settings_, raw56, 56);
+  hasSettings_ = true;
+}
+
 // IslandSystem constructor, PathFinder.cpp:173-206 + expandFrom :409-459
 void HostNavMesh::floodIslands() {
   polyIsland_.assign(tiles_.size(), {});
@@ -479,13 +517,22 @@ void HostNavMesh::zeroAreaAndAreas() {
       }
     }
   }
-  // The reference sums the per-island areas in std::unordered_map iteration order
-  // (PathFinder.cpp:1079-1083); index order here, equal within float tolerance.
+  // The reference sums the per-island areas in the ITERATION ORDER of a std::unordered_map<uint32_t, float>
+  // (PathFinder.cpp:1079-1083) whose keys were inserted in the iteration order of another one
+  // (islandsToPolys_, keys inserted as the islands were first met: 0, 1, 2, ...; PathFinder.cpp:1047-1051).
+  // f32 addition is not associative, so the same two containers are filled in the same way here and the
+  // sum runs in their order.
+  std::unordered_map<uint32_t, int> islandsToPolys;
+  for (uint32_t id = 0; id < islandArea_.size(); ++id) islandsToPolys[id] = 0;
+  std::unordered_map<uint32_t, float> islandsToArea;
+  islandsToArea.reserve(islandsToPolys.size());
+  for (auto& itr : islandsToPolys) islandsToArea[itr.first] = 0.0f;
+  for (uint32_t id = 0; id < islandArea_.size(); ++id) islandsToArea[id] = islandArea_[id];
   totalArea_ = 0.f;
-  for (float a : islandArea_) totalArea_ += a;
+  for (auto& itr : islandsToArea) totalArea_ += itr.second;
 }
 
-void HostNavMesh::finish(const int32_t* givenIslands) {
+void HostNavMesh::finish(const int32_t* givenIslands, const float* givenRadii, int numRadii) {
   floodIslands();
   if (givenIslands) {
     size_t k = 0;
@@ -512,7 +559,11 @@ void HostNavMesh::finish(const int32_t* givenIslands) {
       }
     }
     islandRadius_.assign(maxId + 1, 0.f);
-    for (int32_t id = 0; id <= maxId; ++id) {
+    if (givenRadii && numRadii == maxId + 1) {
+      islandRadius_.assign(givenRadii, givenRadii + numRadii);
+      iv.clear();
+    }
+    for (int32_t id = 0; id <= maxId && !iv.empty(); ++id) {
       const size_t n = iv[id].size() / 3;
       if (!n) continue;
       float cx = 0, cy = 0, cz = 0;

@@ -120,9 +120,17 @@ class HostNavMesh {
   bool addFinalisedTile(const uint8_t* data, size_t len, uint32_t tileRef, std::string& err);
   bool init(const DtNavMeshParams& p, std::string& err);
   // initNavQuery's host work: IslandSystem ctor, then removeZeroAreaPolys.
-  // givenIslands (optional, per poly in tile-table/poly order) overrides the flood fill.
-  void finish(const int32_t* givenIslands);
+  // givenIslands (optional, per poly in tile-table/poly order) overrides the flood fill;
+  // givenRadii (optional, one per island id) are IslandSystem::islandRadius_ as the caller's
+  // PathFinder computed them (the f32 centroid sum runs in its DFS order, which cannot be
+  // replayed from finalised flags: trap T5); without them the radii are recomputed per id.
+  void finish(const int32_t* givenIslands, const float* givenRadii = nullptr, int numRadii = 0);
   void flatten(FlatNav& out) const;
+  // PathFinder::Impl::saveNavMesh (PathFinder.cpp:1177-1223): the MSET v2 image of the tiles as they are
+  // now (links connected, zero-area polys disabled) -- also for a mesh handed over as live tiles.
+  // Fails like the reference when no NavMeshSettings block is known (PathFinder.cpp:1199-1203).
+  bool saveMSET(std::vector<uint8_t>& out, std::string& err) const;
+  void setSettings(const uint8_t* raw56);
 
   // test hooks
   const std::vector<HostTile>& tiles() const { return tiles_; }

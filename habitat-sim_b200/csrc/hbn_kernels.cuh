@@ -5,11 +5,8 @@
 //                  loads, candidate polys evaluated W at a time (findNearestPoly).  Used for
 //                  small batches; large ones go through the candidate-list pipeline of
 //                  hbn_snap.cuh (thread per point walk, thread per candidate closest point).
-//  k_findpath_w<..> one warp per query, pulled from an atomic work counter.  The first find_path
-//                  mapping; kept selectable (HBN_FP_G=warp) and as the 2048-entry open-list
-//                  tier of k_astar_g.  The default is k_astar_lane (hbn_astar_lane.cuh): one
-//                  query per lane, search state in HBM.
-//  k_wall<..>      same workspace scheme for findDistanceToWall's Dijkstra.
+//  (find_path: hbn_findpath.cuh + hbn_astar_lane.cuh -- one query per lane, search state in HBM)
+//  k_wall<..>      warp per query over a shared / hybrid A* workspace: findDistanceToWall's Dijkstra.
 //  k_trystep_*     one thread per query (64-node BFS in local memory).
 //  k_random<W>     W lanes per sample; both reservoir scans run lane-parallel.
 //  k_random_near<W> get_random_navigable_point_near: the circle / island filter evaluated lane-parallel
@@ -18,7 +15,6 @@
 #include <cuda_runtime.h>
 #include "hbn_query.h"
 #include "hbn_snap.h"
-#include "hbn_astar_warp.cuh"
 
 namespace hbn {
 
@@ -75,9 +71,9 @@ __global__ void __launch_bounds__(256) k_snap(NavView nav, const float* __restri
   }
 }
 
-// Two independent projectToPoly batches in ONE launch (find_path's starts and ends, try_step's
-// start and end): small batches are latency chains, and two half-empty launches back to back
-// cost twice the chain.  Group q serves point q of job a, or point q - a.n of job b.
+// Up to three independent projectToPoly batches in ONE launch (find_path's starts and ends, try_step's
+// start and end, the env step's positions, targets and goals): small batches are latency chains, and
+// half-empty launches back to back cost the chain once each.  Group q serves point q of job a, then b, then c.
 struct SnapJob {
   const float* pts;
   int64_t n;
@@ -86,19 +82,19 @@ struct SnapJob {
 };
 
 template <int W>
-__global__ void __launch_bounds__(256) k_snap_dual(NavView nav, SnapJob a, SnapJob b) {
+__global__ void __launch_bounds__(256) k_snap_dual(NavView nav, SnapJob a, SnapJob b, SnapJob c3) {
   __shared__ uint32_t queue[256 / W][2 * W];
   WarpGroup<W> grp;
   const int gInBlock = threadIdx.x / W;
   const int64_t groupsPerGrid = static_cast<int64_t>(gridDim.x) * (blockDim.x / W);
   const float ext[3] = {2.f, 4.f, 2.f};
-  const int64_t n = a.n + b.n;
+  const int64_t n = a.n + b.n + c3.n;
   for (int64_t q = static_cast<int64_t>(blockIdx.x) * (blockDim.x / W) + gInBlock; q < n; q += groupsPerGrid) {
-    const bool first = q < a.n;
-    const int64_t i = first ? q : q - a.n;
-    const float* pts = first ? a.pts : b.pts;
-    float* out_pts = first ? a.out_pts : b.out_pts;
-    uint32_t* out_g = first ? a.out_g : b.out_g;
+    const SnapJob& job = q < a.n ? a : (q < a.n + b.n ? b : c3);
+    const int64_t i = q < a.n ? q : (q < a.n + b.n ? q - a.n : q - a.n - b.n);
+    const float* pts = job.pts;
+    float* out_pts = job.out_pts;
+    uint32_t* out_g = job.out_g;
     const float c[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
     float rxz = 0.f;
     if (grp.lane() == 0) rxz = snapRadius(nav, c, ext, -1);
@@ -113,6 +109,34 @@ __global__ void __launch_bounds__(256) k_snap_dual(NavView nav, SnapJob a, SnapJ
         out_pts[3 * i + 2] = ok ? r.pt[2] : nanF();
       }
       if (out_g) out_g[i] = r.g;
+    }
+  }
+}
+
+// projectToPoly of the points whose flag is set (the env step's fix-up: positions tryStep nudged).
+template <int W>
+__global__ void __launch_bounds__(256) k_snap_flagged(NavView nav, const float* __restrict__ pts,
+                                                      const uint8_t* __restrict__ flag, int64_t n,
+                                                      float* __restrict__ out_pts, uint32_t* __restrict__ out_g) {
+  __shared__ uint32_t queue[256 / W][2 * W];
+  WarpGroup<W> grp;
+  const int gInBlock = threadIdx.x / W;
+  const int64_t groupsPerGrid = static_cast<int64_t>(gridDim.x) * (blockDim.x / W);
+  const float ext[3] = {2.f, 4.f, 2.f};
+  for (int64_t q = static_cast<int64_t>(blockIdx.x) * (blockDim.x / W) + gInBlock; q < n; q += groupsPerGrid) {
+    if (!flag[q]) continue;  // uniform within the group
+    const float c[3] = {pts[3 * q], pts[3 * q + 1], pts[3 * q + 2]};
+    float rxz = 0.f;
+    if (grp.lane() == 0) rxz = snapRadius(nav, c, ext, -1);
+    rxz = grp.shfl(rxz, 0);
+    const Nearest r = findNearestPoly(nav, grp, c, ext, -1, queue[gInBlock], rxz);
+    grp.sync();
+    if (grp.lane() == 0) {
+      const bool ok = r.g != kNoPoly;
+      out_pts[3 * q] = ok ? r.pt[0] : nanF();
+      out_pts[3 * q + 1] = ok ? r.pt[1] : nanF();
+      out_pts[3 * q + 2] = ok ? r.pt[2] : nanF();
+      out_g[q] = r.g;
     }
   }
 }
@@ -149,192 +173,6 @@ __device__ __forceinline__ AStarWs wsCarveHybrid(void* sm, void* gl, int cap) {
   w.cap = cap;
   w.hashMask = 2 * cap - 1;
   return w;
-}
-
-struct FindPathArgs {
-  const float* starts;    // requested points
-  const float* ends;
-  const uint32_t* sG;     // projectToPoly results
-  const float* sPt;
-  const uint32_t* eG;
-  const float* ePt;
-  int64_t n;              // total queries (when work == nullptr)
-  const uint32_t* work;   // optional list of query indices
-  const uint32_t* workCount;
-  uint32_t* counter;      // atomic work cursor
-  uint32_t* overflow;     // queries that outgrew this tier
-  uint32_t* overflowCount;
-  float* out_dist;
-  int32_t* out_npts;
-  float* out_pts;
-  int max_pts;
-  uint32_t* out_corridor;
-  int32_t* out_ncorridor;
-  uint32_t* out_status;
-  char* scratch;          // global workspace, one slot per warp of the grid (hybrid)
-  int fastFail;
-  // optional work counters (HBN_FP_COUNT_WORK): [0] expanded polys, [1] their links,
-  // [2] their non-null neighbours, [3] corridor polys, [4] corridor links, [5] path points,
-  // [6] queries that ran A*, [7] queries
-  unsigned long long* workCtr;
-  int startDiv;           // > 1: query q starts at point q / startDiv (multi-goal: [n, g] pairs)
-  // mapped host memory: [0] number of watchdog trips (kernel bugs), [1] a query index, [2] where
-  unsigned int* fault;
-};
-
-// One warp per query (hbn_astar_warp.cuh); WPB warps per block, each with its own shared
-// table + heap and its own slot of the global node-record scratch.  OC = open-list capacity of
-// this tier; a query whose open list outgrows it is appended to the overflow list and re-run
-// from scratch by the next tier (the search is deterministic).
-template <int OC, int WPB>
-__global__ void __launch_bounds__(32 * WPB) k_findpath_w(NavView nav, FindPathArgs a) {
-  extern __shared__ __align__(16) char smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const size_t slot = static_cast<size_t>(blockIdx.x) * WPB + warp;
-  const WarpWs<OC> ws = WarpWs<OC>::carve(smem + static_cast<size_t>(warp) * WarpWs<OC>::sharedBytes(),
-                                          a.scratch + slot * WarpWs<OC>::globalBytes());
-  // after the search the heap area holds the corridor, the table area the staged portals
-  uint32_t* pathG = reinterpret_cast<uint32_t*>(ws.heap - 1);
-  uint32_t* pathVia = pathG + kMaxPathPolys;
-  PortalRec* staged = reinterpret_cast<PortalRec*>(ws.tab);
-  static_assert((OC + 2) * sizeof(HeapEnt) >= 2 * kMaxPathPolys * 4, "corridor buffers");
-  static_assert(kTabSize * 4 >= kMaxPathPolys * sizeof(PortalRec), "portal staging");
-  const uint32_t total = a.work ? *a.workCount : static_cast<uint32_t>(a.n);
-  for (;;) {
-    uint32_t wi = 0;
-    if (lane == 0) wi = atomicAdd(a.counter, 1u);
-    wi = __shfl_sync(0xffffffffu, wi, 0);
-    if (wi >= total) break;
-    const int64_t q = a.work ? a.work[wi] : wi;
-    const long long tq0 = clock64();
-    const int64_t qs = a.startDiv > 1 ? q / a.startDiv : q;
-    const uint32_t sG = a.sG[qs], eG = a.eG[q];
-    const float rs[3] = {a.starts[3 * qs], a.starts[3 * qs + 1], a.starts[3 * qs + 2]};
-    const float re[3] = {a.ends[3 * q], a.ends[3 * q + 1], a.ends[3 * q + 2]};
-    const float sp[3] = {a.sPt[3 * qs], a.sPt[3 * qs + 1], a.sPt[3 * qs + 2]};
-    const float ep[3] = {a.ePt[3 * q], a.ePt[3 * q + 1], a.ePt[3 * q + 2]};
-    float* outPts = a.out_pts ? a.out_pts + static_cast<size_t>(q) * a.max_pts * 3 : nullptr;
-    uint32_t* outCorr = a.out_corridor ? a.out_corridor + static_cast<size_t>(q) * kMaxPathPolys : nullptr;
-    // findPathInternal, PF.cpp:1426-1468 (same decision sequence as hbn_query.h findPathInternal)
-    float dist = infF();
-    int npts = 0, ncorr = 0;
-    uint32_t stA = 0, stS = 0;
-    WarpSearch sr;
-    sr.expanded = sr.links = sr.neighbours = 0;
-    uint32_t corrLinks = 0;
-    bool overflow = false;
-    do {
-      if (sG == kNoPoly || eG == kNoPoly) break;
-      if (vfuzzyEq(sp, ep)) {  // PF.cpp:1434-1436
-        dist = 0.f;
-        npts = 2;
-        if (outPts && lane == 0) {
-          if (a.max_pts > 0) { outPts[0] = sp[0]; outPts[1] = sp[1]; outPts[2] = sp[2]; }
-          if (a.max_pts > 1) { outPts[3] = ep[0]; outPts[4] = ep[1]; outPts[5] = ep[2]; }
-        }
-        break;
-      }
-      const int32_t si = nav.polys[sG].island, ei = nav.polys[eG].island;
-      if (si < 0 || si != ei) break;  // hasConnection, PF.cpp:209-221
-      int first = 0;                  // corridor = pathG[first .. first + ncorr)
-      int fullLen = 1;
-      if (sG == eG) {                 // DQ.cpp:996-1001
-        if (lane == 0) { pathG[0] = sG; pathVia[0] = kNoPoly; }
-        ncorr = 1;
-        stA = kDtSuccess;
-        __syncwarp();
-      } else {
-        if (!vfinite(sp) || !vfinite(ep)) { stA = kDtFailure | kDtInvalidParam; break; }
-        sr = astarWarp<OC>(nav, ws, sG, eG, sp, ep, a.fastFail != 0);
-        if (sr.status == kSearchOverflow) { overflow = true; break; }
-        if (sr.status == kSearchWatchdog) {
-          if (lane == 0) { atomicAdd(a.fault, 1u); a.fault[1] = static_cast<unsigned>(q); a.fault[2] = 1u | (sr.expanded & 0x40000000u) | (OC << 8); }
-          stA = kDtFailure;
-          break;
-        }
-        // getPathToNode, DQ.cpp:1167-1205: walk the parent chain from the end; the circular
-        // buffer keeps the kMaxPathPolys polys nearest the start
-        __syncwarp();
-        if (lane == 0) {
-          int k = 0;
-          uint32_t cur = sr.lastBest;
-          for (;;) {
-            const uint4 nb = reinterpret_cast<const uint4*>(&ws.rec[cur])[1];
-            const int idx = (kMaxPathPolys - 1 - k) & (kMaxPathPolys - 1);
-            pathG[idx] = ws.tab[cur] & kNodeGMask;
-            pathVia[idx] = nb.z;
-            corrLinks += nb.y >> 27;
-            k++;
-            if (!nb.w) break;  // start node
-            if (k > kTabSize) {  // a parent cycle would be a bug
-              atomicAdd(a.fault, 1u); a.fault[1] = static_cast<unsigned>(q); a.fault[2] = 2u;
-              break;
-            }
-            cur = nb.w - 1;
-          }
-          fullLen = k;
-        }
-        fullLen = __shfl_sync(0xffffffffu, fullLen, 0);
-        __syncwarp();
-        ncorr = fullLen < kMaxPathPolys ? fullLen : kMaxPathPolys;
-        first = (kMaxPathPolys - fullLen) & (kMaxPathPolys - 1);
-        stA = sr.status | ((fullLen > kMaxPathPolys) ? kDtBufferTooSmall : 0u);
-      }
-      if (outCorr)
-        for (int i = lane; i < ncorr; i += 32)
-          outCorr[i] = nav.polys[pathG[(first + i) & (kMaxPathPolys - 1)]].ref;
-      if (stA != kDtSuccess || ncorr == 0) break;  // PF.cpp:1450
-      // here fullLen <= kMaxPathPolys, so the corridor is contiguous from `first`
-      for (int i = lane; i + 1 < ncorr; i += 32) staged[i] = nav.portals[pathVia[first + i + 1]];
-      __syncwarp();
-      if (lane == 0) {
-        Funnel f;
-        f.out = outPts;
-        f.maxOut = a.max_pts;
-        stS = funnelStraightPath(nav, rs, re, pathG + first, pathVia + first + 1, ncorr, f, staged);
-        npts = f.count;
-        if (stS == kDtSuccess && f.count != 0) dist = f.length;  // PF.cpp:1459
-      }
-      dist = __shfl_sync(0xffffffffu, dist, 0);
-      npts = __shfl_sync(0xffffffffu, npts, 0);
-      stS = __shfl_sync(0xffffffffu, stS, 0);
-    } while (false);
-    __syncwarp();
-    if (lane == 0) {
-      if (overflow) {
-        const uint32_t o = atomicAdd(a.overflowCount, 1u);
-        a.overflow[o] = static_cast<uint32_t>(q);
-      } else {
-        const bool found = dist < infF();
-        a.out_dist[q] = dist;
-        if (a.out_npts) a.out_npts[q] = found ? npts : 0;
-        if (a.out_ncorridor) a.out_ncorridor[q] = ncorr;
-        if (a.out_status) {
-          a.out_status[2 * q] = stA;
-          a.out_status[2 * q + 1] = stS;
-        }
-        {  // slowest query so far (debug aid): fault[4] = kilo-cycles, [5] = query, [6] = expansions
-          const unsigned kc = static_cast<unsigned>((clock64() - tq0) >> 10);
-          if (kc > a.fault[4] && atomicMax(a.fault + 4, kc) < kc) {
-            a.fault[5] = static_cast<unsigned>(q);
-            a.fault[6] = sr.expanded;
-            a.fault[7] = OC;
-          }
-        }
-        if (a.workCtr) {
-          atomicAdd(a.workCtr + 0, static_cast<unsigned long long>(sr.expanded));
-          atomicAdd(a.workCtr + 1, static_cast<unsigned long long>(sr.links));
-          atomicAdd(a.workCtr + 2, static_cast<unsigned long long>(sr.neighbours));
-          atomicAdd(a.workCtr + 3, static_cast<unsigned long long>(ncorr));
-          atomicAdd(a.workCtr + 4, static_cast<unsigned long long>(corrLinks));
-          atomicAdd(a.workCtr + 5, static_cast<unsigned long long>(found ? npts : 0));
-          atomicAdd(a.workCtr + 6, static_cast<unsigned long long>(sr.expanded ? 1 : 0));
-          atomicAdd(a.workCtr + 7, 1ull);
-        }
-      }
-    }
-    __syncwarp();
-  }
 }
 
 // findPath(MultiGoalShortestPath&) goal loop (PF.cpp:1541-1569) over precomputed pair distances:
@@ -509,6 +347,40 @@ __global__ void __launch_bounds__(256) k_trystep_b(NavView nav, const float* __r
   out[3 * q] = ep[0];
   out[3 * q + 1] = ep[1];
   out[3 * q + 2] = ep[2];
+}
+
+// The env step (try_step, then find_path from the new position: simulator.py:660-673 + habitat-lab's
+// geodesic reward): phase B of tryStep that also hands find_path its start projection, so the new
+// position is not projected a second time.  Three cases: tryStep returned `start` unchanged -> the
+// projection of `start` made for phase A; the end point as phase A left it -> the projection of that
+// point made for phase B (e2G, e2Pt); the end point nudged towards the poly centre (PF.cpp:1700-1719)
+// -> flagged for k_snap_flagged.
+__global__ void __launch_bounds__(256) k_envstep_b(NavView nav, const float* __restrict__ starts,
+                                                   const uint32_t* __restrict__ sG, const float* __restrict__ sPt,
+                                                   const uint32_t* __restrict__ e2G, const float* __restrict__ e2Pt,
+                                                   const uint32_t* __restrict__ lastPoly,
+                                                   const float* __restrict__ endPoint, int64_t n,
+                                                   float* __restrict__ out, uint32_t* __restrict__ fpG,
+                                                   float* __restrict__ fpPt, uint8_t* __restrict__ flag) {
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const uint32_t last = lastPoly[q];
+  if (last == kNoPoly) {
+    out[3 * q] = starts[3 * q]; out[3 * q + 1] = starts[3 * q + 1]; out[3 * q + 2] = starts[3 * q + 2];
+    fpG[q] = sG[q];
+    fpPt[3 * q] = sPt[3 * q]; fpPt[3 * q + 1] = sPt[3 * q + 1]; fpPt[3 * q + 2] = sPt[3 * q + 2];
+    flag[q] = 0;
+    return;
+  }
+  const float e0[3] = {endPoint[3 * q], endPoint[3 * q + 1], endPoint[3 * q + 2]};
+  float ep[3] = {e0[0], e0[1], e0[2]};
+  tryStepPhaseB(nav, sG[q], e2G[q], last, ep);
+  out[3 * q] = ep[0]; out[3 * q + 1] = ep[1]; out[3 * q + 2] = ep[2];
+  const bool same = __float_as_uint(ep[0]) == __float_as_uint(e0[0]) && __float_as_uint(ep[1]) == __float_as_uint(e0[1]) &&
+                    __float_as_uint(ep[2]) == __float_as_uint(e0[2]);
+  fpG[q] = e2G[q];
+  fpPt[3 * q] = e2Pt[3 * q]; fpPt[3 * q + 1] = e2Pt[3 * q + 1]; fpPt[3 * q + 2] = e2Pt[3 * q + 2];
+  flag[q] = same ? 0 : 1;
 }
 
 // ------------------------------------------------------------------------------------

@@ -280,9 +280,10 @@ class PathFinder:
         return True
 
     def load_from_tiles(self, tiles, orig, tile_width, tile_height, max_tiles, max_polys,
-                        poly_islands=None) -> bool:
+                        poly_islands=None, island_radii=None) -> bool:
         """Hand-over of a live dtNavMesh's finalised tiles (hbn_navmesh_create_from_tiles).
-        tiles: iterable of (tile_ref, bytes)."""
+        tiles: iterable of (tile_ref, bytes); poly_islands / island_radii: the caller's
+        IslandSystem (island id per poly in tile-table / poly order; radius per island)."""
         tiles = list(tiles)
         arr = (_lib.TileBlob * len(tiles))()
         keep = []
@@ -296,21 +297,49 @@ class PathFinder:
         isl = None
         if poly_islands is not None:
             isl = np.ascontiguousarray(poly_islands, dtype=np.int32)
+        rad = None
+        if island_radii is not None:
+            rad = np.ascontiguousarray(island_radii, dtype=np.float32)
         h = C.c_void_p()
         check(_lib.lib().hbn_navmesh_create_from_tiles(arr, len(tiles), p5, int(max_tiles), int(max_polys),
                                                        isl.ctypes.data if isl is not None else None,
+                                                       rad.ctypes.data if rad is not None else None,
+                                                       len(rad) if rad is not None else 0,
                                                        self._device, C.byref(h)))
         self._adopt(h)
         self._image = None
         return True
 
+    def save_nav_mesh_bytes(self) -> bytes:
+        """The MSET v2 image PathFinder::saveNavMesh (PathFinder.cpp:1177-1223) writes for the navmesh
+        this handle holds -- links connected, zero-area polys disabled -- whether it was loaded from an
+        image or handed over as live tiles (hbn_navmesh_save_mset)."""
+        h = self._need()
+        L = _lib.lib()
+        n = L.hbn_navmesh_save_mset(h, None, 0)
+        if n < 0:
+            raise RuntimeError((L.hbn_last_error() or b"").decode())
+        buf = C.create_string_buffer(n)
+        L.hbn_navmesh_save_mset(h, buf, n)
+        return buf.raw
+
     def save_nav_mesh(self, path: str) -> bool:
-        """PathFinder::saveNavMesh, PathFinder.cpp:1177-1223 (re-emits the loaded MSET image)."""
-        if not self._image:
+        """PathFinder::saveNavMesh, PathFinder.cpp:1177-1223: false without a navmesh or without
+        NavMeshSettings (a handle made from live tiles needs set_nav_mesh_settings_bytes first)."""
+        if not self._h:
+            return False
+        try:
+            data = self.save_nav_mesh_bytes()
+        except RuntimeError:
             return False
         with open(path, "wb") as f:
-            f.write(self._image)
+            f.write(data)
         return True
+
+    def set_nav_mesh_settings_bytes(self, raw56: bytes) -> None:
+        """the 56-byte NavMeshSettings block (PF.h:137-299) of a navmesh handed over as live tiles"""
+        assert len(raw56) == 56
+        check(_lib.lib().hbn_navmesh_set_settings(self._need(), raw56))
 
     def build_navmesh_from_triangles(self, *a, **k):
         raise NotImplementedError(
@@ -541,6 +570,48 @@ class PathFinder:
                                         idx.ctypes.data, npts.ctypes.data if npts is not None else None,
                                         pts.ctypes.data if pts is not None else None, max_points))
         return dict(geodesic_distance=dist, closest_end_point_index=idx, num_points=npts, points=pts)
+
+    def set_option(self, key: str, value: int) -> None:
+        """hbn_navmesh_set_option: "lane_scratch_bytes", "lane_cfg", "blocks_per_sm", "lane_spread",
+        "snap_spread", "snap_dual", "snap_group", "snap_cap", "nvtx"."""
+        check(_lib.lib().hbn_navmesh_set_option(self._need(), key.encode(), int(value)))
+
+    def reserve(self, n: int) -> None:
+        """Size every scratch buffer for batches of up to n queries (hbn_navmesh_reserve): later
+        calls of that size only enqueue kernels (no allocation, capturable into CUDA graphs)."""
+        check(_lib.lib().hbn_navmesh_reserve(self._need(), int(n)))
+
+    @property
+    def scratch_bytes(self) -> int:
+        return int(_lib.lib().hbn_navmesh_scratch_bytes(self._need()))
+
+    def env_steps(self, positions, targets, goals, allow_sliding: bool = True):
+        """One PointNav environment step for N envs (simulator.py:660-673 + habitat-lab's geodesic
+        reward): new_pos = try_step(positions, targets), then geodesic_distance(new_pos, goals).
+        Returns (new_pos [N,3], dist [N]); equal bit for bit to try_steps + geodesic_distances.
+        numpy inputs go through hbn_env_step (one CUDA graph replay per call), torch CUDA tensors
+        through hbn_env_step_dev on the current stream."""
+        h = self._need()
+        L = _lib.lib()
+        if _is_torch(positions):
+            torch, dev, (p, t, g), st = self._torch_args(positions.float().reshape(-1, 3), targets.float().reshape(-1, 3),
+                                                         goals.float().reshape(-1, 3))
+            n = p.shape[0]
+            out = torch.empty((n, 3), dtype=torch.float32, device=dev)
+            dist = torch.empty(n, dtype=torch.float32, device=dev)
+            check(L.hbn_env_step_dev(h, p.data_ptr(), t.data_ptr(), g.data_ptr(), n, 1 if allow_sliding else 0,
+                                     out.data_ptr(), dist.data_ptr(), st))
+            return out, dist
+        p = np.ascontiguousarray(np.asarray(positions, np.float32).reshape(-1, 3))
+        t = np.ascontiguousarray(np.asarray(targets, np.float32).reshape(-1, 3))
+        g = np.ascontiguousarray(np.asarray(goals, np.float32).reshape(-1, 3))
+        n = len(p)
+        assert len(t) == n and len(g) == n
+        out = np.empty((n, 3), np.float32)
+        dist = np.empty(n, np.float32)
+        check(L.hbn_env_step(h, p.ctypes.data, t.ctypes.data, g.ctypes.data, n, 1 if allow_sliding else 0,
+                             out.ctypes.data, dist.ctypes.data))
+        return out, dist
 
     def try_steps(self, starts, ends, allow_sliding: bool = True):
         h = self._need()

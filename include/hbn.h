@@ -58,7 +58,11 @@ int hbn_navmesh_create_from_mset(const void* bytes, size_t len, int device, hbn_
  * connected and poly flags final; dtNavMesh::getTile / getTileRef, DetourNavMesh.h:420-470).
  * params5 = {orig[3], tileWidth, tileHeight}; poly_islands (nullable) = island id per poly
  * in (tile table order, poly order), e.g. from IslandSystem::getPolyIsland (PF.cpp:398);
- * when null the islands are recomputed from the given flags (trap T5 in SURVEY.md). */
+ * when null the islands are recomputed from the given flags (trap T5 in SURVEY.md).
+ * island_radii (nullable, n_islands entries; used with poly_islands) = IslandSystem::islandRadius(i)
+ * (PF.cpp:236-239) of the same PathFinder: the reference sums an island's vertices in the order of
+ * its own flood fill over the flags of that moment, which the finalised tiles no longer tell; without
+ * them the radii are recomputed per island id (equal up to f32 summation order). */
 typedef struct {
   const void* data;
   int32_t size;
@@ -66,7 +70,7 @@ typedef struct {
 } hbn_tile_blob;
 int hbn_navmesh_create_from_tiles(const hbn_tile_blob* tiles, int n_tiles, const float* params5,
                                   int max_tiles, int max_polys, const int32_t* poly_islands,
-                                  int device, hbn_navmesh_t* out);
+                                  const float* island_radii, int n_islands, int device, hbn_navmesh_t* out);
 
 void hbn_navmesh_destroy(hbn_navmesh_t nm);
 
@@ -85,6 +89,26 @@ int hbn_navmesh_get_info(hbn_navmesh_t nm, hbn_navmesh_info* out);
 int hbn_navmesh_island_info(hbn_navmesh_t nm, int island, float* radius, float* area);
 /* raw 56-byte NavMeshSettings block (PF.h:137-299) of the MSET image */
 int hbn_navmesh_get_settings(hbn_navmesh_t nm, void* out56);
+/* NavMeshSettings for a handle made from live tiles (PathFinder::Impl::build keeps them,
+ * PF.cpp:926; saveNavMesh refuses to write without them, PF.cpp:1199-1203) */
+int hbn_navmesh_set_settings(hbn_navmesh_t nm, const void* in56);
+/* PathFinder::Impl::saveNavMesh, PF.cpp:1177-1223: the MSET v2 image of the navmesh as the handle
+ * holds it (links connected, zero-area polys disabled), whether it came from an image or from live
+ * tiles.  Two-call pattern: returns the size in bytes (-1: no settings known, see hbn_last_error);
+ * fills `out` when cap is large enough.  Host function. */
+int64_t hbn_navmesh_save_mset(hbn_navmesh_t nm, void* out, int64_t cap);
+/* Tuning knobs of a handle (defaults come from the environment once, at creation):
+ * "lane_scratch_bytes" (cap on the per-lane search state of find_path in HBM; 0 = half of the free
+ * memory; the grid shrinks under the cap), "lane_cfg", "blocks_per_sm", "lane_spread", "snap_spread",
+ * "snap_dual", "snap_group", "snap_cap", "nvtx".  Unknown keys fail with HBN_ERR_INVALID. */
+int hbn_navmesh_set_option(hbn_navmesh_t nm, const char* key, int64_t value);
+/* Sizes every scratch buffer for batches of up to n queries (find_path / try_step / env step pairs,
+ * snap / obstacle points), so that later *_dev calls of that size only enqueue work: no cudaMalloc /
+ * cudaFree, hence no implicit device synchronisation, and they can be captured into CUDA graphs.
+ * Without it the buffers grow on the first call of each size. */
+int hbn_navmesh_reserve(hbn_navmesh_t nm, int64_t n);
+/* device bytes of scratch the handle currently holds (besides the navmesh itself) */
+int64_t hbn_navmesh_scratch_bytes(hbn_navmesh_t nm);
 /* kernels launched through this handle so far (bench.py's gpu_launches evidence) */
 int64_t hbn_navmesh_launch_count(hbn_navmesh_t nm);
 /* Phase timing of hbn_find_path_dev for bench.py's roofline: while enabled, every call
@@ -98,7 +122,7 @@ int hbn_navmesh_phase_times(hbn_navmesh_t nm, double* out_ms2, int64_t* out_call
  * straight-path points, queries that ran A*, queries}.  Synchronises the device. */
 int hbn_navmesh_work_counters(hbn_navmesh_t nm, uint64_t* out8, int reset);
 /* navmesh triangles for build_navmesh_vertices/indices (getNavMeshData, PF.cpp:1898-1968):
- * detail triangles of every walkable poly of `island` (-1 = all), 9 floats each.
+ * detail triangles of every poly of `island` (-1 = all polys), in tile-table / poly order, 9 floats each.
  * Two-call pattern: returns the triangle count; fills `out` when cap_tris is large enough. */
 int64_t hbn_navmesh_triangles(hbn_navmesh_t nm, int island, float* out, int64_t cap_tris);
 
@@ -139,6 +163,13 @@ int hbn_find_path_multigoal_dev(hbn_navmesh_t nm, const float* starts, const flo
 /* tryStep / tryStepNoSliding, PF.cpp:1575-1722 */
 int hbn_try_step_dev(hbn_navmesh_t nm, const float* starts, const float* ends, int64_t n,
                      int allow_sliding, float* out_pts, void* stream);
+
+/* One environment step of habitat-lab's PointNav loop: tryStep(starts[i], targets[i]) (PF.cpp:1575-1722,
+ * simulator.py:660-673) then findPath(new position, goals[i]) for the geodesic reward
+ * (PF.cpp:1414-1468).  Results are those of hbn_try_step_dev followed by hbn_find_path_dev, bit for
+ * bit; the projections are shared between the two and the whole step is 9 kernels. */
+int hbn_env_step_dev(hbn_navmesh_t nm, const float* starts, const float* targets, const float* goals,
+                     int64_t n, int allow_sliding, float* out_pos, float* out_dist, void* stream);
 
 /* closestObstacleSurfacePoint / distanceToClosestObstacle, PF.cpp:1788-1812.
  * out_hit_pos / out_hit_normal nullable. */
@@ -181,6 +212,10 @@ int hbn_find_path_multigoal(hbn_navmesh_t nm, const float* starts, const float* 
                             float* out_pts, int max_pts);
 int hbn_try_step(hbn_navmesh_t nm, const float* starts, const float* ends, int64_t n,
                  int allow_sliding, float* out_pts);
+/* the env step with host buffers: copies + kernels are captured once per (n, allow_sliding) into a
+ * CUDA graph and replayed */
+int hbn_env_step(hbn_navmesh_t nm, const float* starts, const float* targets, const float* goals,
+                 int64_t n, int allow_sliding, float* out_pos, float* out_dist);
 int hbn_closest_obstacle(hbn_navmesh_t nm, const float* pts, int64_t n, float max_radius,
                          float* out_hit_pos, float* out_hit_normal, float* out_hit_dist);
 int hbn_random_points(hbn_navmesh_t nm, uint64_t seed, uint64_t query0, int64_t n,

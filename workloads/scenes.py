@@ -30,6 +30,12 @@ SCENES = {
 }
 
 
+def scene_triangles(name: str):
+    """(vertices [V,3] f32, triangles [T,3] i32) of a named procedural scene"""
+    gen, kw, _tiled = SCENES[name]
+    return gen(**kw)
+
+
 def navmesh_bytes(name: str, cache: bool = True) -> bytes:
     """MSET v2 image of a named scene (built once with the reference Recast, then cached)."""
     path = os.path.join(_CACHE, name + ".navmesh")
