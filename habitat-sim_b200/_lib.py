@@ -7,7 +7,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "lib", "libhbn.so")
+# HBN_LIBRARY: another build of the same library (tools only: csrc/Makefile DIAG=1)
+_SO = os.environ.get("HBN_LIBRARY") or os.path.join(_HERE, "lib", "libhbn.so")
 _lib = None
 
 f32p = C.POINTER(C.c_float)
@@ -63,7 +64,7 @@ SYMBOLS = [
     "hbn_find_path", "hbn_find_path_multigoal", "hbn_try_step", "hbn_closest_obstacle",
     "hbn_random_points", "hbn_random_points_near_dev", "hbn_random_points_near", "hbn_std_sort_order",
     "hbn_navmesh_set_settings", "hbn_navmesh_save_mset", "hbn_navmesh_set_option", "hbn_navmesh_reserve",
-    "hbn_navmesh_scratch_bytes", "hbn_env_step_dev", "hbn_env_step",
+    "hbn_navmesh_scratch_bytes", "hbn_env_step_dev", "hbn_env_step", "hbn_navmesh_set_bounds",
 ]
 
 
@@ -99,6 +100,7 @@ def lib():
         l.hbn_navmesh_save_mset.restype = C.c_int64
         l.hbn_navmesh_save_mset.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         l.hbn_navmesh_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
+        l.hbn_navmesh_set_bounds.argtypes = [C.c_void_p, C.c_void_p]
         l.hbn_navmesh_reserve.argtypes = [C.c_void_p, C.c_int64]
         l.hbn_navmesh_scratch_bytes.restype = C.c_int64
         l.hbn_navmesh_scratch_bytes.argtypes = [C.c_void_p]

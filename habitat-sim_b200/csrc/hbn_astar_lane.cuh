@@ -31,7 +31,11 @@ __device__ __forceinline__ void astarLaneBody(const NavView& nav, const SearchAr
   extern __shared__ __align__(16) char smem[];
   const int lane = threadIdx.x;
   const uint32_t ltMask = (1u << lane) - 1u;
-  const size_t slotId = static_cast<size_t>(blockIdx.x) * 32 + lane;
+  // lane slots are numbered over the lanes that take queries: a batch spread over many warps
+  // (laneLimit < 32) does not need search state for the idle lanes
+  const int activeLanes = (a.laneLimit > 0 && a.laneLimit < 32) ? a.laneLimit : 32;
+  const bool hasSlot = lane < activeLanes;
+  const size_t slotId = static_cast<size_t>(blockIdx.x) * activeLanes + (hasSlot ? lane : 0);
   LaneSearch<32, TS, CH, V> s;
   s.K = reinterpret_cast<float*>(smem) + lane;
   s.S = reinterpret_cast<uint16_t*>(smem + static_cast<size_t>(TS) * 32 * 4) + lane;
@@ -39,11 +43,11 @@ __device__ __forceinline__ void astarLaneBody(const NavView& nav, const SearchAr
   s.tab = reinterpret_cast<uint16_t*>(sc.tab + slotId * sc.tabBytes);
   s.rec = sc.rec + slotId * kLaneRecBytes;
   s.cv = nullptr;
-  s.gen = sc.gen[slotId];
+  s.gen = hasSlot ? sc.gen[slotId] : 0u;
   // A batch smaller than the grid is spread over more warps (a.laneLimit lanes each): the lanes
   // of a warp diverge in the heap loops, so fewer queries per warp = fewer instructions per step
   // on the latency chain of a small batch.
-  s.mode = (a.laneLimit <= 0 || lane < a.laneLimit) ? kLIdle : kLDone;
+  s.mode = hasSlot ? kLIdle : kLDone;
   s.q = 0; s.endG = 0; s.size = 0; s.nodeCount = 0; s.status = 0; s.xk = 0; s.xcur = 0;
   s.expanded = s.nLinks = s.nNeigh = 0;
   const uint32_t nWork = *a.workCount;
@@ -104,7 +108,7 @@ __device__ __forceinline__ void astarLaneBody(const NavView& nav, const SearchAr
       }
     }
   }
-  sc.gen[slotId] = s.gen;
+  if (hasSlot) sc.gen[slotId] = s.gen;
 }
 
 template <int TS, int MINB, int CH, int V = 1>

@@ -161,20 +161,24 @@ struct LaneSearch {
   // V = 6: 1 + the modify scan looks through the shared part of the heap before the HBM part
   static constexpr bool kScanSharedFirst = V == 6;
   // V = 7: 1 + node-table loads and stores carry an L2 evict_last policy
-  static constexpr bool kTabEvictLast = V == 7 || V >= 10;
+  static constexpr bool kTabEvictLast = V == 7 || (V >= 10 && V < 20) || V == 20;
   // V >= 8: L2 residency by kind of data (profiles/r2_summary.md: with every access at normal priority
   // the 126 MB L2 keeps nothing from one step to the next; 60 % of the read sectors go to DRAM).  Node
   // records are write-once / read-once-much-later: 32 B accesses, no L1 allocation, L2 evict_first.
   // Link records (read-only, a few MB, read by every search): evict_last.
-  static constexpr bool kRecStream = V >= 8;
-  static constexpr bool kLinkKeep = V >= 8;
+  static constexpr bool kRecStream = (V >= 8 && V < 20) || V == 23;  // (V = 20..23: one kind tagged at a time, for ncu's per-class counters)
+  static constexpr bool kLinkKeep = (V >= 8 && V < 20) || V == 22;
   // V >= 9: no closed flag.  The flag only matters when a better path to an allocated node turns up
   // (DQ.cpp:1124-1153: open -> modify, closed -> push again); the modify scan that looks for the node in
   // the heap answers that, so the store of the flag at every pop (a DRAM write-back) is dropped.
   static constexpr bool kNoClosedStore = V >= 9;
   // V >= 11: the heap entries beyond the shared levels (a few hundred bytes per search, touched at
   // nearly every pop and push) are kept in L2 with evict_last as well
-  static constexpr bool kHeapKeep = V >= 11;
+  static constexpr bool kHeapKeep = V == 11 || V == 21;
+  // V = 12: 10, but new records are STORED at normal priority (the best neighbour is usually popped within a
+  // step or two -- that read should still find the record in L2); the pop, their last use, stays evict_first
+  static constexpr bool kRecStoreNormal = V == 12;
+  static constexpr uint32_t kGenMax = kLaneGenMax;
   static_assert((TS & 1) == 1, "TS must be odd");
   // memory of this lane
   float* K;        // shared: heap keys
@@ -225,6 +229,11 @@ struct LaneSearch {
 #endif
     tab[key] = static_cast<uint16_t>(v);
   }
+  // a looked-up table entry: found? / which node
+  HBN_HD bool teFound(const uint32_t te) const { return (te >> kLaneSlotBits) == gen; }
+  static HBN_HD uint32_t teSlot(const uint32_t te) { return te & kLaneSlotMask; }
+  HBN_HD uint32_t lookup(const uint32_t key) const { return tabLoad(key); }
+  HBN_HD void insert(const uint32_t key, const uint32_t slot) const { tabStore(key, (gen << kLaneSlotBits) | slot); }
   HBN_HD LaneRecA* recA(uint32_t s) const { return reinterpret_cast<LaneRecA*>(rec + static_cast<size_t>(s) * 32); }
   HBN_HD LaneRecB* recB(uint32_t s) const { return reinterpret_cast<LaneRecB*>(rec + static_cast<size_t>(s) * 32 + 16); }
   HBN_HD void loadRec(const uint32_t s, LaneRecA& a, LaneRecB& b) const {
@@ -245,6 +254,14 @@ struct LaneSearch {
   }
   HBN_HD void storeRec(const uint32_t s, const LaneRecA& a, const LaneRecB& b) const {
 #if defined(__CUDA_ARCH__)
+    if constexpr (kRecStoreNormal) {
+      asm volatile("st.global.L1::no_allocate.L2::evict_normal.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(
+                       rec + static_cast<size_t>(s) * 32),
+                   "r"(__float_as_uint(a.px)), "r"(__float_as_uint(a.py)), "r"(__float_as_uint(a.pz)),
+                   "r"(__float_as_uint(a.cost)), "r"(b.poly), "r"(b.w1), "r"(b.lnk), "r"(b.w3)
+                   : "memory");
+      return;
+    }
     if constexpr (kRecStream) {
       asm volatile("st.global.L1::no_allocate.L2::evict_first.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(
                        rec + static_cast<size_t>(s) * 32),
@@ -579,7 +596,7 @@ struct LaneSearch {
     const uint32_t slnk = spoly->linkStart | (static_cast<uint32_t>(spoly->linkCount) << 27);
     const float stotal = vdist(sp, ep) * kHScale;
     storeRec(0, LaneRecA{sp[0], sp[1], sp[2], 0.f}, LaneRecB{startG, kLaneNoParent, slnk, 0u});
-    tabStore(spoly->key0, gen << kLaneSlotBits);
+    insert(spoly->key0, 0u);
     hset(0, stotal, 0u);
     size = 1;
     nodeCount = 1;
@@ -618,10 +635,10 @@ struct LaneSearch {
                    const bool fastFail, int* stop, float* opKey, uint32_t* opSlot) {
     const uint32_t nei = lo.nei;
     if ((hi.meta & kLinkDupBit) != 0) {  // an earlier link of this poly may just have created the node
-      te = tabLoad(hi.neiKey);
-      if ((te >> kLaneSlotBits) == gen) ra = loadRecA(te & kLaneSlotMask);
+      te = lookup(hi.neiKey);
+      if (teFound(te)) ra = loadRecA(teSlot(te));
     }
-    const bool found = (te >> kLaneSlotBits) == gen;
+    const bool found = teFound(te);
     uint32_t slot;
     float npos[3];
     if (!found) {  // dtNodePool::getNode, DNode.cpp:121-152: allocation against the pool limit
@@ -633,7 +650,7 @@ struct LaneSearch {
       slot = static_cast<uint32_t>(nodeCount++);
       npos[0] = lo.mx; npos[1] = lo.my; npos[2] = lo.mz;
     } else {
-      slot = te & kLaneSlotMask;
+      slot = teSlot(te);
       npos[0] = ra.px; npos[1] = ra.py; npos[2] = ra.pz;
     }
     // DQ.cpp:1088-1121
@@ -657,7 +674,7 @@ struct LaneSearch {
     storeRec(slot, LaneRecA{npos[0], npos[1], npos[2], cost},
              LaneRecB{nei, bestG | (viaJ << 24), hi.neiLinkStart | ((hi.meta >> kLinkNeiCountShift) << 27),
                       bslot | (1u << 12)});
-    if (!found) tabStore(hi.neiKey, (gen << kLaneSlotBits) | slot);
+    if (!found) insert(hi.neiKey, slot);
     if (heuristic < lastBestCost) {  // DQ.cpp:1154-1159
       lastBestCost = heuristic;
       lastBest = slot;
@@ -804,7 +821,7 @@ struct LaneSearch {
 #endif
       for (int k = 0; k < kLaneChunk; ++k) {
         ra[k] = LaneRecA{0.f, 0.f, 0.f, 0.f};
-        if (cand[k] && (te[k] >> kLaneSlotBits) == gen) ra[k] = loadRecA(te[k] & kLaneSlotMask);
+        if (cand[k] && teFound(te[k])) ra[k] = loadRecA(teSlot(te[k]));
       }
       // cost tests and record updates; the heap operations are queued in link order
       float qKey[kLaneChunk];

@@ -172,10 +172,11 @@ int upload(hbn_navmesh* nm, const std::vector<T>& v, const T** out) {
 // zeroed, generations reset), capped by Options::laneScratchBytes or half of the free device memory:
 // under the cap the grid shrinks and every lane serves more queries.  On any failure both buffers are
 // released, so a later call starts from a clean state.
-int laneScratch(hbn_navmesh* nm, cudaStream_t st, int* blocks, LaneScratch* out) {
+int laneScratch(hbn_navmesh* nm, cudaStream_t st, int* blocks, int lanesPerBlock, LaneScratch* out) {
   const size_t tabB = laneTabBytes(nm->view.numKeys);
   const size_t per = laneScratchBytes(nm->view.numKeys);
-  int64_t want = static_cast<int64_t>(*blocks) * 32;
+  const auto slotsFor = [&](int64_t b) { return (b * lanesPerBlock + 31) / 32 * 32; };
+  int64_t want = slotsFor(*blocks);
   if (want > nm->laneSlots) {
     size_t budget = nm->opt.laneScratchBytes > 0 ? static_cast<size_t>(nm->opt.laneScratchBytes) : 0;
     if (!budget) {
@@ -204,7 +205,7 @@ int laneScratch(hbn_navmesh* nm, cudaStream_t st, int* blocks, LaneScratch* out)
       nm->laneSlots = want;
     }
   }
-  if (static_cast<int64_t>(*blocks) * 32 > nm->laneSlots) *blocks = static_cast<int>(nm->laneSlots / 32);
+  if (slotsFor(*blocks) > nm->laneSlots) *blocks = static_cast<int>(std::max<int64_t>(1, nm->laneSlots / lanesPerBlock));
   const size_t lanes = static_cast<size_t>(nm->laneSlots);
   char* p = static_cast<char*>(nm->wsLane.p);
   out->tab = p;
@@ -227,6 +228,14 @@ const void* laneKernel(int cfg, size_t* shared) {
     HBN_LANE_CASE(30, 63, k_astar_lane<63, 16, 4, 8>)   // records evict_first (32 B accesses), links evict_last
     HBN_LANE_CASE(31, 63, k_astar_lane<63, 16, 4, 9>)   // + no closed-flag store
     HBN_LANE_CASE(35, 63, k_astar_lane<63, 16, 4, 11>)  // + heap tail evict_last (slower)
+    HBN_LANE_CASE(36, 63, k_astar_lane<63, 16, 4, 12>)  // 10 with record stores at normal priority (same time)
+#ifdef HBN_DIAG_KERNELS  // one kind of data tagged at a time: ncu's per-eviction-class L2 counters then read per kind
+    HBN_LANE_CASE(40, 63, k_astar_lane<63, 16, 4, 20>)  // node table
+    HBN_LANE_CASE(41, 63, k_astar_lane<63, 16, 4, 21>)  // heap tail
+    HBN_LANE_CASE(42, 63, k_astar_lane<63, 16, 4, 22>)  // link records
+    HBN_LANE_CASE(43, 63, k_astar_lane<63, 16, 4, 23>)  // node records
+    HBN_LANE_CASE(44, 63, k_astar_lane<63, 16, 4, 24>)  // nothing tagged (no closed-flag store only)
+#endif
     HBN_LANE_CASE(23, 95, k_astar_lane<95, 11, 4, 1>)   // 95 shared heap entries at 11 warps per SM
     HBN_LANE_CASE(34, 95, k_astar_lane<95, 11, 4, 10>)
     default: *shared = laneSharedBytes<kLaneTS>(); return reinterpret_cast<const void*>(&k_astar_lane<kLaneTS, kLaneMinB, 4, kLaneV>);
@@ -297,12 +306,6 @@ int finishCreate(HostNavMesh& meshIn, const int32_t* islands, const float* radii
   up(f.tileIslCnt, &v.tileIslCnt);
   if (rc != HBN_OK) return rc;
   nm->view = v;
-  if (const char* e = getenv("HBN_L2_FETCH")) {  // experiment: L2 fetch granularity (32 / 64 / 128 B)
-    CK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, static_cast<size_t>(atoi(e))));
-    size_t got = 0;
-    cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
-    fprintf(stderr, "[hbn] L2 fetch granularity %zu\n", got);
-  }
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   nm->smCount = prop.multiProcessorCount;
@@ -334,8 +337,7 @@ int finishCreate(HostNavMesh& meshIn, const int32_t* islands, const float* radii
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wall<kCapL, kWsHybrid>, threads, smL));
   nm->blocksWallL = std::max(1, occ) * nm->smCount;
   // global scratch: one slot per resident warp
-  rc = nm->wsL.ensure(static_cast<size_t>(nm->blocksWallL) * kFpWarps * wsGlobalBytes(kCapL, kWsHybrid));
-  if (rc == HBN_OK) rc = nm->counters.ensure(64);
+  rc = nm->counters.ensure(64);
   if (rc == HBN_OK) rc = nm->work.ensure(64);
   if (rc == HBN_OK) {
     if (cudaHostAlloc(reinterpret_cast<void**>(&nm->faultHost), 64, cudaHostAllocMapped) != cudaSuccess ||
@@ -585,6 +587,13 @@ int hbn_navmesh_island_info(hbn_navmesh_t nm, int island, float* radius, float* 
   return HBN_OK;
 }
 
+int hbn_navmesh_set_bounds(hbn_navmesh_t nm, const float* bounds6) {
+  if (!nm || !bounds6) return fail(HBN_ERR_INVALID, "null argument");
+  std::lock_guard<std::recursive_mutex> lk(nm->mu);
+  memcpy(nm->flat.bounds, bounds6, 24);
+  return HBN_OK;
+}
+
 int hbn_navmesh_set_settings(hbn_navmesh_t nm, const void* in56) {
   if (!nm || !in56) return fail(HBN_ERR_INVALID, "null argument");
   std::lock_guard<std::recursive_mutex> lk(nm->mu);
@@ -647,7 +656,9 @@ int hbn_navmesh_reserve(hbn_navmesh_t nm, int64_t n) {
   DeviceGuard g(nm->device);
   std::lock_guard<std::recursive_mutex> lk(nm->mu);
   int rc;
-  if ((rc = envStepReserve(nm, n)) || (rc = nm->lists.ensure(n * 4))) return rc;
+  if ((rc = envStepReserve(nm, n)) || (rc = nm->lists.ensure(n * 4)) || (rc = nm->io.ensure(n * 64 + 8192)) ||
+      (rc = nm->wsL.ensure(static_cast<size_t>(nm->blocksWallL) * kFpWarps * wsGlobalBytes(kCapL, kWsHybrid))))
+    return rc;
   if (n >= kSnapSmall) {  // the candidate-list snap pipeline's scratch
     const int64_t cmax = std::min(n, kSnapChunk);
     const size_t cap = nm->opt.snapCap > 0 ? static_cast<size_t>(nm->opt.snapCap) : static_cast<size_t>(cmax) * kSnapAvgCap;
@@ -882,10 +893,8 @@ static int findPathLaunch(hbn_navmesh_t nm, const float* starts, const float* en
       int lanes = 32, blocks = 1;
       laneGrid(nm, cn, &lanes, &blocks);
       LaneScratch sc{};
-      if ((rc = laneScratch(nm, st, &blocks, &sc))) return rc;
-      // fewer lane slots than the grid wanted (memory cap): every active lane takes more queries
-      if (static_cast<int64_t>(blocks) * lanes < std::min<int64_t>(cn, static_cast<int64_t>(nm->blocksFpLane) * 32) && lanes < 32)
-        lanes = static_cast<int>(std::min<int64_t>(32, (cn + blocks - 1) / blocks));
+      // (under a memory cap the grid comes back smaller: every lane then takes more queries)
+      if ((rc = laneScratch(nm, st, &blocks, lanes, &sc))) return rc;
       ga.laneLimit = lanes;
       size_t smLane = 0;
       const void* fn = laneKernel(nm->opt.laneCfg, &smLane);
@@ -1064,7 +1073,7 @@ static int envStepReserve(hbn_navmesh* nm, int64_t n) {
   int lanes = 32, blocks = 1;
   laneGrid(nm, n, &lanes, &blocks);
   LaneScratch sc{};
-  return laneScratch(nm, nm->stream, &blocks, &sc);
+  return laneScratch(nm, nm->stream, &blocks, lanes, &sc);
 }
 
 // One environment step of the PointNav loop (simulator.py:660-673 + the geodesic reward): tryStep from
@@ -1127,7 +1136,9 @@ int hbn_closest_obstacle_dev(hbn_navmesh_t nm, const float* pts, int64_t n, floa
   NvtxRange nv(nm->opt.nvtx, "hbn_closest_obstacle");
   CallOrder order(nm, st);
   int rc;
-  if ((rc = nm->sG.ensure(n * 4)) || (rc = nm->sPt.ensure(n * 12)) || (rc = nm->lists.ensure(n * 4))) return rc;
+  if ((rc = nm->sG.ensure(n * 4)) || (rc = nm->sPt.ensure(n * 12)) || (rc = nm->lists.ensure(n * 4)) ||
+      (rc = nm->wsL.ensure(static_cast<size_t>(nm->blocksWallL) * kFpWarps * wsGlobalBytes(kCapL, kWsHybrid))))
+    return rc;
   uint32_t* cnt = static_cast<uint32_t*>(nm->counters.p);
   CK(cudaMemsetAsync(cnt, 0, 64, st));
   if ((rc = snapLaunch(nm, pts, nullptr, n, static_cast<float*>(nm->sPt.p), static_cast<uint32_t*>(nm->sG.p),

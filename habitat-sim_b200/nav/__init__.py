@@ -18,7 +18,7 @@ from .._lib import HbnError, check
 
 from .sharding import gather as gather_shards, shard_slice, shard_slices  # noqa: E402,F401
 
-__all__ = ["shard_slices", "shard_slice", "gather_shards", "PathFinder", "ShortestPath", "MultiGoalShortestPath", "HitRecord", "NavMeshSettings",
+__all__ = ["shard_slices", "shard_slice", "gather_shards", "MultiGpuPathFinder", "PathFinder", "ShortestPath", "MultiGoalShortestPath", "HitRecord", "NavMeshSettings",
            "GreedyFollowerCodes", "GreedyGeodesicFollowerImpl", "GreedyGeodesicFollower",
            "GreedyGeodesicFollowerBatch", "GreedyGeodesicFollowerBatchImpl", "HbnError",
            "multigoal_find_path", "std_sort_order"]
@@ -280,7 +280,7 @@ class PathFinder:
         return True
 
     def load_from_tiles(self, tiles, orig, tile_width, tile_height, max_tiles, max_polys,
-                        poly_islands=None, island_radii=None) -> bool:
+                        poly_islands=None, island_radii=None, bounds=None) -> bool:
         """Hand-over of a live dtNavMesh's finalised tiles (hbn_navmesh_create_from_tiles).
         tiles: iterable of (tile_ref, bytes); poly_islands / island_radii: the caller's
         IslandSystem (island id per poly in tile-table / poly order; radius per island)."""
@@ -308,6 +308,10 @@ class PathFinder:
                                                        self._device, C.byref(h)))
         self._adopt(h)
         self._image = None
+        if bounds is not None:  # PathFinder::bounds() of a freshly built mesh: the input geometry's
+            b6 = np.ascontiguousarray(np.concatenate([np.asarray(bounds[0], np.float32), np.asarray(bounds[1], np.float32)]))
+            check(_lib.lib().hbn_navmesh_set_bounds(h, b6.ctypes.data))
+            check(_lib.lib().hbn_navmesh_get_info(self._h, C.byref(self._info)))
         return True
 
     def save_nav_mesh_bytes(self) -> bytes:
@@ -836,6 +840,7 @@ class PathFinder:
         return list(range(3 * n))
 
 
+from .multigpu import MultiGpuPathFinder  # noqa: E402,F401
 from .greedy_follower import (GreedyFollowerCodes, GreedyGeodesicFollower,  # noqa: E402
                               GreedyGeodesicFollowerBatch, GreedyGeodesicFollowerBatchImpl,
                               GreedyGeodesicFollowerImpl)

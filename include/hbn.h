@@ -11,7 +11,10 @@
  *  - plain pointers and sizes only; every function returns an hbn_status (0 = ok) and never
  *    throws; hbn_last_error() gives the message of the calling thread's last failure.
  *  - `*_dev` entry points take DEVICE pointers and a cudaStream_t (as void*); they enqueue
- *    kernels only and never synchronise, so they can be captured in CUDA graphs.
+ *    kernels and never synchronise.  The handle's scratch grows on the first call of a size
+ *    (cudaMalloc / cudaFree); after hbn_navmesh_reserve(nm, n) calls of up to n queries allocate
+ *    nothing and can be captured in CUDA graphs.  Calls on one handle from different streams
+ *    are ordered by the handle (an event per call), not run concurrently.
  *  - entry points without the suffix take HOST pointers, do the H2D/D2H copies on the
  *    handle's own stream and return after the results are in the caller's buffers.
  *  - points are float32 xyz triples, y up; poly refs are 32-bit dtPolyRef values
@@ -89,6 +92,10 @@ int hbn_navmesh_get_info(hbn_navmesh_t nm, hbn_navmesh_info* out);
 int hbn_navmesh_island_info(hbn_navmesh_t nm, int island, float* radius, float* area);
 /* raw 56-byte NavMeshSettings block (PF.h:137-299) of the MSET image */
 int hbn_navmesh_get_settings(hbn_navmesh_t nm, void* out56);
+/* PathFinder::bounds() for a handle made from live tiles: a navmesh the reference has just BUILT reports
+ * the bounds of the input geometry (PF.cpp:619-621, 927), a loaded one the union of the tile bounds
+ * (PF.cpp:1160-1170) -- which is what the handle computes by itself.  bounds6 = {min xyz, max xyz}. */
+int hbn_navmesh_set_bounds(hbn_navmesh_t nm, const float* bounds6);
 /* NavMeshSettings for a handle made from live tiles (PathFinder::Impl::build keeps them,
  * PF.cpp:926; saveNavMesh refuses to write without them, PF.cpp:1199-1203) */
 int hbn_navmesh_set_settings(hbn_navmesh_t nm, const void* in56);

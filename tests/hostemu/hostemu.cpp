@@ -233,7 +233,7 @@ static void laneSearchRun(void* h, const float* starts, const float* ends, long 
     if (a.g == kNoPoly || b.g == kNoPoly || vfuzzyEq(a.pt, b.pt)) continue;
     const int32_t si = nav.polys[a.g].island, ei = nav.polys[b.g].island;
     if (si < 0 || si != ei || a.g == b.g || !vfinite(a.pt) || !vfinite(b.pt)) continue;  // k_fp_classify
-    if (s.gen >= kLaneGenMax) {
+    if (s.gen >= s.kGenMax) {
       memset(s.tab, 0, laneTabBytes(nav.numKeys));
       s.gen = 0;
     }
@@ -394,7 +394,7 @@ static long laneLockstep(void* h, const float* starts, const float* ends, long n
     const Nearest t = findNearestPoly(nav, grp, ends + 3 * i, kExt, -1, q);
     if (s.g == kNoPoly || t.g == kNoPoly || s.g == t.g) continue;
     if (nav.polys[s.g].island < 0 || nav.polys[s.g].island != nav.polys[t.g].island) continue;
-    if (a.gen >= kLaneGenMax) {
+    if (a.gen >= a.kGenMax || b.gen >= b.kGenMax) {
       memset(a.tab, 0, laneTabBytes(nav.numKeys)); a.gen = 0;
       memset(b.tab, 0, laneTabBytes(nav.numKeys)); b.gen = 0;
     }

@@ -667,6 +667,77 @@ def test_sharding_gloo_world2():
         assert f"rank {rank} ok" in out
 
 
+class _EmuBackend:
+    """PathFinder-like object over tests/hostemu (the product's query code compiled for the host) for
+    the CPU test of the in-process multi-GPU dispatcher; thread-safe like a real handle is per call."""
+
+    def __init__(self, device):
+        self.device = device
+        self._emu = hostemu()
+        self._h = None
+        self._seed = 0
+        self.calls = []
+
+    def load_nav_mesh_bytes(self, img):
+        self._h = C.c_void_p(self._emu.emu_create(img, C.c_long(len(img))))
+        return bool(self._h)
+
+    def find_paths(self, st, en, max_points=0, corridors=False, exact_status=False):
+        self.calls.append(len(st))
+        d = np.zeros(len(st), np.float32)
+        self._emu.emu_find_path(self._h, P(np.ascontiguousarray(st), f32p), P(np.ascontiguousarray(en), f32p),
+                                C.c_long(len(st)), 2048, 1, P(d, f32p), None, None, 0, None, None, None)
+        return dict(geodesic_distance=d)
+
+    def try_steps(self, st, en, sliding=True):
+        out = np.zeros((len(st), 3), np.float32)
+        self._emu.emu_try_step(self._h, P(np.ascontiguousarray(st), f32p), P(np.ascontiguousarray(en), f32p),
+                               C.c_long(len(st)), 1 if sliding else 0, P(out, f32p))
+        return out
+
+    def env_steps(self, p, t, g, sliding=True):
+        pos = self.try_steps(p, t, sliding)
+        return pos, self.find_paths(pos, g)["geodesic_distance"]
+
+    def random_navigable_points(self, n, max_tries=10, island_index=-1, seed=None, query0=0):
+        out = np.zeros((n, 3), np.float32)
+        refs = np.zeros(n, np.uint32)
+        self._emu.emu_random_points(self._h, C.c_long(n), max_tries, None, C.c_ulonglong(seed), C.c_ulonglong(query0),
+                                    P(out, f32p), P(refs, u32p))
+        return out, refs
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_multi_gpu_dispatcher_split_and_gather(world):
+    """nav.MultiGpuPathFinder on the CPU: `world` backends (host emulation instead of CUDA handles), one
+    worker thread each; a batch is cut into contiguous slices, every backend answers its slice, the
+    results land in one array -- equal to the unsharded answer for any world, including batches smaller
+    than the number of devices and the global-index random streams."""
+    import habitat_sim_b200  # noqa: F401
+    from habitat_sim_b200.nav import MultiGpuPathFinder
+    name = "c2_apartment"
+    img = navmesh_image(name)
+    single = _EmuBackend(0)
+    assert single.load_nav_mesh_bytes(img)
+    mg = MultiGpuPathFinder(devices=range(world), _factory=_EmuBackend)
+    assert mg.load_nav_mesh_bytes(img) and mg.world == world
+    for n in (1, 5, 1001):
+        pts = query_points(name, 3 * n, 90 + n)
+        st, en, gl = pts[:n].copy(), pts[n:2 * n].copy(), pts[2 * n:].copy()
+        want = single.find_paths(st, en)["geodesic_distance"]
+        assert beq(mg.geodesic_distances(st, en), want).all()
+        assert beq(mg.try_steps(st, en), single.try_steps(st, en)).all()
+        wp, wd = single.env_steps(st, en, gl)
+        gp, gd = mg.env_steps(st, en, gl)
+        assert beq(gp, wp).all() and beq(gd, wd).all()
+        rp, rr = mg.random_navigable_points(n, seed=5, query0=40)
+        sp, sr = single.random_navigable_points(n, seed=5, query0=40)
+        assert beq(rp, sp).all() and (rr == sr).all()
+    sizes = [pf.calls[-1] for pf in mg._pfs if pf.calls]
+    assert max(sizes) - min(sizes) <= 1 or world > 1001
+    mg.close()
+
+
 def test_navmesh_settings_json_like_the_reference(tmp_path):
     """NavMeshSettings JSON form (PathFinder.cpp:68-93, io/JsonEspTypes.cpp:287-331): round trip as in
     the reference's tests/test_nav.py:678-695, and the reference's own fixture
