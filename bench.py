@@ -259,7 +259,9 @@ class WallC5(SnapC4):
         Workload.__init__(self, args, rank)
         from workloads.scenes import pointnav_pairs
         self.n = args.queries
-        (self.pts,) = self.cache(f"{self.scene}_wall_{self.n}_{rank}", lambda: [pointnav_pairs(self.geom, self.n, 9 + rank, jitter=0.05)[0]])
+        m = min(self.n, 2_000_000)  # seeded points are generated for 2 M queries and repeated up to the batch size
+        (base,) = self.cache(f"{self.scene}_wall_{m}_{rank}", lambda: [pointnav_pairs(self.geom, m, 9 + rank, jitter=0.05)[0]])
+        self.pts = np.ascontiguousarray(np.tile(base, ((self.n + m - 1) // m, 1))[: self.n])
         self.units = self.n
         self.h2d_bytes, self.d2h_bytes = int(self.pts.nbytes), 4 * self.n
 

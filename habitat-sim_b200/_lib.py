@@ -28,6 +28,11 @@ class HbnError(RuntimeError):
         self.code = code
 
 
+class FollowerParams(C.Structure):
+    _fields_ = [("goal_dist", C.c_float), ("forward_amount", C.c_float), ("sin_half_turn", C.c_double),
+                ("cos_half_turn", C.c_double), ("n_steps", C.c_int32), ("allow_sliding", C.c_int32)]
+
+
 class NavMeshInfo(C.Structure):
     _fields_ = [("device", C.c_int32), ("num_tiles", C.c_int32), ("num_polys", C.c_int32),
                 ("num_links", C.c_int32), ("num_bv_nodes", C.c_int32), ("num_islands", C.c_int32),
@@ -65,6 +70,7 @@ SYMBOLS = [
     "hbn_random_points", "hbn_random_points_near_dev", "hbn_random_points_near", "hbn_std_sort_order",
     "hbn_navmesh_set_settings", "hbn_navmesh_save_mset", "hbn_navmesh_set_option", "hbn_navmesh_reserve",
     "hbn_navmesh_scratch_bytes", "hbn_env_step_dev", "hbn_env_step", "hbn_navmesh_set_bounds",
+    "hbn_follower_best_prims_dev", "hbn_follower_best_prims",
 ]
 
 
@@ -106,6 +112,8 @@ def lib():
         l.hbn_navmesh_scratch_bytes.argtypes = [C.c_void_p]
         vp = C.c_void_p
         for suffix, extra in (("_dev", [vp]), ("", [])):
+            getattr(l, "hbn_follower_best_prims" + suffix).argtypes = [vp, vp, vp, vp, C.c_int64,
+                                                                      C.POINTER(FollowerParams), vp, vp] + extra
             getattr(l, "hbn_env_step" + suffix).argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int, vp, vp] + extra
             getattr(l, "hbn_snap_point" + suffix).argtypes = [vp, vp, vp, C.c_int64, vp, vp, vp] + extra
             getattr(l, "hbn_is_navigable" + suffix).argtypes = [vp, vp, C.c_int64, C.c_float, vp] + extra

@@ -25,17 +25,23 @@ __host__ __device__ constexpr size_t laneSharedBytes() { return static_cast<size
 
 // TS: heap entries per lane in shared memory; MINB: resident one-warp blocks per SM the
 // register allocation must allow; CH: links per load stage; V: heap code variant (LaneSearch).
-template <int TS, int CH, int V>
+// WPB: warps per block.  Every warp is on its own (no block-level synchronisation); blocks of more than
+// one warp only exist because a block costs 1 KB of reserved shared memory: two-warp blocks leave room
+// for 71 instead of 63 heap entries per lane at 16 warps per SM.
+template <int TS, int CH, int V, int WPB = 1>
 __device__ __forceinline__ void astarLaneBody(const NavView& nav, const SearchArgs& a, const LaneScratch& sc) {
   constexpr uint32_t FULL = 0xffffffffu;
-  extern __shared__ __align__(16) char smem[];
-  const int lane = threadIdx.x;
+  extern __shared__ __align__(16) char smemAll[];
+  const int lane = threadIdx.x & 31;
+  const unsigned warpId = blockIdx.x * WPB + (threadIdx.x >> 5);
+  if (warpId >= static_cast<unsigned>(a.numWarps)) return;  // the whole warp
+  char* smem = smemAll + static_cast<size_t>(threadIdx.x >> 5) * laneSharedBytes<TS>();
   const uint32_t ltMask = (1u << lane) - 1u;
   // lane slots are numbered over the lanes that take queries: a batch spread over many warps
   // (laneLimit < 32) does not need search state for the idle lanes
   const int activeLanes = (a.laneLimit > 0 && a.laneLimit < 32) ? a.laneLimit : 32;
   const bool hasSlot = lane < activeLanes;
-  const size_t slotId = static_cast<size_t>(blockIdx.x) * activeLanes + (hasSlot ? lane : 0);
+  const size_t slotId = static_cast<size_t>(warpId) * activeLanes + (hasSlot ? lane : 0);
   LaneSearch<32, TS, CH, V> s;
   s.K = reinterpret_cast<float*>(smem) + lane;
   s.S = reinterpret_cast<uint16_t*>(smem + static_cast<size_t>(TS) * 32 * 4) + lane;
@@ -111,9 +117,9 @@ __device__ __forceinline__ void astarLaneBody(const NavView& nav, const SearchAr
   if (hasSlot) sc.gen[slotId] = s.gen;
 }
 
-template <int TS, int MINB, int CH, int V = 1>
-__global__ void __launch_bounds__(32, MINB) k_astar_lane(NavView nav, SearchArgs a, LaneScratch sc) {
-  astarLaneBody<TS, CH, V>(nav, a, sc);
+template <int TS, int MINB, int CH, int V = 1, int WPB = 1>
+__global__ void __launch_bounds__(32 * WPB, MINB / WPB) k_astar_lane(NavView nav, SearchArgs a, LaneScratch sc) {
+  astarLaneBody<TS, CH, V, WPB>(nav, a, sc);
 }
 
 // The same with the register budget given directly: ptxas turns "MINB one-warp blocks" into 96

@@ -15,6 +15,7 @@
 #include "hbn_findpath.cuh"
 #include "hbn_astar_lane.cuh"
 #include "hbn_snap.cuh"
+#include "hbn_follower.cuh"
 #include <cub/device/device_scan.cuh>
 
 using namespace hbn;
@@ -120,6 +121,7 @@ struct hbn_navmesh {
   bool lastValid = false;
   // scratch (device)
   DevBuf sG, eG, e2G, sPt, ePt, epPt, e2Pt, lastPoly, lists, counters, wsL, io, work, mgDist, mgBounds, mgOrder, mgEnd, mgMask;
+  DevBuf folS, folT, folE, folF, folGeo, folObs, folGeo0, folPos;  // batched follower: primitives of all agents
   DevBuf envG, envPt, envFlag, envPos;  // env step: find_path's start projection, fix-up flags, the goals' polys
   // find_path pipeline: class, cost class, search list, status, corridor rings
   DevBuf fpCls, fpBucket, fpWork, fpStat, fpLen, fpCorr;
@@ -127,7 +129,7 @@ struct hbn_navmesh {
   // lane-per-query search: per-lane node table + records + heap tail in HBM, sized from the batch
   DevBuf wsLane, laneGen;
   int64_t laneSlots = 0;    // lane slots the scratch holds (tables zeroed, generations 0 when allocated)
-  int blocksFpLane = 0;     // resident one-warp blocks of the search kernel (occupancy x SMs)
+  int blocksFpLane = 0;     // resident WARPS of the search kernel (occupancy x SMs); the grid unit of laneGrid / laneScratch
   // pinned staging for the host-buffer entry points
   void* pinned = nullptr;
   size_t pinnedCap = 0;
@@ -220,10 +222,15 @@ int laneScratch(hbn_navmesh* nm, cudaStream_t st, int* blocks, int lanesPerBlock
 // entries in shared memory, resident warps per SM, links per load stage, code variant V of LaneSearch.
 // All are bit-exact (tests/test_zz_tuning_variants.py); the measurements that picked the shipped one are in
 // profiles/r2_summary.md (and profiles/r1_summary.md for the variants deleted since).
-const void* laneKernel(int cfg, size_t* shared) {
+const void* laneKernel(int cfg, size_t* shared, int* wpb) {
+  *wpb = 1;
 #define HBN_LANE_CASE(N, TS, ...) \
   case N: *shared = laneSharedBytes<TS>(); return reinterpret_cast<const void*>(&__VA_ARGS__);
+#define HBN_LANE_CASE_W(N, TS, W, ...) \
+  case N: *shared = laneSharedBytes<TS>() * W; *wpb = W; return reinterpret_cast<const void*>(&__VA_ARGS__);
   switch (cfg) {
+    HBN_LANE_CASE_W(38, 71, 2, k_astar_lane<71, 16, 4, 10, 2>)  // two-warp blocks: 71 shared heap entries at 16 warps per SM
+    HBN_LANE_CASE_W(39, 63, 2, k_astar_lane<63, 16, 4, 10, 2>)
     HBN_LANE_CASE(1, 63, k_astar_lane<63, 16, 4, 1>)    // round 1's kernel: every access at normal L2 priority
     HBN_LANE_CASE(30, 63, k_astar_lane<63, 16, 4, 8>)   // records evict_first (32 B accesses), links evict_last
     HBN_LANE_CASE(31, 63, k_astar_lane<63, 16, 4, 9>)   // + no closed-flag store
@@ -241,6 +248,7 @@ const void* laneKernel(int cfg, size_t* shared) {
     default: *shared = laneSharedBytes<kLaneTS>(); return reinterpret_cast<const void*>(&k_astar_lane<kLaneTS, kLaneMinB, 4, kLaneV>);
   }
 #undef HBN_LANE_CASE
+#undef HBN_LANE_CASE_W
 }
 
 int envInt(const char* name, int dflt) {
@@ -251,12 +259,13 @@ int envInt(const char* name, int dflt) {
 // (re)select the search kernel of Options::laneCfg: shared-memory opt-in, occupancy, grid size
 int laneConfigure(hbn_navmesh* nm) {
   size_t smLane = 0;
-  const void* fn = laneKernel(nm->opt.laneCfg, &smLane);
+  int wpb = 1;
+  const void* fn = laneKernel(nm->opt.laneCfg, &smLane, &wpb);
   CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smLane)));
   CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   int occ = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32, smLane));
-  occ = std::max(1, occ);
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32 * wpb, smLane));
+  occ = std::max(1, occ) * wpb;  // resident warps per SM
   if (nm->opt.blocksPerSm > 0) occ = std::min(occ, nm->opt.blocksPerSm);
   nm->blocksFpLane = occ * nm->smCount;
   return HBN_OK;
@@ -544,6 +553,7 @@ void hbn_navmesh_destroy(hbn_navmesh_t nm) {
   for (DevBuf* b : {&nm->sG, &nm->eG, &nm->e2G, &nm->sPt, &nm->ePt, &nm->epPt, &nm->e2Pt, &nm->lastPoly,
                     &nm->lists, &nm->counters, &nm->wsL, &nm->io, &nm->work, &nm->mgDist,
                     &nm->mgBounds, &nm->mgOrder, &nm->mgEnd, &nm->mgMask, &nm->envG, &nm->envPt, &nm->envFlag, &nm->envPos,
+                    &nm->folS, &nm->folT, &nm->folE, &nm->folF, &nm->folGeo, &nm->folObs, &nm->folGeo0, &nm->folPos,
                     &nm->fpCls, &nm->fpWork, &nm->fpStat,
                     &nm->fpLen, &nm->fpCorr, &nm->fpBucket, &nm->wsLane, &nm->laneGen, &nm->snapCnt, &nm->snapOff,
                     &nm->snapG, &nm->snapQ, &nm->snapD, &nm->snapOut, &nm->snapBest, &nm->snapTmp, &nm->snapTodo})
@@ -643,6 +653,7 @@ int64_t hbn_navmesh_scratch_bytes(hbn_navmesh_t nm) {
   for (const DevBuf* b : {&nm->sG, &nm->eG, &nm->e2G, &nm->sPt, &nm->ePt, &nm->epPt, &nm->e2Pt, &nm->lastPoly,
                           &nm->lists, &nm->counters, &nm->wsL, &nm->io, &nm->work, &nm->mgDist, &nm->mgBounds,
                           &nm->mgOrder, &nm->mgEnd, &nm->mgMask, &nm->envG, &nm->envPt, &nm->envFlag, &nm->envPos,
+                          &nm->folS, &nm->folT, &nm->folE, &nm->folF, &nm->folGeo, &nm->folObs, &nm->folGeo0, &nm->folPos,
                           &nm->fpCls, &nm->fpWork, &nm->fpStat, &nm->fpLen, &nm->fpCorr, &nm->fpBucket, &nm->wsLane,
                           &nm->laneGen, &nm->snapCnt, &nm->snapOff, &nm->snapG, &nm->snapQ, &nm->snapD, &nm->snapOut,
                           &nm->snapBest, &nm->snapTmp, &nm->snapTodo})
@@ -896,10 +907,12 @@ static int findPathLaunch(hbn_navmesh_t nm, const float* starts, const float* en
       // (under a memory cap the grid comes back smaller: every lane then takes more queries)
       if ((rc = laneScratch(nm, st, &blocks, lanes, &sc))) return rc;
       ga.laneLimit = lanes;
+      ga.numWarps = blocks;
       size_t smLane = 0;
-      const void* fn = laneKernel(nm->opt.laneCfg, &smLane);
+      int wpb = 1;
+      const void* fn = laneKernel(nm->opt.laneCfg, &smLane, &wpb);
       void* kargs[] = {&nm->view, &ga, &sc};
-      CK(cudaLaunchKernel(fn, dim3(static_cast<unsigned>(blocks)), dim3(32), kargs, smLane, st));
+      CK(cudaLaunchKernel(fn, dim3(static_cast<unsigned>((blocks + wpb - 1) / wpb)), dim3(32 * wpb), kargs, smLane, st));
       nm->launches++;
       CK(cudaGetLastError());
     }
@@ -1122,6 +1135,59 @@ int hbn_env_step_dev(hbn_navmesh_t nm, const float* starts, const float* targets
   const GivenSnaps given{fpG, fpPt, gG, gPt};
   return findPathLaunch(nm, out_pos, goals, n, 1, out_dist, nullptr, nullptr, 0, nullptr, nullptr, nullptr,
                         kFpGivenSnaps, st, nullptr, &given);
+}
+
+int hbn_closest_obstacle_dev(hbn_navmesh_t nm, const float* pts, int64_t n, float max_radius,
+                             float* out_hit_pos, float* out_hit_normal, float* out_hit_dist,
+                             void* stream);
+
+// GreedyGeodesicFollowerImpl::nextBestPrimAlong for n agents (hbn_follower.cuh): geodesic distance now,
+// the forward target of every primitive, try_step / find_path / closest_obstacle over all of them,
+// reward and selection -- six batched device calls, nothing on the host in between.
+int hbn_follower_best_prims_dev(hbn_navmesh_t nm, const double* rots, const double* poss, const float* goals,
+                                int64_t n, const hbn_follower_params* fp, int32_t* out_prim, float* out_geo,
+                                void* stream) {
+  if (!nm || !fp || (n > 0 && (!rots || !poss || !goals || !out_prim))) return fail(HBN_ERR_INVALID, "null argument");
+  if (n <= 0) return HBN_OK;
+  if (fp->n_steps <= 0 || fp->n_steps > 4096) return fail(HBN_ERR_INVALID, "bad n_steps");
+  const int64_t m = n * 2 * fp->n_steps;
+  if (m >= (1ll << 31)) return fail(HBN_ERR_INVALID, "batch too large");
+  DeviceGuard g(nm->device);
+  std::lock_guard<std::recursive_mutex> lk(nm->mu);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  NvtxRange nv(nm->opt.nvtx, "hbn_follower_best_prims");
+  CallOrder order(nm, st);
+  int rc;
+  if ((rc = nm->folS.ensure(m * 12)) || (rc = nm->folT.ensure(m * 12)) || (rc = nm->folE.ensure(m * 12)) ||
+      (rc = nm->folF.ensure(m * 12)) || (rc = nm->folGeo.ensure(m * 4)) || (rc = nm->folObs.ensure(m * 4)) ||
+      (rc = nm->folGeo0.ensure(n * 4)) || (rc = nm->folPos.ensure(n * 12)))
+    return rc;
+  FollowerParams p{};
+  p.goalDist = fp->goal_dist;
+  p.forwardAmount = fp->forward_amount;
+  p.sinHalf = fp->sin_half_turn;
+  p.cosHalf = fp->cos_half_turn;
+  p.nSteps = fp->n_steps;
+  float* S = static_cast<float*>(nm->folS.p);
+  float* T = static_cast<float*>(nm->folT.p);
+  float* E = static_cast<float*>(nm->folE.p);
+  float* F = static_cast<float*>(nm->folF.p);
+  float* geoAfter = static_cast<float*>(nm->folGeo.p);
+  float* obs = static_cast<float*>(nm->folObs.p);
+  float* geo0 = out_geo ? out_geo : static_cast<float*>(nm->folGeo0.p);
+  float* pos32 = static_cast<float*>(nm->folPos.p);
+  const unsigned ab = static_cast<unsigned>((n + 127) / 128);
+  k_follower_targets<<<ab, 128, 0, st>>>(rots, poss, goals, n, p, pos32, S, T, E);
+  nm->launches++;
+  CK(cudaGetLastError());
+  if ((rc = findPathLaunch(nm, pos32, goals, n, 1, geo0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0, st))) return rc;
+  if ((rc = hbn_try_step_dev(nm, S, T, m, fp->allow_sliding, F, stream))) return rc;
+  if ((rc = findPathLaunch(nm, F, E, m, 1, geoAfter, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0, st))) return rc;
+  if ((rc = hbn_closest_obstacle_dev(nm, F, m, 1.1f * 0.2f, nullptr, nullptr, obs, stream))) return rc;
+  k_follower_select<<<ab, 128, 0, st>>>(geo0, S, T, F, geoAfter, obs, n, p, out_prim);
+  nm->launches++;
+  CK(cudaGetLastError());
+  return HBN_OK;
 }
 
 int hbn_closest_obstacle_dev(hbn_navmesh_t nm, const float* pts, int64_t n, float max_radius,
@@ -1437,6 +1503,21 @@ int hbn_env_step(hbn_navmesh_t nm, const float* starts, const float* targets, co
     nm->lastValid = true;
   }
   return io.finish();
+}
+
+int hbn_follower_best_prims(hbn_navmesh_t nm, const double* rots, const double* poss, const float* goals, int64_t n,
+                            const hbn_follower_params* fp, int32_t* out_prim, float* out_geo) {
+  HOST_PROLOGUE
+  const size_t oR = io.add(n * 32, rots, nullptr);
+  const size_t oP = io.add(n * 24, poss, nullptr);
+  const size_t oG = io.add(n * 12, goals, nullptr);
+  const size_t oO = io.add(n * 4, nullptr, out_prim);
+  const size_t oD = out_geo ? io.add(n * 4, nullptr, out_geo) : 0;
+  if ((rc = io.prepare()) || (rc = io.h2d())) return rc;
+  if ((rc = hbn_follower_best_prims_dev(nm, io.dev<double>(oR), io.dev<double>(oP), io.dev<float>(oG), n, fp,
+                                        io.dev<int32_t>(oO), out_geo ? io.dev<float>(oD) : nullptr, nm->stream)))
+    return rc;
+  return io.d2h();
 }
 
 int hbn_closest_obstacle(hbn_navmesh_t nm, const float* pts, int64_t n, float max_radius,

@@ -43,6 +43,7 @@ struct SearchArgs {
   unsigned long long* workCtr;
   unsigned int* fault;
   int laneLimit;              // k_astar_lane: lanes of a warp that take queries (0 = all 32); small batches spread over more warps
+  int numWarps;               // k_astar_lane: warps of the grid that work (the last block may hold idle ones)
 };
 
 // The search list is ordered by expected cost: a persistent kernel finishes when its longest query does,

@@ -617,6 +617,24 @@ class PathFinder:
                              out.ctypes.data, dist.ctypes.data))
         return out, dist
 
+    def follower_best_prims(self, rots, poss, goals, goal_dist: float, forward_amount: float, turn_amount: float,
+                            n_steps: int, allow_sliding: bool = True):
+        """nextBestPrimAlong (GreedyFollower.cpp:83-140) of N agents on the device
+        (hbn_follower_best_prims): rots [N,4] float64 quaternions (x, y, z, w), poss [N,3] float64,
+        goals [N,3].  Returns (prim int32 [N], geodesic distance now f32 [N]); prim: -2 ERROR, -1 STOP,
+        -3 none acceptable, else (turns << 1) | side (0 = LEFT, 1 = RIGHT) before one FORWARD."""
+        r = np.ascontiguousarray(np.asarray(rots, np.float64).reshape(-1, 4))
+        p = np.ascontiguousarray(np.asarray(poss, np.float64).reshape(-1, 3))
+        g = np.ascontiguousarray(np.asarray(goals, np.float32).reshape(-1, 3))
+        n = len(r)
+        fp = _lib.FollowerParams(float(goal_dist), float(forward_amount), math.sin(turn_amount / 2.0),
+                                 math.cos(turn_amount / 2.0), int(n_steps), 1 if allow_sliding else 0)
+        prim = np.empty(n, np.int32)
+        geo = np.empty(n, np.float32)
+        check(_lib.lib().hbn_follower_best_prims(self._need(), r.ctypes.data, p.ctypes.data, g.ctypes.data, n,
+                                                 C.byref(fp), prim.ctypes.data, geo.ctypes.data))
+        return prim, geo
+
     def try_steps(self, starts, ends, allow_sliding: bool = True):
         h = self._need()
         L = _lib.lib()

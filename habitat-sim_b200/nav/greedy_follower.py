@@ -171,8 +171,8 @@ class GreedyGeodesicFollowerBatchImpl:
                 upd = active & (reward[:, c] > best_reward)
             best_reward[upd] = reward[upd, c]
             best[upd] = c
-            if c & 1:  # RIGHT candidate: GreedyFollower.cpp:133-135
-                active &= ~(best_reward > 0.99)
+            if c & 1:  # RIGHT candidate: GreedyFollower.cpp:131-135 (float bestReward > 0.99f)
+                active &= ~(best_reward.astype(np.float32) > np.float32(0.99))
                 if not active.any():
                     break
         for j, i in enumerate(search):
@@ -181,6 +181,30 @@ class GreedyGeodesicFollowerBatchImpl:
             else:
                 side = GreedyFollowerCodes.RIGHT if (best[j] & 1) else GreedyFollowerCodes.LEFT
                 out[i] = [side] * int(best[j] >> 1) + [GreedyFollowerCodes.FORWARD]
+        return out
+
+    def _decide(self, rot, pos, end):
+        """Best primitive of every agent described by rot / pos / end (nextBestPrimAlong,
+        GreedyFollower.cpp:83-140).  A PathFinder of this package does all of it on the device
+        (hbn_follower_best_prims: kinematics, the three batched queries, rewards, selection); any
+        other backend (the tests' oracle adapter) gets the numpy restatement above."""
+        dev = getattr(self.pathfinder, "follower_best_prims", None)
+        if dev is None:
+            return self._next_best_prims(rot, pos, end, self._geo(pos, end))
+        prim, _geo = dev(rot, pos, end, self.goal_dist, self.forward_amount, self.turn_amount, self._n_steps,
+                         self.allow_sliding)
+        out = []
+        for c in prim:
+            c = int(c)
+            if c == -2:
+                out.append([GreedyFollowerCodes.ERROR])
+            elif c == -1:
+                out.append([GreedyFollowerCodes.STOP])
+            elif c < 0:
+                out.append([])
+            else:
+                side = GreedyFollowerCodes.RIGHT if (c & 1) else GreedyFollowerCodes.LEFT
+                out.append([side] * (c >> 1) + [GreedyFollowerCodes.FORWARD])
         return out
 
     def _is_thrashing(self, actions):
@@ -203,12 +227,11 @@ class GreedyGeodesicFollowerBatchImpl:
         rot = np.asarray(rots, np.float64).reshape(self.n, 4)
         pos = np.asarray(poss, np.float64).reshape(self.n, 3)
         end = np.asarray(ends, np.float64).reshape(self.n, 3)
-        geo = self._geo(pos, end)
         need = [i for i in range(self.n) if not (self.fix_thrashing and self._thrashing[i])]
         prims = {}
         if need:
             ix = np.asarray(need)
-            for i, acts in zip(need, self._next_best_prims(rot[ix], pos[ix], end[ix], geo[ix])):
+            for i, acts in zip(need, self._decide(rot[ix], pos[ix], end[ix])):
                 prims[i] = acts
         out = []
         for i in range(self.n):
@@ -238,8 +261,7 @@ class GreedyGeodesicFollowerBatchImpl:
         running = np.ones(self.n, bool)
         while running.any():
             ix = np.nonzero(running)[0]
-            geo = self._geo(pos[ix], end[ix])
-            prims = self._next_best_prims(rot[ix], pos[ix], end[ix], geo)
+            prims = self._decide(rot[ix], pos[ix], end[ix])
             fwd = []
             for i, prim in zip(ix, prims):
                 if not prim:

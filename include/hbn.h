@@ -178,6 +178,24 @@ int hbn_try_step_dev(hbn_navmesh_t nm, const float* starts, const float* ends, i
 int hbn_env_step_dev(hbn_navmesh_t nm, const float* starts, const float* targets, const float* goals,
                      int64_t n, int allow_sliding, float* out_pos, float* out_dist, void* stream);
 
+/* GreedyGeodesicFollowerImpl::nextBestPrimAlong (GreedyFollower.cpp:83-140) for n agents at once: the
+ * kinematics of every primitive [LEFT]*k+[FORWARD] / [RIGHT]*k+[FORWARD] (default_controls.py: rotate
+ * about +Y by turn_amount, move forward_amount along local -Z), their try_step + geodesic distance +
+ * obstacle distance (GreedyFollower.cpp:46-81), computeReward and the selection all run on the device.
+ * rots: [n, 4] float64 quaternions (x, y, z, w); poss: [n, 3] float64; goals: [n, 3] float32.
+ * out_prim[i]: -2 = ERROR (no path), -1 = STOP (within goal_dist), -3 = no acceptable primitive,
+ * else (k << 1) | side: k turns (side 0 = LEFT, 1 = RIGHT) followed by one FORWARD.
+ * out_geo (nullable): the geodesic distance from the current position. */
+typedef struct {
+  float goal_dist, forward_amount;
+  double sin_half_turn, cos_half_turn; /* sin / cos of turn_amount / 2 */
+  int32_t n_steps;                      /* headings per side: the reference's loop count, angle += turn in f32 while < pi */
+  int32_t allow_sliding;
+} hbn_follower_params;
+int hbn_follower_best_prims_dev(hbn_navmesh_t nm, const double* rots, const double* poss, const float* goals,
+                                int64_t n, const hbn_follower_params* params, int32_t* out_prim,
+                                float* out_geo, void* stream);
+
 /* closestObstacleSurfacePoint / distanceToClosestObstacle, PF.cpp:1788-1812.
  * out_hit_pos / out_hit_normal nullable. */
 int hbn_closest_obstacle_dev(hbn_navmesh_t nm, const float* pts, int64_t n, float max_radius,
@@ -223,6 +241,8 @@ int hbn_try_step(hbn_navmesh_t nm, const float* starts, const float* ends, int64
  * CUDA graph and replayed */
 int hbn_env_step(hbn_navmesh_t nm, const float* starts, const float* targets, const float* goals,
                  int64_t n, int allow_sliding, float* out_pos, float* out_dist);
+int hbn_follower_best_prims(hbn_navmesh_t nm, const double* rots, const double* poss, const float* goals,
+                            int64_t n, const hbn_follower_params* params, int32_t* out_prim, float* out_geo);
 int hbn_closest_obstacle(hbn_navmesh_t nm, const float* pts, int64_t n, float max_radius,
                          float* out_hit_pos, float* out_hit_normal, float* out_hit_dist);
 int hbn_random_points(hbn_navmesh_t nm, uint64_t seed, uint64_t query0, int64_t n,

@@ -436,7 +436,7 @@ int emu_find_path_lane_v(void* h, int ts, int v, const float* starts, const floa
 #define HBN_EMU_LANE(T, VV) \
   if (ts == T && v == VV) { laneSearchRun<T, VV>(h, starts, ends, n, fastFail, allCorridors, out_corridor, out_info); return 0; }
   HBN_EMU_LANE(3, 1) HBN_EMU_LANE(3, 2) HBN_EMU_LANE(7, 2) HBN_EMU_LANE(31, 2) HBN_EMU_LANE(63, 2)
-  HBN_EMU_LANE(3, 9) HBN_EMU_LANE(63, 9) HBN_EMU_LANE(95, 9)
+  HBN_EMU_LANE(3, 9) HBN_EMU_LANE(63, 9) HBN_EMU_LANE(95, 9) HBN_EMU_LANE(71, 10)
 #undef HBN_EMU_LANE
   return -1;
 }
@@ -586,7 +586,7 @@ long emu_lane_lockstep(void* h, int ts, int v, const float* starts, const float*
 #define HBN_EMU_LOCK(T, VV) if (ts == T && v == VV) return laneLockstep<T, VV>(h, starts, ends, n, fastFail);
   HBN_EMU_LOCK(3, 1) HBN_EMU_LOCK(3, 2) HBN_EMU_LOCK(7, 2) HBN_EMU_LOCK(31, 2) HBN_EMU_LOCK(63, 2)
   HBN_EMU_LOCK(47, 1) HBN_EMU_LOCK(47, 2) HBN_EMU_LOCK(55, 1) HBN_EMU_LOCK(39, 1) HBN_EMU_LOCK(63, 3) HBN_EMU_LOCK(47, 4) HBN_EMU_LOCK(63, 5) HBN_EMU_LOCK(63, 6) HBN_EMU_LOCK(59, 1) HBN_EMU_LOCK(95, 1) HBN_EMU_LOCK(63, 7)
-  HBN_EMU_LOCK(3, 9) HBN_EMU_LOCK(63, 9) HBN_EMU_LOCK(95, 9) HBN_EMU_LOCK(63, 10)
+  HBN_EMU_LOCK(3, 9) HBN_EMU_LOCK(63, 9) HBN_EMU_LOCK(95, 9) HBN_EMU_LOCK(63, 10) HBN_EMU_LOCK(71, 10)
 #undef HBN_EMU_LOCK
   return -1;
 }

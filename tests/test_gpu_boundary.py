@@ -295,3 +295,32 @@ def test_calls_on_different_streams_do_not_race_on_the_scratch():
         assert beq(a.cpu().numpy(), want).all()
         assert beq(b.cpu().numpy(), want2).all()
         assert beq(c, want[:5000]).all()
+
+
+def test_multi_gpu_dispatcher_on_devices():
+    """nav.MultiGpuPathFinder with real handles: every visible device (and, so that the thread / slice
+    logic runs on a one-GPU box too, two handles on device 0).  The split batch equals the unsplit one."""
+    import torch
+    import habitat_sim_b200  # noqa: F401
+    from habitat_sim_b200.nav import MultiGpuPathFinder
+    from workloads.scenes import NavMeshGeom, pointnav_pairs
+    name = "c4_building"
+    img = navmesh_image(name)
+    st, en = pointnav_pairs(NavMeshGeom(img), 50_001, 23)
+    single = gpu_pathfinder(name)
+    want = single.find_paths(st, en)["geodesic_distance"]
+    want_step = single.try_steps(st[:4000], en[:4000])
+    rp, rr = single.random_navigable_points(3001, seed=9, query0=100)
+    configs = [[0, 0]]
+    if torch.cuda.device_count() > 1:
+        configs.append(list(range(torch.cuda.device_count())))
+    for devices in configs:
+        mg = MultiGpuPathFinder(devices)
+        assert mg.load_nav_mesh_bytes(img) and mg.world == len(devices)
+        mg.set_option("lane_scratch_bytes", 2 << 30)
+        assert beq(mg.geodesic_distances(st, en), want).all(), devices
+        assert beq(mg.try_steps(st[:4000], en[:4000]), want_step).all()
+        gp, gr = mg.random_navigable_points(3001, seed=9, query0=100)
+        assert beq(gp, rp).all() and (gr == rr).all()
+        assert mg.num_islands == single.num_islands  # scalar API: the first handle
+        mg.close()

@@ -250,7 +250,7 @@ def test_hostemu_lane_search_matches_oracle(name):
     emu.emu_destroy(h)
 
 
-@pytest.mark.parametrize("ts,v", [(3, 1), (3, 2), (7, 2), (31, 2), (63, 2), (3, 9), (63, 9), (95, 9)])
+@pytest.mark.parametrize("ts,v", [(3, 1), (3, 2), (7, 2), (31, 2), (63, 2), (3, 9), (63, 9), (95, 9), (71, 10)])
 @pytest.mark.parametrize("name", ["c3_multiroom", "c4_building"])
 def test_hostemu_lane_search_variants(name, ts, v):
     """The heap-code variants of hbn_astar_lane.h (V = 2: two heap levels per global-memory round
@@ -306,7 +306,7 @@ def test_hostemu_lane_heap_fuzz(ts, v):
             assert emu.emu_lane_heap_fuzz(ts, v, seed, C.c_long(8000), levels) == 0, (levels, seed)
 
 
-@pytest.mark.parametrize("ts,v", [(3, 1), (3, 2), (7, 2), (31, 2), (39, 1), (47, 1), (47, 2), (47, 4), (55, 1), (63, 2), (59, 1), (63, 3), (63, 5), (63, 6), (63, 7), (95, 1), (3, 9), (63, 9), (95, 9), (63, 10)])
+@pytest.mark.parametrize("ts,v", [(3, 1), (3, 2), (7, 2), (31, 2), (39, 1), (47, 1), (47, 2), (47, 4), (55, 1), (63, 2), (59, 1), (63, 3), (63, 5), (63, 6), (63, 7), (95, 1), (3, 9), (63, 9), (95, 9), (63, 10), (71, 10)])
 @pytest.mark.parametrize("name", ["c3_multiroom", "c4_building"])
 def test_hostemu_lane_variants_lockstep(name, ts, v):
     """Every variant in lock step with the shipped one: same heap entries, node count, best node
