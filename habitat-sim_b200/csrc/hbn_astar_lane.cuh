@@ -13,11 +13,13 @@
 namespace hbn {
 
 struct LaneScratch {  // one slot per lane of the grid in each region
+  char* dir;            // node directories, dirBytes each (zeroed at allocation; a search leaves its directory zeroed)
   char* tab;            // node tables, tabBytes each (zeroed at allocation, wiped every 31 queries)
   char* rec;            // node records, kLaneRecBytes each
   char* heap;           // heap entries beyond the shared levels, kLaneHeapBytes each
   uint32_t* gen;        // table generation of every lane slot (persists across launches)
-  size_t tabBytes;
+  size_t tabBytes, dirBytes;
+  int groupCap;         // groups a search may open (kLaneGroupsMax; tests lower it to force the overflow path)
 };
 
 template <int TS>
@@ -28,7 +30,7 @@ __host__ __device__ constexpr size_t laneSharedBytes() { return static_cast<size
 // WPB: warps per block.  Every warp is on its own (no block-level synchronisation); blocks of more than
 // one warp only exist because a block costs 1 KB of reserved shared memory: two-warp blocks leave room
 // for 71 instead of 63 heap entries per lane at 16 warps per SM.
-template <int TS, int CH, int V, int WPB = 1>
+template <int TS, int CH, int V, int WPB = 1, int F = 0>
 __device__ __forceinline__ void astarLaneBody(const NavView& nav, const SearchArgs& a, const LaneScratch& sc) {
   constexpr uint32_t FULL = 0xffffffffu;
   extern __shared__ __align__(16) char smemAll[];
@@ -42,12 +44,16 @@ __device__ __forceinline__ void astarLaneBody(const NavView& nav, const SearchAr
   const int activeLanes = (a.laneLimit > 0 && a.laneLimit < 32) ? a.laneLimit : 32;
   const bool hasSlot = lane < activeLanes;
   const size_t slotId = static_cast<size_t>(warpId) * activeLanes + (hasSlot ? lane : 0);
-  LaneSearch<32, TS, CH, V> s;
+  LaneSearch<32, TS, CH, V, F> s;
   s.K = reinterpret_cast<float*>(smem) + lane;
   s.S = reinterpret_cast<uint16_t*>(smem + static_cast<size_t>(TS) * 32 * 4) + lane;
   s.G = reinterpret_cast<LaneHeapEnt*>(sc.heap + slotId * kLaneHeapBytes);
   s.tab = reinterpret_cast<uint16_t*>(sc.tab + slotId * sc.tabBytes);
-  s.rec = sc.rec + slotId * kLaneRecBytes;
+  s.dir = reinterpret_cast<uint32_t*>(sc.dir + slotId * sc.dirBytes);
+  s.dirLo = 0xffffffffu; s.dirHi = 0u;
+  s.nGroups = 0u;
+  s.groupCap = static_cast<uint32_t>(sc.groupCap);
+  s.rec = sc.rec + slotId * kLaneRecBytesMax;
   s.cv = nullptr;
   s.gen = hasSlot ? sc.gen[slotId] : 0u;
   // A batch smaller than the grid is spread over more warps (a.laneLimit lanes each): the lanes
@@ -96,7 +102,11 @@ __device__ __forceinline__ void astarLaneBody(const NavView& nav, const SearchAr
     const int ev = s.step(nav, fastFail, allCorridors);
     if (ev != kLEvNone) {
       const uint32_t q = s.q;
-      if (ev == kLEvFault) {
+      if (ev == kLEvOverflow) {  // to the table kernel (launched after this one on the overflow list)
+        a.overflow[atomicAdd(a.overflowCount, 1u)] = q;
+        a.astat[q] = kSearchOverflow;
+        a.fullLen[q] = 0;
+      } else if (ev == kLEvFault) {
         atomicAdd(a.fault, 1u);
         a.fault[1] = q;
         a.fault[2] = 5u | (TS << 8);
@@ -117,16 +127,9 @@ __device__ __forceinline__ void astarLaneBody(const NavView& nav, const SearchAr
   if (hasSlot) sc.gen[slotId] = s.gen;
 }
 
-template <int TS, int MINB, int CH, int V = 1, int WPB = 1>
+template <int TS, int MINB, int CH, int V = 1, int WPB = 1, int F = 0>
 __global__ void __launch_bounds__(32 * WPB, MINB / WPB) k_astar_lane(NavView nav, SearchArgs a, LaneScratch sc) {
-  astarLaneBody<TS, CH, V, WPB>(nav, a, sc);
-}
-
-// The same with the register budget given directly: ptxas turns "MINB one-warp blocks" into 96
-// registers for 17-20 blocks and 80 for 21-25, although 18 blocks would allow 112 and 19 blocks 104.
-template <int TS, int REGS, int CH, int V = 1>
-__global__ void __maxnreg__(REGS) k_astar_lane_r(NavView nav, SearchArgs a, LaneScratch sc) {
-  astarLaneBody<TS, CH, V>(nav, a, sc);
+  astarLaneBody<TS, CH, V, WPB, F>(nav, a, sc);
 }
 
 }  // namespace hbn

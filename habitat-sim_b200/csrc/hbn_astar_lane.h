@@ -2,14 +2,14 @@
 //
 // dtNavMeshQuery::findPath (DQ.cpp:973-1165) is a serial algorithm; its result depends on the
 // exact order of its heap operations (DNode.cpp:156-200) and of node allocation against the
-// 2048-node pool (PF.cpp:937).  Splitting one query over lanes (hbn_astar_warp.cuh,
-// hbn_astar_group.cuh) leaves most issue slots on warp-uniform bookkeeping: ~500 warp
+// 2048-node pool (PF.cpp:937).  Splitting one query over lanes (round 1's first two mappings,
+// deleted since) leaves most issue slots on warp-uniform bookkeeping: ~500 warp
 // instructions per poly expansion, and shared memory caps an SM at ~25 queries in flight.
 // Here a query belongs to ONE lane and a warp advances 32 queries in lock step (k_astar_lane,
 // hbn_astar_lane.cuh): one warp instruction serves 32 expansions, and the per-query state that
 // does not fit on chip lives in HBM, sized for 180 GB:
 //
-//   shared  : the top TS entries (6 levels at TS = 63) of the binary heap, 6 B per entry
+//   shared  : the top TS entries (71 shipped: 6 levels + 8) of the binary heap, 6 B per entry
 //             {f32 total, u16 node}, interleaved over the lanes of the warp (entry i of lane l
 //             at word i*32 + l: never a bank conflict).  Nothing else: heap positions of the
 //             nodes are NOT tracked (a first version kept them in HBM: one scattered 2 B store
@@ -27,8 +27,9 @@
 //                 query just bumps the generation (the table is wiped every 31 queries);
 //             (c) 2048 node records of 32 B in ALLOCATION order (dtNodePool's index order):
 //                 {pos, cost | poly, parent poly + entering link, link window, parent node}.
-//                 A node is open or closed; "closed" is the sign bit of the stored cost (costs
-//                 are >= +0), so the first 16 B answer everything a revisit asks.
+//                 The first 16 B answer everything a revisit asks.  (Variant 1 keeps Detour's
+//                 closed flag in the sign bit of the stored cost; the shipped variant stores no
+//                 flag at all, see LaneSearch.)
 //   A node's total is not stored: it is cost + heuristic(pos), recomputed with the same
 //   operations.
 //
@@ -107,12 +108,24 @@ constexpr size_t kLaneRecBytes = static_cast<size_t>(kMaxNodes) * 32;
 // a multiple of 32: a 4-entry group of every lane's heap then sits in ONE 32 B sector
 constexpr size_t kLaneHeapBytes = (static_cast<size_t>(kMaxNodes + 2) * sizeof(LaneHeapEnt) + 31) & ~static_cast<size_t>(31);
 HBN_HD size_t laneTabBytes(uint32_t numKeys) { return (static_cast<size_t>(numKeys) * 2 + 15) & ~static_cast<size_t>(15); }
+// V >= 40: the node directory, one u32 per block of 16 node keys, in whole 32 B sectors
+constexpr uint32_t kLaneBlockShift = 4;                  // 16 keys per block = 16 records per group
+constexpr uint32_t kLaneBlockKeys = 1u << kLaneBlockShift;
+constexpr uint32_t kLaneGroupsMax = 256;                 // groups of 16 records a search may open
+constexpr uint32_t kLaneGroupNodes = kLaneGroupsMax * kLaneBlockKeys;  // node ids < 4096 (12 bits, LaneRecB::w3)
+HBN_HD size_t laneDirBytes(uint32_t numKeys) {
+  return ((static_cast<size_t>(numKeys) + kLaneBlockKeys * 8 - 1) / (kLaneBlockKeys * 8)) * 32;
+}
+// per lane: [directory | node table] (zeroed at allocation), records (by node id: 2048 in allocation order or 4096
+// in groups), heap tail.  One layout for every variant: the table variants ignore the directory and vice versa.
+constexpr size_t kLaneRecBytesMax = static_cast<size_t>(kLaneGroupNodes) * 32;
 HBN_HD size_t laneScratchBytes(uint32_t numKeys) {
-  return laneTabBytes(numKeys) + kLaneRecBytes + kLaneHeapBytes;
+  return laneDirBytes(numKeys) + laneTabBytes(numKeys) + kLaneRecBytesMax + kLaneHeapBytes;
 }
 
 enum { kLIdle = 0, kLSearch = 1, kLExtract = 2, kLDone = 3 };
-enum { kLEvNone = 0, kLEvFinished = 1, kLEvFault = 3, kLEvPoolExhausted = 4 /* internal */ };
+enum { kLEvNone = 0, kLEvFinished = 1, kLEvFault = 3, kLEvPoolExhausted = 4 /* internal */,
+       kLEvOverflow = 5 /* V >= 40: more than kLaneGroupsMax groups; the query goes to the table kernel */ };
 
 // KEEP: the link records are the read-only, L2-sized part of the working set (a few MB against GBs of
 // per-query search state streaming through L2): one 32 B load, evict_last in L1 and L2 (device only).
@@ -141,50 +154,58 @@ HBN_HD void laneLoadLink(const LinkRec* p, LaneLinkLo& lo, LaneLinkHi& hi) {
 // HS: distance (in elements) between consecutive shared heap entries of this lane (32 on the
 // device, 1 in the host build); TS: heap entries kept in shared memory (odd, so that the
 // children 2i+1, 2i+2 of an entry are both on the same side and pair-aligned in global);
-// CH: links per load stage (registers vs. rounds); V: code variant of the heap operations --
-// 1 = one heap level per HBM round trip; 2 = the sift-down fetches children AND grandchildren
-// of an HBM-level entry together (two levels per round trip), the bubble-up that ends a pop
-// compares against the key it has just moved instead of re-loading it, and the replay has one
-// bubble-up site for pushes and modifies.  Both go through the same heap states.
+// CH: links per load stage (registers vs. rounds); V: memory-policy variant (below).
 // step() contains warp collectives on the device: all 32 lanes of the warp must call it
 // together, whatever their mode.
-template <int HS, int TS, int CH, int V = 1>
+// F: code-shape bits.  The kernel is ~40 KB of SASS, more than the 32 KB instruction cache level next to the
+// SM (the profile shows warps waiting for instructions), so: 1 = the replay of the queued heap operations is
+// ONE loop body instead of kLaneChunk unrolled copies; 2 = the L2 cache policies are created once and kept in
+// registers instead of once per access.
+template <int HS, int TS, int CH, int V = 1, int F = 0>
 struct LaneSearch {
+  static constexpr bool kRolledReplay = (F & 1) != 0;
+  static constexpr bool kHoistPolicy = (F & 2) != 0;
+  static constexpr bool kRolledVisit = (F & 4) != 0;  // 4 = the per-link cost tests are one loop body as well
   static constexpr int kLaneChunk = CH;  // links handled per load stage
-  // V: 1 shipped; 2 heap code variant 2; 3 = 1 + node-table entries of the popped poly's
-  // neighbours prefetched into L2 before the sift-down (device only); 4 = 2 + that prefetch
-  static constexpr bool kHeap2 = V == 2 || V == 4;
-  static constexpr bool kTabPrefetch = V >= 3 && V <= 5;
-  // V = 5: 3 + at every sift-down level the four grandchildren (one 32 B sector) are started
-  // towards L2 while the children are compared, so only the first HBM level pays DRAM latency
-  static constexpr bool kSiftPrefetch = V == 5;
-  // V = 6: 1 + the modify scan looks through the shared part of the heap before the HBM part
-  static constexpr bool kScanSharedFirst = V == 6;
-  // V = 7: 1 + node-table loads and stores carry an L2 evict_last policy
-  static constexpr bool kTabEvictLast = V == 7 || (V >= 10 && V < 20) || V == 20;
-  // V >= 8: L2 residency by kind of data (profiles/r2_summary.md: with every access at normal priority
-  // the 126 MB L2 keeps nothing from one step to the next; 60 % of the read sectors go to DRAM).  Node
-  // records are write-once / read-once-much-later: 32 B accesses, no L1 allocation, L2 evict_first.
-  // Link records (read-only, a few MB, read by every search): evict_last.
-  static constexpr bool kRecStream = (V >= 8 && V < 20) || V == 23;  // (V = 20..23: one kind tagged at a time, for ncu's per-class counters)
-  static constexpr bool kLinkKeep = (V >= 8 && V < 20) || V == 22;
+  // V = 1: every access at normal L2 priority, closed flag stored at every pop (round 1's kernel).
+  // V >= 8: L2 residency by kind of data.  With every access at normal priority the 126 MB L2 keeps next
+  // to nothing from one step to the next (75 k searches in flight x ~35 KB of live state each) and the
+  // kernel runs at the DRAM's random-access rate (profiles/r2_summary.md).  Node records are write-once /
+  // read-once-much-later: one 32 B access each, no L1 allocation, L2 evict_first.  Link records
+  // (read-only, a few MB, read by every search): one 32 B load, evict_last.
   // V >= 9: no closed flag.  The flag only matters when a better path to an allocated node turns up
   // (DQ.cpp:1124-1153: open -> modify, closed -> push again); the modify scan that looks for the node in
   // the heap answers that, so the store of the flag at every pop (a DRAM write-back) is dropped.
+  // V = 10 (shipped): + the node table's loads and stores carry evict_last (its working set per search is
+  // a few KB thanks to the space-filling key order).
+  // V = 20..24 (diagnostic build only): one kind of data tagged with an eviction class at a time, so that
+  // ncu's per-class L2 counters read per kind.
+  // V >= 40: NO node table.  A table lookup is a DRAM access (the u16 tables of the 75 k searches in flight,
+  // 87 sectors touched per search, are far beyond the L2), four in five of them only to learn that the node
+  // is new, and the revisits wait for two DRAM accesses in a row (table, then record) -- in lock step nearly
+  // every warp has one such lane per step.  Instead the records are addressed by KEY: the keys are numbered
+  // along a space-filling curve, so a search touches few blocks of 16 consecutive keys (87 on average, at
+  // most 214 on 20 k C4 queries); the first node of a block opens a GROUP of 16 records, and a DIRECTORY
+  // entry per block {16-bit mask of the keys allocated | group + 1 << 16} says where it is: node id =
+  // group * 16 + key % 16.  The directory is 2 bits per key: what a search touches of it (~20 sectors) stays
+  // in L2 (evict_last), so "new node" costs no DRAM access at all (the record store is a full sector: no
+  // fill) and a revisit costs one.  A search clears the directory words it has set when it ends; one that
+  // needs more than kLaneGroupsMax groups gives up (kLEvOverflow) and is redone by the table kernel (V = 10).
+  // Node ids are group-relative, not allocation order: nothing observable depends on the id (the pool limit
+  // counts nodes, ties in the heap are broken by heap position).
+  static constexpr bool kGroups = V >= 40 && V < 50;
+  static constexpr bool kTabEvictLast = (V >= 10 && V < 20) || V == 20;
+  static constexpr bool kRecStream = (V >= 8 && V < 20) || V == 23 || kGroups;
+  static constexpr bool kLinkKeep = (V >= 8 && V < 20) || V == 22 || kGroups;
   static constexpr bool kNoClosedStore = V >= 9;
-  // V >= 11: the heap entries beyond the shared levels (a few hundred bytes per search, touched at
-  // nearly every pop and push) are kept in L2 with evict_last as well
-  static constexpr bool kHeapKeep = V == 11 || V == 21;
-  // V = 12: 10, but new records are STORED at normal priority (the best neighbour is usually popped within a
-  // step or two -- that read should still find the record in L2); the pop, their last use, stays evict_first
-  static constexpr bool kRecStoreNormal = V == 12;
-  static constexpr uint32_t kGenMax = kLaneGenMax;
+  static constexpr bool kHeapKeep = V == 21;
   static_assert((TS & 1) == 1, "TS must be odd");
   // memory of this lane
   float* K;        // shared: heap keys
   uint16_t* S;     // shared: heap nodes
   LaneHeapEnt* G;  // global: heap entries TS.. (entry j at G[j - TS])
   uint16_t* tab;   // node table
+  uint32_t* dir;   // node directory (kGroups)
   char* rec;       // node records
   uint32_t* cv;    // corridor ring of the current query (entering links, see ViaCorridor)
   // query
@@ -193,6 +214,8 @@ struct LaneSearch {
   // search state
   int mode, size, nodeCount;
   uint32_t gen;
+  uint32_t dirLo, dirHi;  // kGroups: first / last 16 B unit of the directory this search has written (lo > hi: none yet)
+  uint32_t nGroups, groupCap;  // kGroups: groups opened / allowed (kLaneGroupsMax; tests lower it)
   uint32_t lastBest, lastBestG;
   float lastBestCost;
   bool outOfNodes;
@@ -203,6 +226,24 @@ struct LaneSearch {
   uint32_t xcur;
   LaneRecB xB;
 
+  // L2 cache policies of the accesses below (device only)
+  static HBN_HD unsigned long long polLast() {
+    unsigned long long pol = 0;
+#if defined(__CUDA_ARCH__)
+    if constexpr (kHoistPolicy) asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+#endif
+    return pol;
+  }
+  static HBN_HD unsigned long long polFirst() {
+    unsigned long long pol = 0;
+#if defined(__CUDA_ARCH__)
+    if constexpr (kHoistPolicy) asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+#endif
+    return pol;
+  }
+
   // Node-table accesses.  V = 7 marks them evict_last in L2: with the keys numbered along the
   // space-filling curve the table working set of a search is a few KB, which is worth keeping
   // against the record stream (device only; a hint, the values are the same).
@@ -211,7 +252,7 @@ struct LaneSearch {
     if constexpr (kTabEvictLast) {
       unsigned long long pol;
       unsigned short v;
-      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+      pol = polLast();
       asm volatile("ld.global.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(tab + key), "l"(pol) : "memory");
       return v;
     }
@@ -222,17 +263,93 @@ struct LaneSearch {
 #if defined(__CUDA_ARCH__)
     if constexpr (kTabEvictLast) {
       unsigned long long pol;
-      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+      pol = polLast();
       asm volatile("st.global.L2::cache_hint.u16 [%0], %1, %2;" ::"l"(tab + key), "h"(static_cast<unsigned short>(v)), "l"(pol) : "memory");
       return;
     }
 #endif
     tab[key] = static_cast<uint16_t>(v);
   }
-  // a looked-up table entry: found? / which node
-  HBN_HD bool teFound(const uint32_t te) const { return (te >> kLaneSlotBits) == gen; }
-  static HBN_HD uint32_t teSlot(const uint32_t te) { return te & kLaneSlotMask; }
-  HBN_HD uint32_t lookup(const uint32_t key) const { return tabLoad(key); }
+  // ---- kGroups: directory entry of a key's block; te = found << 31 | (found ? node id : group + 1 of the block)
+  HBN_HD uint32_t dirLoad(const uint32_t key) const {
+#if defined(__CUDA_ARCH__)
+    unsigned long long pol;
+    uint32_t w;
+    // .cg: the entry is updated by a reduction in L2 (dirOr), an L1 copy could be stale
+    if constexpr (V == 41) {
+      asm volatile("ld.global.cg.b32 %0, [%1];" : "=r"(w) : "l"(dir + (key >> kLaneBlockShift)) : "memory");
+      return w;
+    }
+    pol = polLast();
+    asm volatile("ld.global.cg.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(w) : "l"(dir + (key >> kLaneBlockShift)), "l"(pol) : "memory");
+    return w;
+#else
+    return dir[key >> kLaneBlockShift];
+#endif
+  }
+  static HBN_HD uint32_t dirTe(const uint32_t e, const uint32_t key) {
+    const uint32_t k = key & (kLaneBlockKeys - 1u);
+    return ((e >> k) & 1u) ? (0x80000000u | ((((e >> 16) - 1u) << kLaneBlockShift) | k)) : (e >> 16);
+  }
+  HBN_HD void dirOr(const uint32_t key, const uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    unsigned long long pol;
+    if constexpr (V == 41) {
+      asm volatile("red.global.or.b32 [%0], %1;" ::"l"(dir + (key >> kLaneBlockShift)), "r"(v) : "memory");
+    } else {
+      pol = polLast();
+      asm volatile("red.global.or.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(dir + (key >> kLaneBlockShift)), "r"(v), "l"(pol) : "memory");
+    }
+#else
+    dir[key >> kLaneBlockShift] |= v;
+#endif
+    const uint32_t u = key >> (kLaneBlockShift + 2);
+    dirLo = u < dirLo ? u : dirLo;
+    dirHi = u > dirHi ? u : dirHi;
+  }
+  // Node id of a key the search has not allocated yet: in the group of its block, opened now if it has none
+  // (g1 = group + 1 of the block as far as the caller knows, 0 = none).  kNoPoly: no group left.
+  HBN_HD uint32_t dirAlloc(const uint32_t key, uint32_t g1) {
+    const uint32_t k = key & (kLaneBlockKeys - 1u);
+    // no group seen: an earlier link of this expansion may have opened it since the entry was loaded
+    if (g1 == 0u) g1 = dirLoad(key) >> 16;
+    if (g1 == 0u) {
+      if (nGroups >= groupCap) return kNoPoly;
+      g1 = ++nGroups;
+      dirOr(key, (g1 << 16) | (1u << k));
+    } else {
+      dirOr(key, 1u << k);
+    }
+    return ((g1 - 1u) << kLaneBlockShift) | k;
+  }
+  // the end of a search: the directory goes back to all zero
+  HBN_HD void clearDir() {
+    if constexpr (kGroups) {
+      if (dirLo <= dirHi) {
+#if defined(__CUDA_ARCH__)
+        uint4* p = reinterpret_cast<uint4*>(dir);
+        for (uint32_t u = dirLo; u <= dirHi; ++u) p[u] = make_uint4(0u, 0u, 0u, 0u);
+#else
+        memset(dir + 4 * static_cast<size_t>(dirLo), 0, 16 * static_cast<size_t>(dirHi - dirLo + 1));
+#endif
+      }
+      dirLo = 0xffffffffu;
+      dirHi = 0u;
+    }
+  }
+  // a looked-up node: found? / which node
+  HBN_HD bool teFound(const uint32_t te) const {
+    if constexpr (kGroups) return (te >> 31) != 0u;
+    return (te >> kLaneSlotBits) == gen;
+  }
+  static HBN_HD uint32_t teSlot(const uint32_t te) {
+    if constexpr (kGroups) return te & (kLaneGroupNodes - 1u);
+    return te & kLaneSlotMask;
+  }
+  HBN_HD uint32_t lookup(const uint32_t key) const {
+    if constexpr (kGroups) return dirTe(dirLoad(key), key);
+    return tabLoad(key);
+  }
   HBN_HD void insert(const uint32_t key, const uint32_t slot) const { tabStore(key, (gen << kLaneSlotBits) | slot); }
   HBN_HD LaneRecA* recA(uint32_t s) const { return reinterpret_cast<LaneRecA*>(rec + static_cast<size_t>(s) * 32); }
   HBN_HD LaneRecB* recB(uint32_t s) const { return reinterpret_cast<LaneRecB*>(rec + static_cast<size_t>(s) * 32 + 16); }
@@ -254,14 +371,6 @@ struct LaneSearch {
   }
   HBN_HD void storeRec(const uint32_t s, const LaneRecA& a, const LaneRecB& b) const {
 #if defined(__CUDA_ARCH__)
-    if constexpr (kRecStoreNormal) {
-      asm volatile("st.global.L1::no_allocate.L2::evict_normal.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(
-                       rec + static_cast<size_t>(s) * 32),
-                   "r"(__float_as_uint(a.px)), "r"(__float_as_uint(a.py)), "r"(__float_as_uint(a.pz)),
-                   "r"(__float_as_uint(a.cost)), "r"(b.poly), "r"(b.w1), "r"(b.lnk), "r"(b.w3)
-                   : "memory");
-      return;
-    }
     if constexpr (kRecStream) {
       asm volatile("st.global.L1::no_allocate.L2::evict_first.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(
                        rec + static_cast<size_t>(s) * 32),
@@ -279,7 +388,7 @@ struct LaneSearch {
     if constexpr (kRecStream) {
       unsigned long long pol;
       LaneRecA a;
-      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+      pol = polFirst();
       asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
                    : "=f"(a.px), "=f"(a.py), "=f"(a.pz), "=f"(a.cost)
                    : "l"(rec + static_cast<size_t>(s) * 32), "l"(pol)
@@ -294,7 +403,7 @@ struct LaneSearch {
     if constexpr (kRecStream) {
       unsigned long long pol;
       LaneRecB b;
-      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+      pol = polFirst();
       asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
                    : "=r"(b.poly), "=r"(b.w1), "=r"(b.lnk), "=r"(b.w3)
                    : "l"(rec + static_cast<size_t>(s) * 32 + 16), "l"(pol)
@@ -309,7 +418,7 @@ struct LaneSearch {
 #if defined(__CUDA_ARCH__)
     if constexpr (kRecStream) {
       unsigned long long pol;
-      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+      pol = polFirst();
       asm volatile("st.global.L1::no_allocate.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(&recA(s)->cost),
                    "f"(laneSetClosed(cost)), "l"(pol)
                    : "memory");
@@ -335,7 +444,7 @@ struct LaneSearch {
     if constexpr (kHeapKeep) {
       unsigned long long pol;
       LaneHeapEnt e;
-      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+      pol = polLast();
       asm volatile("ld.global.L2::cache_hint.v2.b32 {%0,%1}, [%2], %3;"
                    : "=r"(*reinterpret_cast<uint32_t*>(&e.key)), "=r"(e.slot)
                    : "l"(p), "l"(pol)
@@ -349,7 +458,7 @@ struct LaneSearch {
 #if defined(__CUDA_ARCH__)
     if constexpr (kHeapKeep) {
       unsigned long long pol;
-      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+      pol = polLast();
       asm volatile("st.global.L2::cache_hint.v2.b32 [%0], {%1,%2}, %3;" ::"l"(p), "r"(__float_as_uint(k)), "r"(s),
                    "l"(pol)
                    : "memory");
@@ -391,27 +500,6 @@ struct LaneSearch {
           __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(G), l));
       const uint16_t* col = S - lane + l;  // lane l's column of the shared heap
       int hit = -1;
-      if constexpr (kScanSharedFirst) {
-        // the open list is small (80 entries on average at a modify, 71 % of the nodes looked for
-        // sit in the shared part): look there first and touch the HBM part only on a miss
-        const int ns = n < TS ? n : TS;
-        for (int i = lane; i < ns; i += 32)
-          if (static_cast<uint32_t>(col[i * 32]) == tgt) hit = i;
-        if (__ballot_sync(0xffffffffu, hit >= 0) == 0u && n > TS) {  // warp-uniform
-          for (int base = TS + lane; base < n; base += 128) {
-            uint32_t hs[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int i = base + 32 * u;
-              hs[u] = 0xffffffffu;
-              if (i < n) hs[u] = g[i - TS].slot;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (hs[u] == tgt) hit = base + 32 * u;
-          }
-        }
-      } else
       for (int base = lane; base < n; base += 128) {  // 4 independent loads in flight per lane
         uint32_t hs[4];
 #pragma unroll
@@ -443,8 +531,8 @@ struct LaneSearch {
   }
 
   // dtNodeQueue::bubbleUp, DNode.cpp:156-167
-  HBN_HD void heapUp(int i, const float key, const uint32_t slot) const {
-    while (i > 0) {
+  HBN_HD void heapUp(int i, const float key, const uint32_t slot, const bool bubble = true) const {
+    while (bubble && i > 0) {
       const int parent = (i - 1) >> 1;
       float pk;
       uint32_t ps;
@@ -455,27 +543,12 @@ struct LaneSearch {
     }
     hset(i, key, slot);
   }
-  // bubbleUp whose first comparison is against a parent key the caller already holds (pkv)
-  HBN_HD void heapUpK(int i, const float key, const uint32_t slot, const bool pkv, const float pk0) const {
-    if (!(i == 0 || (pkv && !(pk0 > key)))) {
-      while (i > 0) {
-        const int parent = (i - 1) >> 1;
-        float pk;
-        uint32_t ps;
-        hget(parent, pk, ps);
-        if (!(pk > key)) break;
-        hset(i, pk, ps);
-        i = parent;
-      }
-    }
-    hset(i, key, slot);
-  }
   static HBN_HD LaneHeapPair loadPair(const LaneHeapEnt* p) {
 #if defined(__CUDA_ARCH__)
     if constexpr (kHeapKeep) {
       unsigned long long pol;
       LaneHeapPair r;
-      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+      pol = polLast();
       asm volatile("ld.global.L2::cache_hint.v4.b32 {%0,%1,%2,%3}, [%4], %5;"
                    : "=r"(*reinterpret_cast<uint32_t*>(&r.a.key)), "=r"(r.a.slot),
                      "=r"(*reinterpret_cast<uint32_t*>(&r.b.key)), "=r"(r.b.slot)
@@ -492,76 +565,9 @@ struct LaneSearch {
     uint32_t ls;
     hget(n, lk, ls);
     int i = 0, child = 1;
-    if constexpr (kHeap2) {
-      static_assert((TS & 3) == 3, "grandchildren 4i+3..4i+6 must start a 4-entry group of the global part");
-      float moved = 0.f;  // the key the last iteration moved up: it is the parent of the hole `i`
-      while (child < n) {
-        if (child < TS) {  // shared levels: one at a time
-          float c0 = K[child * HS], c1 = K[(child + 1) * HS];
-          uint32_t s0 = S[child * HS], s1 = S[(child + 1) * HS];
-          if ((child + 1) < n && c0 > c1) {
-            c0 = c1;
-            s0 = s1;
-            child++;
-          }
-          hset(i, c0, s0);
-          moved = c0;
-          i = child;
-          child = 2 * i + 1;
-        } else {
-          // HBM levels: the children pair and the four grandchildren (entries 2*child+1 ..
-          // 2*child+4, contiguous) are independent loads of one round trip; the grandchildren
-          // lie inside the lane's array whenever one of them is a heap entry (2*child+4 <= n+3).
-          const int gc = 2 * child + 1;
-          const LaneHeapPair p = loadPair(&G[child - TS]);
-          LaneHeapPair q0 = LaneHeapPair{{0.f, 0u}, {0.f, 0u}}, q1 = q0;
-          if (gc < n) {
-            q0 = loadPair(&G[gc - TS]);
-            q1 = loadPair(&G[gc + 2 - TS]);
-          }
-          float c0 = p.a.key, c1 = p.b.key;
-          uint32_t s0 = p.a.slot, s1 = p.b.slot;
-          bool second = false;
-          if ((child + 1) < n && c0 > c1) {
-            c0 = c1;
-            s0 = s1;
-            child++;
-            second = true;
-          }
-          hset(i, c0, s0);
-          moved = c0;
-          i = child;
-          child = 2 * i + 1;
-          if (child < n) {  // then gc < n held: q0 / q1 are loaded
-            c0 = second ? q1.a.key : q0.a.key;
-            c1 = second ? q1.b.key : q0.b.key;
-            s0 = second ? q1.a.slot : q0.a.slot;
-            s1 = second ? q1.b.slot : q0.b.slot;
-            if ((child + 1) < n && c0 > c1) {
-              c0 = c1;
-              s0 = s1;
-              child++;
-            }
-            hset(i, c0, s0);
-            moved = c0;
-            i = child;
-            child = 2 * i + 1;
-          }
-        }
-      }
-      heapUpK(i, lk, ls, i > 0, moved);
-      return;
-    }
     while (child < n) {  // child is odd; child + 1 <= n is inside the arrays
       float c0, c1;
       uint32_t s0, s1;
-#if defined(__CUDA_ARCH__)
-      if constexpr (kSiftPrefetch) {
-        static_assert(!kSiftPrefetch || (TS & 3) == 3, "a grandchildren group must not straddle the shared part");
-        const int gc = 2 * child + 1;
-        if (gc >= TS && gc < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(&G[gc - TS]));
-      }
-#endif
       if (child < TS) {
         c0 = K[child * HS];
         c1 = K[(child + 1) * HS];
@@ -591,16 +597,24 @@ struct LaneSearch {
     endG = endPoly;
     ep[0] = endPos[0]; ep[1] = endPos[1]; ep[2] = endPos[2];
     cv = corridorRing;
-    gen++;
     const PolyRec* spoly = &nav.polys[startG];
     const uint32_t slnk = spoly->linkStart | (static_cast<uint32_t>(spoly->linkCount) << 27);
     const float stotal = vdist(sp, ep) * kHScale;
-    storeRec(0, LaneRecA{sp[0], sp[1], sp[2], 0.f}, LaneRecB{startG, kLaneNoParent, slnk, 0u});
-    insert(spoly->key0, 0u);
-    hset(0, stotal, 0u);
+    uint32_t s0 = 0u;  // the start node
+    if constexpr (kGroups) {
+      dirLo = 0xffffffffu;
+      dirHi = 0u;
+      nGroups = 0u;
+      s0 = dirAlloc(spoly->key0, 0u);  // (a finished search has left the directory all zero)
+    } else {
+      gen++;
+      insert(spoly->key0, 0u);
+    }
+    storeRec(s0, LaneRecA{sp[0], sp[1], sp[2], 0.f}, LaneRecB{startG, kLaneNoParent, slnk, 0u});
+    hset(0, stotal, s0);
     size = 1;
     nodeCount = 1;
-    lastBest = 0;
+    lastBest = s0;
     lastBestG = startG;
     lastBestCost = stotal;
     outOfNodes = false;
@@ -612,6 +626,7 @@ struct LaneSearch {
 
   // DQ.cpp:1156-1164: status; the corridor is extracted when somebody will read it
   HBN_HD int finishSearch(bool allCorridors) {
+    clearDir();
     status = kDtSuccess;
     if (lastBestG != endG) status |= kDtPartialResult;
     if (outOfNodes) status |= kDtOutOfNodes;
@@ -647,7 +662,16 @@ struct LaneSearch {
         if (fastFail) *stop = kLEvPoolExhausted;  // PF.cpp:1450 has decided "no path" already
         return kOpNone;
       }
-      slot = static_cast<uint32_t>(nodeCount++);
+      if constexpr (kGroups) {
+        slot = dirAlloc(hi.neiKey, te);
+        if (slot == kNoPoly) {
+          *stop = kLEvOverflow;
+          return kOpNone;
+        }
+        nodeCount++;
+      } else {
+        slot = static_cast<uint32_t>(nodeCount++);
+      }
       npos[0] = lo.mx; npos[1] = lo.my; npos[2] = lo.mz;
     } else {
       slot = teSlot(te);
@@ -674,7 +698,8 @@ struct LaneSearch {
     storeRec(slot, LaneRecA{npos[0], npos[1], npos[2], cost},
              LaneRecB{nei, bestG | (viaJ << 24), hi.neiLinkStart | ((hi.meta >> kLinkNeiCountShift) << 27),
                       bslot | (1u << 12)});
-    if (!found) insert(hi.neiKey, slot);
+    if constexpr (!kGroups)
+      if (!found) insert(hi.neiKey, slot);
     if (heuristic < lastBestCost) {  // DQ.cpp:1154-1159
       lastBestCost = heuristic;
       lastBest = slot;
@@ -739,18 +764,6 @@ struct LaneSearch {
 #pragma unroll
           for (int k = 0; k < CH; ++k)
             if (k < cnt) asm volatile("prefetch.global.L1 [%0];" ::"l"(lp + 32 * k));
-          if constexpr (kTabPrefetch) {
-            // The table entries of the neighbours are a DRAM round trip that only starts after
-            // the sift-down today.  Their keys sit in the (L2-resident) link records: fetch those
-            // now and start the entries towards L2, so that round trip overlaps the sift's.
-            uint32_t nk[CH];
-#pragma unroll
-            for (int k = 0; k < CH; ++k)
-              nk[k] = k < cnt ? __ldg(reinterpret_cast<const uint32_t*>(lp + 32 * k + 28)) : 0u;
-#pragma unroll
-            for (int k = 0; k < CH; ++k)
-              if (k < cnt && nk[k] < nav.numKeys) asm volatile("prefetch.global.L2 [%0];" ::"l"(tab + nk[k]));
-          }
         }
 #endif
         heapPopSift(size);
@@ -766,6 +779,7 @@ struct LaneSearch {
           lastBestG = bestG;
           ev = finishSearch(allCorridors);
         } else if (expanded >= kLaneMaxExpansions) {
+          clearDir();
           mode = kLIdle;
           ev = kLEvFault;
         } else {
@@ -814,7 +828,7 @@ struct LaneSearch {
       for (int k = 0; k < kLaneChunk; ++k) {
         if (lo[k].nei != kNoPoly) nNeigh++;
         cand[k] = lo[k].nei != kNoPoly && lo[k].nei != parentG && (hi[k].meta & kLinkPassBit) != 0;
-        te[k] = cand[k] ? tabLoad(hi[k].neiKey) : 0u;
+        te[k] = cand[k] ? lookup(hi[k].neiKey) : 0u;
       }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -834,6 +848,49 @@ struct LaneSearch {
         qKey[k] = 0.f;
         qSlot[k] = 0u;
       }
+      if constexpr (kRolledVisit) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int k = 0; k < kLaneChunk; ++k) {
+          if (!warpAny(act && base + k < ln)) break;
+          // link k of the chunk, picked with compile-time register indices
+          LaneLinkLo l = lo[0];
+          LaneLinkHi h = hi[0];
+          uint32_t t = te[0];
+          LaneRecA r = ra[0];
+          bool c = cand[0];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+          for (int u = 1; u < kLaneChunk; ++u)
+            if (u == k) {
+              l = lo[u];
+              h = hi[u];
+              t = te[u];
+              r = ra[u];
+              c = cand[u];
+            }
+          if (c && stop == kLEvNone) {
+            float key = 0.f;
+            uint32_t slot = 0u;
+            const int op = visit(bslot, bestG, bpos, bcost, static_cast<uint32_t>(base + k), l, h, t, r, fastFail,
+                                 &stop, &key, &slot);
+            if (op != kOpNone) {
+              const uint32_t v = slot | (op == kOpModify ? 0x10000u : 0u);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+              for (int j = 0; j < kLaneChunk; ++j)
+                if (j == nq) {
+                  qKey[j] = key;
+                  qSlot[j] = v;
+                }
+              nq++;
+            }
+          }
+        }
+      } else {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -857,7 +914,49 @@ struct LaneSearch {
           }
         }
       }
+      }
       // replay: push = bubbleUp from the end, modify = locate + bubbleUp (DNode.h:118-142)
+      if constexpr (kRolledReplay) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int j = 0; j < kLaneChunk; ++j) {
+          if (!warpAny(j < nq)) break;
+          float key = qKey[0];
+          uint32_t qs = qSlot[0];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+          for (int t = 1; t < kLaneChunk; ++t)  // queue entry j with compile-time register indices
+            if (t == j) {
+              key = qKey[t];
+              qs = qSlot[t];
+            }
+          const bool mine = j < nq;
+          const bool isModify = mine && (qs & 0x10000u) != 0;
+          const uint32_t slot = qs & 0xffffu;
+          const int hp = findPosAll(isModify, slot);
+          if (mine) {
+            int pos = hp;
+            bool bubble = true;
+            if (isModify && (hp >= 0 || !kNoClosedStore)) {
+              if (hp < 0) stop = kLEvFault;  // an open node that is not in the heap would be a bug
+              pkValid = false;
+            } else {  // push (with kNoClosedStore also: the improved node was closed, DQ.cpp:1147-1152)
+              // bubbleUp's first comparison against the prefetched parent key: valid as long as
+              // no earlier operation of this expansion has moved an entry
+              pos = size;
+              bubble = !(pkValid && pushed < 2 && !((pushed == 0 ? pk0 : pk1) > key));
+              if (bubble) pkValid = false;
+              pushed++;
+              size++;
+            }
+            if (pos >= 0) {
+              heapUp(pos, key, slot, bubble);
+            }
+          }
+        }
+      } else {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -867,28 +966,6 @@ struct LaneSearch {
         const bool isModify = mine && (qSlot[j] & 0x10000u) != 0;
         const uint32_t slot = qSlot[j] & 0xffffu;
         const int hp = findPosAll(isModify, slot);
-        if constexpr (kHeap2) {
-          if (mine) {
-            int at = size;
-            bool pkv = false;
-            float pk = 0.f;
-            if (isModify) {
-              at = hp;
-              if (hp < 0) stop = kLEvFault;  // an open node that is not in the heap would be a bug
-            } else {
-              pkv = pkValid && pushed < 2;
-              pk = pushed == 0 ? pk0 : pk1;
-              pushed++;
-              size++;
-            }
-            // A key fetched at pop time may be stale by now, but only too LARGE: between two pops
-            // every operation is a bubble-up, which can only lower the key held at a position.
-            // So "parent <= new key" on the stale value implies it on the current one (the entry
-            // stays where it is), and in the other case heapUpK reloads.  No invalidation needed.
-            if (at >= 0) heapUpK(at, qKey[j], slot, pkv, pk);
-          }
-          continue;
-        }
         if (mine) {
           if (isModify && (hp >= 0 || !kNoClosedStore)) {
             if (hp < 0) stop = kLEvFault;  // an open node that is not in the heap would be a bug
@@ -908,13 +985,15 @@ struct LaneSearch {
           }
         }
       }
-      if (!kHeap2) pkValid = false;  // a further chunk of links starts from other positions
+      }
+      pkValid = false;  // a further chunk of links starts from other positions
     }
     if (stop == kLEvPoolExhausted) {
       ev = finishSearch(allCorridors);
-    } else if (stop == kLEvFault) {
+    } else if (stop == kLEvFault || stop == kLEvOverflow) {
+      clearDir();
       mode = kLIdle;
-      ev = kLEvFault;
+      ev = stop;
     }
     return ev;
   }

@@ -206,6 +206,8 @@ void emu_key_stats(void* h, long* out) {
 // out_corridor [n,256] poly refs of the (possibly truncated) corridor.
 }  // extern "C"
 
+static uint32_t g_groupCap = kLaneGroupsMax;  // emu_set_group_cap
+static long g_overflows = 0;
 template <int TS, int V>
 static void laneSearchRun(void* h, const float* starts, const float* ends, long n, int fastFail, int allCorridors,
                           unsigned* out_corridor, unsigned* out_info) {
@@ -220,10 +222,12 @@ static void laneSearchRun(void* h, const float* starts, const float* ends, long 
   std::vector<uint32_t> ring(kMaxPathPolys);
   LaneSearch<1, TS, 4, V> s{};  // 4 links per load stage, as shipped
   s.K = K.data(); s.S = S.data();
-  s.tab = reinterpret_cast<uint16_t*>(base);
-  s.rec = base + laneTabBytes(nav.numKeys);
-  s.G = reinterpret_cast<LaneHeapEnt*>(s.rec + kLaneRecBytes);
+  s.dir = reinterpret_cast<uint32_t*>(base);
+  s.tab = reinterpret_cast<uint16_t*>(base + laneDirBytes(nav.numKeys));
+  s.rec = base + laneDirBytes(nav.numKeys) + laneTabBytes(nav.numKeys);
+  s.G = reinterpret_cast<LaneHeapEnt*>(s.rec + kLaneRecBytesMax);
   s.gen = 0;
+  s.groupCap = g_groupCap;
   s.mode = kLIdle;
   for (long i = 0; i < n; ++i) {
     unsigned* o = out_info + i * 4;
@@ -233,15 +237,35 @@ static void laneSearchRun(void* h, const float* starts, const float* ends, long 
     if (a.g == kNoPoly || b.g == kNoPoly || vfuzzyEq(a.pt, b.pt)) continue;
     const int32_t si = nav.polys[a.g].island, ei = nav.polys[b.g].island;
     if (si < 0 || si != ei || a.g == b.g || !vfinite(a.pt) || !vfinite(b.pt)) continue;  // k_fp_classify
-    if (s.gen >= s.kGenMax) {
+    if (s.gen >= kLaneGenMax) {
       memset(s.tab, 0, laneTabBytes(nav.numKeys));
       s.gen = 0;
     }
     s.begin(nav, static_cast<uint32_t>(i), a.g, a.pt, b.g, b.pt, ring.data());
     int ev = kLEvNone;
     while (ev == kLEvNone) ev = s.step(nav, fastFail != 0, allCorridors != 0);
+    if (ev == kLEvOverflow) {  // as on the device: the query is redone by the table kernel
+      g_overflows++;
+      std::vector<char> scratch2(laneScratchBytes(nav.numKeys) + 64, 0);
+      char* base2 = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(scratch2.data()) + 15) & ~uintptr_t(15));
+      LaneSearch<1, TS, 4, 10> t{};
+      t.K = K.data(); t.S = S.data();
+      t.dir = reinterpret_cast<uint32_t*>(base2);
+      t.tab = reinterpret_cast<uint16_t*>(base2 + laneDirBytes(nav.numKeys));
+      t.rec = base2 + laneDirBytes(nav.numKeys) + laneTabBytes(nav.numKeys);
+      t.G = reinterpret_cast<LaneHeapEnt*>(t.rec + kLaneRecBytesMax);
+      t.gen = 0;
+      t.mode = kLIdle;
+      t.begin(nav, static_cast<uint32_t>(i), a.g, a.pt, b.g, b.pt, ring.data());
+      ev = kLEvNone;
+      while (ev == kLEvNone) ev = t.step(nav, fastFail != 0, allCorridors != 0);
+      s.status = t.status; s.xk = t.xk; s.nodeCount = t.nodeCount;
+    }
     o[3] = static_cast<unsigned>(ev);
-    if (ev != kLEvFinished) continue;
+    if (s.kGroups)  // a finished search leaves its node directory all zero
+      for (size_t w = 0; w < laneDirBytes(nav.numKeys) / 4; ++w)
+        if (s.dir[w] != 0) o[3] = kLEvFault;
+    if (o[3] != kLEvFinished) continue;
     o[0] = s.status;
     o[1] = static_cast<unsigned>(s.xk);
     o[2] = static_cast<unsigned>(s.nodeCount);
@@ -321,15 +345,7 @@ static long laneHeapFuzz(unsigned seed, long ops, int keyLevels) {
       const uint32_t node = nextNode++;
       keyOf[node] = key; open[node] = 1;
       ref.push(key, node);
-      if (h.kHeap2 && h.size > 0 && (rnd() & 1)) {  // with the parent key held, as the replay does
-        float pk; uint32_t ps;
-        h.hget((h.size - 1) >> 1, pk, ps);
-        h.heapUpK(h.size, key, node, true, pk);
-      } else if (h.kHeap2) {
-        h.heapUpK(h.size, key, node, false, 0.f);
-      } else {
-        h.heapUp(h.size, key, node);
-      }
+      h.heapUp(h.size, key, node);
       h.size++;
     } else if (r < 85) {
       const uint32_t a = ref.pop();
@@ -349,7 +365,7 @@ static long laneHeapFuzz(unsigned seed, long ops, int keyLevels) {
       ref.modify(node, key);
       const int pos = h.findPosAll(true, node);
       if (pos < 0) return op + 1;
-      if (h.kHeap2) h.heapUpK(pos, key, node, false, 0.f); else h.heapUp(pos, key, node);
+      h.heapUp(pos, key, node);
     }
     if (static_cast<size_t>(h.size) != ref.k.size()) return op + 1;
     for (int i = 0; i < h.size; ++i) {
@@ -365,7 +381,7 @@ static long laneHeapFuzz(unsigned seed, long ops, int keyLevels) {
 // step() both must hold the same heap (every entry), node count, best node and event -- a
 // difference that happens not to change the corridor still counts.  Returns 0, or 1 + the index
 // of the first query that diverges.
-template <int TS, int V>
+template <int TS, int V, int F = 0>
 static long laneLockstep(void* h, const float* starts, const float* ends, long n, int fastFail) {
   Emu* e = static_cast<Emu*>(h);
   HostGroup grp;
@@ -377,14 +393,16 @@ static long laneLockstep(void* h, const float* starts, const float* ends, long n
   std::vector<uint16_t> Sa(63), Sb(TS);
   std::vector<uint32_t> ra(kMaxPathPolys), rb(kMaxPathPolys);
   LaneSearch<1, 63, 4, 1> a{};
-  LaneSearch<1, TS, 4, V> b{};
+  LaneSearch<1, TS, 4, V, F> b{};
   auto carve = [&](auto& s, std::vector<char>& buf, std::vector<float>& K, std::vector<uint16_t>& S) {
     char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(buf.data()) + 15) & ~uintptr_t(15));
     s.K = K.data(); s.S = S.data();
-    s.tab = reinterpret_cast<uint16_t*>(base);
-    s.rec = base + laneTabBytes(nav.numKeys);
-    s.G = reinterpret_cast<LaneHeapEnt*>(s.rec + kLaneRecBytes);
+    s.dir = reinterpret_cast<uint32_t*>(base);
+    s.tab = reinterpret_cast<uint16_t*>(base + laneDirBytes(nav.numKeys));
+    s.rec = base + laneDirBytes(nav.numKeys) + laneTabBytes(nav.numKeys);
+    s.G = reinterpret_cast<LaneHeapEnt*>(s.rec + kLaneRecBytesMax);
     s.gen = 0;
+    s.groupCap = g_groupCap;
     s.mode = kLIdle;
   };
   carve(a, sa, Ka, Sa);
@@ -394,7 +412,7 @@ static long laneLockstep(void* h, const float* starts, const float* ends, long n
     const Nearest t = findNearestPoly(nav, grp, ends + 3 * i, kExt, -1, q);
     if (s.g == kNoPoly || t.g == kNoPoly || s.g == t.g) continue;
     if (nav.polys[s.g].island < 0 || nav.polys[s.g].island != nav.polys[t.g].island) continue;
-    if (a.gen >= a.kGenMax || b.gen >= b.kGenMax) {
+    if (a.gen >= kLaneGenMax || b.gen >= kLaneGenMax) {
       memset(a.tab, 0, laneTabBytes(nav.numKeys)); a.gen = 0;
       memset(b.tab, 0, laneTabBytes(nav.numKeys)); b.gen = 0;
     }
@@ -404,7 +422,15 @@ static long laneLockstep(void* h, const float* starts, const float* ends, long n
     while (ev == kLEvNone) {
       ev = a.step(nav, fastFail != 0, true);
       const int evb = b.step(nav, fastFail != 0, true);
-      if (ev != evb || a.size != b.size || a.nodeCount != b.nodeCount || a.lastBest != b.lastBest ||
+      if (b.kGroups && evb == kLEvOverflow) { ev = evb; break; }  // (the table kernel's job; not under test here)
+      // node ids are allocation order in one variant and group-relative in the other: the nodes are
+      // compared through the (poly, entering link) of their records
+      const auto same = [&](uint32_t na, uint32_t nb) {
+        if (!b.kGroups) return na == nb;
+        const LaneRecB x = *a.recB(na), y = *b.recB(nb);
+        return x.poly == y.poly && x.w1 == y.w1 && x.lnk == y.lnk && laneCost(a.recA(na)->cost) == laneCost(b.recA(nb)->cost);
+      };
+      if (ev != evb || a.size != b.size || a.nodeCount != b.nodeCount || !same(a.lastBest, b.lastBest) ||
           a.mode != b.mode || a.xk != b.xk)
         return i + 1;
       if (a.mode == kLSearch)
@@ -413,15 +439,25 @@ static long laneLockstep(void* h, const float* starts, const float* ends, long n
           uint32_t na, nb;
           a.hget(j, ka, na);
           b.hget(j, kb, nb);
-          if (ka != kb || na != nb) return i + 1;
+          if (ka != kb || !same(na, nb)) return i + 1;
         }
     }
+    if (ev == kLEvOverflow) continue;
     if (a.status != b.status || memcmp(ra.data(), rb.data(), sizeof(uint32_t) * kMaxPathPolys) != 0) return i + 1;
   }
   return 0;
 }
 
 extern "C" {
+
+// groups a search of the node-directory variants may open (default kLaneGroupsMax); returns the number of
+// searches that overflowed to the table variant since the last call
+long emu_set_group_cap(int cap) {
+  g_groupCap = cap < 1 ? 1u : static_cast<uint32_t>(cap);
+  const long r = g_overflows;
+  g_overflows = 0;
+  return r;
+}
 
 void emu_find_path_lane(void* h, const float* starts, const float* ends, long n, int fastFail, int allCorridors,
                         unsigned* out_corridor, unsigned* out_info) {
@@ -435,10 +471,84 @@ int emu_find_path_lane_v(void* h, int ts, int v, const float* starts, const floa
                          int allCorridors, unsigned* out_corridor, unsigned* out_info) {
 #define HBN_EMU_LANE(T, VV) \
   if (ts == T && v == VV) { laneSearchRun<T, VV>(h, starts, ends, n, fastFail, allCorridors, out_corridor, out_info); return 0; }
-  HBN_EMU_LANE(3, 1) HBN_EMU_LANE(3, 2) HBN_EMU_LANE(7, 2) HBN_EMU_LANE(31, 2) HBN_EMU_LANE(63, 2)
-  HBN_EMU_LANE(3, 9) HBN_EMU_LANE(63, 9) HBN_EMU_LANE(95, 9) HBN_EMU_LANE(71, 10)
+  HBN_EMU_LANE(3, 1) HBN_EMU_LANE(3, 9) HBN_EMU_LANE(63, 9) HBN_EMU_LANE(95, 9) HBN_EMU_LANE(71, 10) HBN_EMU_LANE(7, 10) HBN_EMU_LANE(31, 10)
+  HBN_EMU_LANE(71, 40) HBN_EMU_LANE(3, 40)
 #undef HBN_EMU_LANE
   return -1;
+}
+
+// Memory-locality statistics of the lane search on a sample of queries (tools/lane_stats.py; design aid for
+// the per-lane data layout).  out[0] searches, [1] expansions, [2] nodes allocated, [3] distinct 32 B sectors
+// of a u16-per-key table touched (summed over searches), [4] the same for a bit-per-key map, [5] sum over the
+// searches of the span (in 16 B units) between the lowest and highest touched map word, [6..] histogram of
+// the age (expansions since the node was allocated) of the popped node: <=1, <=2, <=4, ... <=1024, more.
+void emu_lane_stats(void* h, const float* starts, const float* ends, long n, long* out) {
+  Emu* e = static_cast<Emu*>(h);
+  HostGroup grp;
+  uint32_t q[2];
+  const NavView& nav = e->nav;
+  constexpr int TS = 71;
+  std::vector<char> scratch(laneScratchBytes(nav.numKeys) + 64, 0);
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(scratch.data()) + 15) & ~uintptr_t(15));
+  std::vector<float> K(TS);
+  std::vector<uint16_t> S(TS);
+  std::vector<uint32_t> ring(kMaxPathPolys);
+  LaneSearch<1, TS, 4, 10> s{};
+  s.K = K.data(); s.S = S.data();
+  s.dir = reinterpret_cast<uint32_t*>(base);
+  s.tab = reinterpret_cast<uint16_t*>(base + laneDirBytes(nav.numKeys));
+  s.rec = base + laneDirBytes(nav.numKeys) + laneTabBytes(nav.numKeys);
+  s.G = reinterpret_cast<LaneHeapEnt*>(s.rec + kLaneRecBytesMax);
+  s.gen = 0;
+  s.mode = kLIdle;
+  for (int i = 0; i < 32; ++i) out[i] = 0;
+  std::vector<long> born(kMaxNodes);
+  for (long i = 0; i < n; ++i) {
+    const Nearest a = findNearestPoly(nav, grp, starts + 3 * i, kExt, -1, q);
+    const Nearest b = findNearestPoly(nav, grp, ends + 3 * i, kExt, -1, q);
+    if (a.g == kNoPoly || b.g == kNoPoly || vfuzzyEq(a.pt, b.pt)) continue;
+    const int32_t si = nav.polys[a.g].island, ei = nav.polys[b.g].island;
+    if (si < 0 || si != ei || a.g == b.g || !vfinite(a.pt) || !vfinite(b.pt)) continue;
+    memset(s.tab, 0, laneTabBytes(nav.numKeys));
+    s.gen = 0;
+    s.begin(nav, static_cast<uint32_t>(i), a.g, a.pt, b.g, b.pt, ring.data());
+    int ev = kLEvNone;
+    long t = 0;
+    born[0] = 0;
+    while (ev == kLEvNone) {
+      const int before = s.nodeCount;
+      if (s.mode == kLSearch && s.size > 0) {
+        const long age = t - born[s.S[0]];
+        int bkt = 0;
+        while (bkt < 11 && age > (1L << bkt)) bkt++;
+        out[6 + bkt]++;
+        t++;
+      }
+      ev = s.step(nav, true, false);
+      for (int k = before; k < s.nodeCount; ++k) born[k] = t;
+    }
+    out[0]++;
+    out[1] += s.expanded;
+    out[2] += s.nodeCount;
+    long lastT = -1, lastB = -1, lo = -1, hi = -1;
+    for (uint32_t k = 0; k < nav.numKeys; ++k) {
+      if ((s.tab[k] >> kLaneSlotBits) != s.gen) continue;
+      if (static_cast<long>(k >> 4) != lastT) { lastT = k >> 4; out[3]++; }
+      if (static_cast<long>(k >> 8) != lastB) { lastB = k >> 8; out[4]++; }
+      if (lo < 0) lo = k >> 7;
+      hi = k >> 7;
+    }
+    out[5] += hi - lo + 1;
+    // distinct blocks of 8 / 16 / 32 keys: [18..20] sums, [21..23] maxima; [24] searches with > 256 16-key blocks
+    long cnt[3] = {0, 0, 0}, last[3] = {-1, -1, -1};
+    for (uint32_t k = 0; k < nav.numKeys; ++k) {
+      if ((s.tab[k] >> kLaneSlotBits) != s.gen) continue;
+      for (int b = 0; b < 3; ++b)
+        if (static_cast<long>(k >> (3 + b)) != last[b]) { last[b] = k >> (3 + b); cnt[b]++; }
+    }
+    for (int b = 0; b < 3; ++b) { out[18 + b] += cnt[b]; if (cnt[b] > out[21 + b]) out[21 + b] = cnt[b]; }
+    if (cnt[1] > 256) out[24]++;
+  }
 }
 
 // find_path(MultiGoalShortestPath), fresh object per start: ends [n, g, 3]
@@ -576,18 +686,22 @@ void emu_random_points_near(void* h, long n, const float* centers, float radius,
 // every operation.  Returns 0, the 1-based index of the first diverging operation, or -1.
 long emu_lane_heap_fuzz(int ts, int v, unsigned seed, long ops, int keyLevels) {
 #define HBN_EMU_HEAP(T, VV) if (ts == T && v == VV) return laneHeapFuzz<T, VV>(seed, ops, keyLevels);
-  HBN_EMU_HEAP(3, 1) HBN_EMU_HEAP(3, 2) HBN_EMU_HEAP(7, 2) HBN_EMU_HEAP(31, 2) HBN_EMU_HEAP(63, 1) HBN_EMU_HEAP(63, 2)
-  HBN_EMU_HEAP(47, 1) HBN_EMU_HEAP(47, 2) HBN_EMU_HEAP(55, 1) HBN_EMU_HEAP(39, 1)
+  HBN_EMU_HEAP(3, 1) HBN_EMU_HEAP(7, 1) HBN_EMU_HEAP(31, 1) HBN_EMU_HEAP(63, 1) HBN_EMU_HEAP(71, 10) HBN_EMU_HEAP(95, 10)
+  HBN_EMU_HEAP(47, 1) HBN_EMU_HEAP(55, 1) HBN_EMU_HEAP(39, 1)
 #undef HBN_EMU_HEAP
   return -1;
 }
 
 long emu_lane_lockstep(void* h, int ts, int v, const float* starts, const float* ends, long n, int fastFail) {
 #define HBN_EMU_LOCK(T, VV) if (ts == T && v == VV) return laneLockstep<T, VV>(h, starts, ends, n, fastFail);
-  HBN_EMU_LOCK(3, 1) HBN_EMU_LOCK(3, 2) HBN_EMU_LOCK(7, 2) HBN_EMU_LOCK(31, 2) HBN_EMU_LOCK(63, 2)
-  HBN_EMU_LOCK(47, 1) HBN_EMU_LOCK(47, 2) HBN_EMU_LOCK(55, 1) HBN_EMU_LOCK(39, 1) HBN_EMU_LOCK(63, 3) HBN_EMU_LOCK(47, 4) HBN_EMU_LOCK(63, 5) HBN_EMU_LOCK(63, 6) HBN_EMU_LOCK(59, 1) HBN_EMU_LOCK(95, 1) HBN_EMU_LOCK(63, 7)
-  HBN_EMU_LOCK(3, 9) HBN_EMU_LOCK(63, 9) HBN_EMU_LOCK(95, 9) HBN_EMU_LOCK(63, 10) HBN_EMU_LOCK(71, 10)
+#define HBN_EMU_LOCKF(T, VV, FF) if (ts == T && v == VV + 100 * FF) return laneLockstep<T, VV, FF>(h, starts, ends, n, fastFail);
+  // v = V + 100 * F: code-shape bits of LaneSearch (rolled loops, hoisted policies)
+  HBN_EMU_LOCKF(71, 10, 1) HBN_EMU_LOCKF(71, 40, 1) HBN_EMU_LOCKF(3, 40, 7) HBN_EMU_LOCKF(71, 40, 7) HBN_EMU_LOCKF(71, 10, 7) HBN_EMU_LOCKF(3, 10, 5)
+  HBN_EMU_LOCK(3, 1) HBN_EMU_LOCK(7, 1) HBN_EMU_LOCK(31, 1) HBN_EMU_LOCK(47, 1) HBN_EMU_LOCK(55, 1) HBN_EMU_LOCK(39, 1) HBN_EMU_LOCK(59, 1) HBN_EMU_LOCK(95, 1)
+  HBN_EMU_LOCK(3, 9) HBN_EMU_LOCK(63, 9) HBN_EMU_LOCK(95, 9) HBN_EMU_LOCK(63, 10) HBN_EMU_LOCK(71, 10) HBN_EMU_LOCK(95, 10) HBN_EMU_LOCK(63, 8)
+  HBN_EMU_LOCK(71, 40) HBN_EMU_LOCK(3, 40)
 #undef HBN_EMU_LOCK
+#undef HBN_EMU_LOCKF
   return -1;
 }
 

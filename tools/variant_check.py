@@ -38,7 +38,9 @@ def as_u32(a):
 img = navmesh_bytes("c4_building")
 base = None
 for cfg in (os.environ.get("VARIANT_CFGS") or "0,0k0,24,17,22,20,21,18,19,23,1,8,10,13,15").split(","):
-    os.environ["HBN_LANE_CFG"] = cfg.replace("k0", "")
+    # "50g40": cfg 50 with 40 directory groups per search (forces the overflow launch)
+    os.environ["HBN_LANE_CFG"] = cfg.replace("k0", "").split("g")[0]
+    os.environ["HBN_LANE_GROUP_CAP"] = cfg.split("g")[1] if "g" in cfg else "0"
     os.environ["HBN_KEY_ORDER"] = "0" if cfg.endswith("k0") else "1"  # k0: node keys in poly order
     pf = PathFinder(0)
     assert pf.load_nav_mesh_bytes(img)
