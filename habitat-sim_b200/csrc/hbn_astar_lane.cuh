@@ -13,13 +13,11 @@
 namespace hbn {
 
 struct LaneScratch {  // one slot per lane of the grid in each region
-  char* dir;            // node directories, dirBytes each (zeroed at allocation; a search leaves its directory zeroed)
   char* tab;            // node tables, tabBytes each (zeroed at allocation, wiped every 31 queries)
   char* rec;            // node records, kLaneRecBytes each
   char* heap;           // heap entries beyond the shared levels, kLaneHeapBytes each
   uint32_t* gen;        // table generation of every lane slot (persists across launches)
-  size_t tabBytes, dirBytes;
-  int groupCap;         // groups a search may open (kLaneGroupsMax; tests lower it to force the overflow path)
+  size_t tabBytes;
 };
 
 template <int TS>
@@ -49,11 +47,7 @@ __device__ __forceinline__ void astarLaneBody(const NavView& nav, const SearchAr
   s.S = reinterpret_cast<uint16_t*>(smem + static_cast<size_t>(TS) * 32 * 4) + lane;
   s.G = reinterpret_cast<LaneHeapEnt*>(sc.heap + slotId * kLaneHeapBytes);
   s.tab = reinterpret_cast<uint16_t*>(sc.tab + slotId * sc.tabBytes);
-  s.dir = reinterpret_cast<uint32_t*>(sc.dir + slotId * sc.dirBytes);
-  s.dirLo = 0xffffffffu; s.dirHi = 0u;
-  s.nGroups = 0u;
-  s.groupCap = static_cast<uint32_t>(sc.groupCap);
-  s.rec = sc.rec + slotId * kLaneRecBytesMax;
+  s.rec = sc.rec + slotId * kLaneRecBytes;
   s.cv = nullptr;
   s.gen = hasSlot ? sc.gen[slotId] : 0u;
   // A batch smaller than the grid is spread over more warps (a.laneLimit lanes each): the lanes
@@ -102,11 +96,7 @@ __device__ __forceinline__ void astarLaneBody(const NavView& nav, const SearchAr
     const int ev = s.step(nav, fastFail, allCorridors);
     if (ev != kLEvNone) {
       const uint32_t q = s.q;
-      if (ev == kLEvOverflow) {  // to the table kernel (launched after this one on the overflow list)
-        a.overflow[atomicAdd(a.overflowCount, 1u)] = q;
-        a.astat[q] = kSearchOverflow;
-        a.fullLen[q] = 0;
-      } else if (ev == kLEvFault) {
+      if (ev == kLEvFault) {
         atomicAdd(a.fault, 1u);
         a.fault[1] = q;
         a.fault[2] = 5u | (TS << 8);

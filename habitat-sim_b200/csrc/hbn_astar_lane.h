@@ -108,24 +108,12 @@ constexpr size_t kLaneRecBytes = static_cast<size_t>(kMaxNodes) * 32;
 // a multiple of 32: a 4-entry group of every lane's heap then sits in ONE 32 B sector
 constexpr size_t kLaneHeapBytes = (static_cast<size_t>(kMaxNodes + 2) * sizeof(LaneHeapEnt) + 31) & ~static_cast<size_t>(31);
 HBN_HD size_t laneTabBytes(uint32_t numKeys) { return (static_cast<size_t>(numKeys) * 2 + 15) & ~static_cast<size_t>(15); }
-// V >= 40: the node directory, one u32 per block of 16 node keys, in whole 32 B sectors
-constexpr uint32_t kLaneBlockShift = 4;                  // 16 keys per block = 16 records per group
-constexpr uint32_t kLaneBlockKeys = 1u << kLaneBlockShift;
-constexpr uint32_t kLaneGroupsMax = 256;                 // groups of 16 records a search may open
-constexpr uint32_t kLaneGroupNodes = kLaneGroupsMax * kLaneBlockKeys;  // node ids < 4096 (12 bits, LaneRecB::w3)
-HBN_HD size_t laneDirBytes(uint32_t numKeys) {
-  return ((static_cast<size_t>(numKeys) + kLaneBlockKeys * 8 - 1) / (kLaneBlockKeys * 8)) * 32;
-}
-// per lane: [directory | node table] (zeroed at allocation), records (by node id: 2048 in allocation order or 4096
-// in groups), heap tail.  One layout for every variant: the table variants ignore the directory and vice versa.
-constexpr size_t kLaneRecBytesMax = static_cast<size_t>(kLaneGroupNodes) * 32;
 HBN_HD size_t laneScratchBytes(uint32_t numKeys) {
-  return laneDirBytes(numKeys) + laneTabBytes(numKeys) + kLaneRecBytesMax + kLaneHeapBytes;
+  return laneTabBytes(numKeys) + kLaneRecBytes + kLaneHeapBytes;
 }
 
 enum { kLIdle = 0, kLSearch = 1, kLExtract = 2, kLDone = 3 };
-enum { kLEvNone = 0, kLEvFinished = 1, kLEvFault = 3, kLEvPoolExhausted = 4 /* internal */,
-       kLEvOverflow = 5 /* V >= 40: more than kLaneGroupsMax groups; the query goes to the table kernel */ };
+enum { kLEvNone = 0, kLEvFinished = 1, kLEvFault = 3, kLEvPoolExhausted = 4 /* internal */ };
 
 // KEEP: the link records are the read-only, L2-sized part of the working set (a few MB against GBs of
 // per-query search state streaming through L2): one 32 B load, evict_last in L1 and L2 (device only).
@@ -157,15 +145,19 @@ HBN_HD void laneLoadLink(const LinkRec* p, LaneLinkLo& lo, LaneLinkHi& hi) {
 // CH: links per load stage (registers vs. rounds); V: memory-policy variant (below).
 // step() contains warp collectives on the device: all 32 lanes of the warp must call it
 // together, whatever their mode.
-// F: code-shape bits.  The kernel is ~40 KB of SASS, more than the 32 KB instruction cache level next to the
-// SM (the profile shows warps waiting for instructions), so: 1 = the replay of the queued heap operations is
-// ONE loop body instead of kLaneChunk unrolled copies; 2 = the L2 cache policies are created once and kept in
-// registers instead of once per access.
+// F: code-shape bits.  With everything unrolled the kernel is 40.6 KB of SASS, more than the 32 KB
+// instruction cache level next to the SM, and its 16 warps sit at different places of it: the profile shows
+// 0.47 warps per issue slot waiting for instructions (profiles/r2_summary.md).  1 = the replay of the queued
+// heap operations is ONE loop body (findPosAll + bubbleUp inlined once, not kLaneChunk times): 29.8 KB;
+// 2 = the L2 cache policies are created once and kept in registers instead of once per access: 26.4 KB.
+// Shipped: F = 3 (-6 % per 1 M C4 queries).  Rolling the per-link cost tests too (21 KB) costs more in
+// register selects than it saves (+18 %); a node DIRECTORY instead of the node table (records addressed by
+// key in groups of 16, the directory L2-resident: -17 % DRAM bytes, bit-exact) was 10-16 % slower in every
+// code shape -- the kernel waits for latency, not for DRAM bandwidth.  Both are in the history (2759383).
 template <int HS, int TS, int CH, int V = 1, int F = 0>
 struct LaneSearch {
   static constexpr bool kRolledReplay = (F & 1) != 0;
   static constexpr bool kHoistPolicy = (F & 2) != 0;
-  static constexpr bool kRolledVisit = (F & 4) != 0;  // 4 = the per-link cost tests are one loop body as well
   static constexpr int kLaneChunk = CH;  // links handled per load stage
   // V = 1: every access at normal L2 priority, closed flag stored at every pop (round 1's kernel).
   // V >= 8: L2 residency by kind of data.  With every access at normal priority the 126 MB L2 keeps next
@@ -180,23 +172,9 @@ struct LaneSearch {
   // a few KB thanks to the space-filling key order).
   // V = 20..24 (diagnostic build only): one kind of data tagged with an eviction class at a time, so that
   // ncu's per-class L2 counters read per kind.
-  // V >= 40: NO node table.  A table lookup is a DRAM access (the u16 tables of the 75 k searches in flight,
-  // 87 sectors touched per search, are far beyond the L2), four in five of them only to learn that the node
-  // is new, and the revisits wait for two DRAM accesses in a row (table, then record) -- in lock step nearly
-  // every warp has one such lane per step.  Instead the records are addressed by KEY: the keys are numbered
-  // along a space-filling curve, so a search touches few blocks of 16 consecutive keys (87 on average, at
-  // most 214 on 20 k C4 queries); the first node of a block opens a GROUP of 16 records, and a DIRECTORY
-  // entry per block {16-bit mask of the keys allocated | group + 1 << 16} says where it is: node id =
-  // group * 16 + key % 16.  The directory is 2 bits per key: what a search touches of it (~20 sectors) stays
-  // in L2 (evict_last), so "new node" costs no DRAM access at all (the record store is a full sector: no
-  // fill) and a revisit costs one.  A search clears the directory words it has set when it ends; one that
-  // needs more than kLaneGroupsMax groups gives up (kLEvOverflow) and is redone by the table kernel (V = 10).
-  // Node ids are group-relative, not allocation order: nothing observable depends on the id (the pool limit
-  // counts nodes, ties in the heap are broken by heap position).
-  static constexpr bool kGroups = V >= 40 && V < 50;
   static constexpr bool kTabEvictLast = (V >= 10 && V < 20) || V == 20;
-  static constexpr bool kRecStream = (V >= 8 && V < 20) || V == 23 || kGroups;
-  static constexpr bool kLinkKeep = (V >= 8 && V < 20) || V == 22 || kGroups;
+  static constexpr bool kRecStream = (V >= 8 && V < 20) || V == 23;
+  static constexpr bool kLinkKeep = (V >= 8 && V < 20) || V == 22;
   static constexpr bool kNoClosedStore = V >= 9;
   static constexpr bool kHeapKeep = V == 21;
   static_assert((TS & 1) == 1, "TS must be odd");
@@ -205,7 +183,6 @@ struct LaneSearch {
   uint16_t* S;     // shared: heap nodes
   LaneHeapEnt* G;  // global: heap entries TS.. (entry j at G[j - TS])
   uint16_t* tab;   // node table
-  uint32_t* dir;   // node directory (kGroups)
   char* rec;       // node records
   uint32_t* cv;    // corridor ring of the current query (entering links, see ViaCorridor)
   // query
@@ -214,8 +191,6 @@ struct LaneSearch {
   // search state
   int mode, size, nodeCount;
   uint32_t gen;
-  uint32_t dirLo, dirHi;  // kGroups: first / last 16 B unit of the directory this search has written (lo > hi: none yet)
-  uint32_t nGroups, groupCap;  // kGroups: groups opened / allowed (kLaneGroupsMax; tests lower it)
   uint32_t lastBest, lastBestG;
   float lastBestCost;
   bool outOfNodes;
@@ -270,86 +245,10 @@ struct LaneSearch {
 #endif
     tab[key] = static_cast<uint16_t>(v);
   }
-  // ---- kGroups: directory entry of a key's block; te = found << 31 | (found ? node id : group + 1 of the block)
-  HBN_HD uint32_t dirLoad(const uint32_t key) const {
-#if defined(__CUDA_ARCH__)
-    unsigned long long pol;
-    uint32_t w;
-    // .cg: the entry is updated by a reduction in L2 (dirOr), an L1 copy could be stale
-    if constexpr (V == 41) {
-      asm volatile("ld.global.cg.b32 %0, [%1];" : "=r"(w) : "l"(dir + (key >> kLaneBlockShift)) : "memory");
-      return w;
-    }
-    pol = polLast();
-    asm volatile("ld.global.cg.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(w) : "l"(dir + (key >> kLaneBlockShift)), "l"(pol) : "memory");
-    return w;
-#else
-    return dir[key >> kLaneBlockShift];
-#endif
-  }
-  static HBN_HD uint32_t dirTe(const uint32_t e, const uint32_t key) {
-    const uint32_t k = key & (kLaneBlockKeys - 1u);
-    return ((e >> k) & 1u) ? (0x80000000u | ((((e >> 16) - 1u) << kLaneBlockShift) | k)) : (e >> 16);
-  }
-  HBN_HD void dirOr(const uint32_t key, const uint32_t v) {
-#if defined(__CUDA_ARCH__)
-    unsigned long long pol;
-    if constexpr (V == 41) {
-      asm volatile("red.global.or.b32 [%0], %1;" ::"l"(dir + (key >> kLaneBlockShift)), "r"(v) : "memory");
-    } else {
-      pol = polLast();
-      asm volatile("red.global.or.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(dir + (key >> kLaneBlockShift)), "r"(v), "l"(pol) : "memory");
-    }
-#else
-    dir[key >> kLaneBlockShift] |= v;
-#endif
-    const uint32_t u = key >> (kLaneBlockShift + 2);
-    dirLo = u < dirLo ? u : dirLo;
-    dirHi = u > dirHi ? u : dirHi;
-  }
-  // Node id of a key the search has not allocated yet: in the group of its block, opened now if it has none
-  // (g1 = group + 1 of the block as far as the caller knows, 0 = none).  kNoPoly: no group left.
-  HBN_HD uint32_t dirAlloc(const uint32_t key, uint32_t g1) {
-    const uint32_t k = key & (kLaneBlockKeys - 1u);
-    // no group seen: an earlier link of this expansion may have opened it since the entry was loaded
-    if (g1 == 0u) g1 = dirLoad(key) >> 16;
-    if (g1 == 0u) {
-      if (nGroups >= groupCap) return kNoPoly;
-      g1 = ++nGroups;
-      dirOr(key, (g1 << 16) | (1u << k));
-    } else {
-      dirOr(key, 1u << k);
-    }
-    return ((g1 - 1u) << kLaneBlockShift) | k;
-  }
-  // the end of a search: the directory goes back to all zero
-  HBN_HD void clearDir() {
-    if constexpr (kGroups) {
-      if (dirLo <= dirHi) {
-#if defined(__CUDA_ARCH__)
-        uint4* p = reinterpret_cast<uint4*>(dir);
-        for (uint32_t u = dirLo; u <= dirHi; ++u) p[u] = make_uint4(0u, 0u, 0u, 0u);
-#else
-        memset(dir + 4 * static_cast<size_t>(dirLo), 0, 16 * static_cast<size_t>(dirHi - dirLo + 1));
-#endif
-      }
-      dirLo = 0xffffffffu;
-      dirHi = 0u;
-    }
-  }
-  // a looked-up node: found? / which node
-  HBN_HD bool teFound(const uint32_t te) const {
-    if constexpr (kGroups) return (te >> 31) != 0u;
-    return (te >> kLaneSlotBits) == gen;
-  }
-  static HBN_HD uint32_t teSlot(const uint32_t te) {
-    if constexpr (kGroups) return te & (kLaneGroupNodes - 1u);
-    return te & kLaneSlotMask;
-  }
-  HBN_HD uint32_t lookup(const uint32_t key) const {
-    if constexpr (kGroups) return dirTe(dirLoad(key), key);
-    return tabLoad(key);
-  }
+  // a looked-up table entry: found? / which node
+  HBN_HD bool teFound(const uint32_t te) const { return (te >> kLaneSlotBits) == gen; }
+  static HBN_HD uint32_t teSlot(const uint32_t te) { return te & kLaneSlotMask; }
+  HBN_HD uint32_t lookup(const uint32_t key) const { return tabLoad(key); }
   HBN_HD void insert(const uint32_t key, const uint32_t slot) const { tabStore(key, (gen << kLaneSlotBits) | slot); }
   HBN_HD LaneRecA* recA(uint32_t s) const { return reinterpret_cast<LaneRecA*>(rec + static_cast<size_t>(s) * 32); }
   HBN_HD LaneRecB* recB(uint32_t s) const { return reinterpret_cast<LaneRecB*>(rec + static_cast<size_t>(s) * 32 + 16); }
@@ -600,21 +499,13 @@ struct LaneSearch {
     const PolyRec* spoly = &nav.polys[startG];
     const uint32_t slnk = spoly->linkStart | (static_cast<uint32_t>(spoly->linkCount) << 27);
     const float stotal = vdist(sp, ep) * kHScale;
-    uint32_t s0 = 0u;  // the start node
-    if constexpr (kGroups) {
-      dirLo = 0xffffffffu;
-      dirHi = 0u;
-      nGroups = 0u;
-      s0 = dirAlloc(spoly->key0, 0u);  // (a finished search has left the directory all zero)
-    } else {
-      gen++;
-      insert(spoly->key0, 0u);
-    }
-    storeRec(s0, LaneRecA{sp[0], sp[1], sp[2], 0.f}, LaneRecB{startG, kLaneNoParent, slnk, 0u});
-    hset(0, stotal, s0);
+    gen++;
+    storeRec(0, LaneRecA{sp[0], sp[1], sp[2], 0.f}, LaneRecB{startG, kLaneNoParent, slnk, 0u});
+    insert(spoly->key0, 0u);
+    hset(0, stotal, 0u);
     size = 1;
     nodeCount = 1;
-    lastBest = s0;
+    lastBest = 0;
     lastBestG = startG;
     lastBestCost = stotal;
     outOfNodes = false;
@@ -626,7 +517,6 @@ struct LaneSearch {
 
   // DQ.cpp:1156-1164: status; the corridor is extracted when somebody will read it
   HBN_HD int finishSearch(bool allCorridors) {
-    clearDir();
     status = kDtSuccess;
     if (lastBestG != endG) status |= kDtPartialResult;
     if (outOfNodes) status |= kDtOutOfNodes;
@@ -662,16 +552,7 @@ struct LaneSearch {
         if (fastFail) *stop = kLEvPoolExhausted;  // PF.cpp:1450 has decided "no path" already
         return kOpNone;
       }
-      if constexpr (kGroups) {
-        slot = dirAlloc(hi.neiKey, te);
-        if (slot == kNoPoly) {
-          *stop = kLEvOverflow;
-          return kOpNone;
-        }
-        nodeCount++;
-      } else {
-        slot = static_cast<uint32_t>(nodeCount++);
-      }
+      slot = static_cast<uint32_t>(nodeCount++);
       npos[0] = lo.mx; npos[1] = lo.my; npos[2] = lo.mz;
     } else {
       slot = teSlot(te);
@@ -698,8 +579,7 @@ struct LaneSearch {
     storeRec(slot, LaneRecA{npos[0], npos[1], npos[2], cost},
              LaneRecB{nei, bestG | (viaJ << 24), hi.neiLinkStart | ((hi.meta >> kLinkNeiCountShift) << 27),
                       bslot | (1u << 12)});
-    if constexpr (!kGroups)
-      if (!found) insert(hi.neiKey, slot);
+    if (!found) insert(hi.neiKey, slot);
     if (heuristic < lastBestCost) {  // DQ.cpp:1154-1159
       lastBestCost = heuristic;
       lastBest = slot;
@@ -779,7 +659,6 @@ struct LaneSearch {
           lastBestG = bestG;
           ev = finishSearch(allCorridors);
         } else if (expanded >= kLaneMaxExpansions) {
-          clearDir();
           mode = kLIdle;
           ev = kLEvFault;
         } else {
@@ -828,7 +707,7 @@ struct LaneSearch {
       for (int k = 0; k < kLaneChunk; ++k) {
         if (lo[k].nei != kNoPoly) nNeigh++;
         cand[k] = lo[k].nei != kNoPoly && lo[k].nei != parentG && (hi[k].meta & kLinkPassBit) != 0;
-        te[k] = cand[k] ? lookup(hi[k].neiKey) : 0u;
+        te[k] = cand[k] ? tabLoad(hi[k].neiKey) : 0u;
       }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -848,49 +727,6 @@ struct LaneSearch {
         qKey[k] = 0.f;
         qSlot[k] = 0u;
       }
-      if constexpr (kRolledVisit) {
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-        for (int k = 0; k < kLaneChunk; ++k) {
-          if (!warpAny(act && base + k < ln)) break;
-          // link k of the chunk, picked with compile-time register indices
-          LaneLinkLo l = lo[0];
-          LaneLinkHi h = hi[0];
-          uint32_t t = te[0];
-          LaneRecA r = ra[0];
-          bool c = cand[0];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-          for (int u = 1; u < kLaneChunk; ++u)
-            if (u == k) {
-              l = lo[u];
-              h = hi[u];
-              t = te[u];
-              r = ra[u];
-              c = cand[u];
-            }
-          if (c && stop == kLEvNone) {
-            float key = 0.f;
-            uint32_t slot = 0u;
-            const int op = visit(bslot, bestG, bpos, bcost, static_cast<uint32_t>(base + k), l, h, t, r, fastFail,
-                                 &stop, &key, &slot);
-            if (op != kOpNone) {
-              const uint32_t v = slot | (op == kOpModify ? 0x10000u : 0u);
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-              for (int j = 0; j < kLaneChunk; ++j)
-                if (j == nq) {
-                  qKey[j] = key;
-                  qSlot[j] = v;
-                }
-              nq++;
-            }
-          }
-        }
-      } else {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -913,7 +749,6 @@ struct LaneSearch {
             nq++;
           }
         }
-      }
       }
       // replay: push = bubbleUp from the end, modify = locate + bubbleUp (DNode.h:118-142)
       if constexpr (kRolledReplay) {
@@ -990,10 +825,9 @@ struct LaneSearch {
     }
     if (stop == kLEvPoolExhausted) {
       ev = finishSearch(allCorridors);
-    } else if (stop == kLEvFault || stop == kLEvOverflow) {
-      clearDir();
+    } else if (stop == kLEvFault) {
       mode = kLIdle;
-      ev = stop;
+      ev = kLEvFault;
     }
     return ev;
   }

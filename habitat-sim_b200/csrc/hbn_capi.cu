@@ -43,6 +43,7 @@ constexpr size_t kFpCounterBytes = (16 + 2 * 32) * 4;
 constexpr int kLaneTS = 71;    // lane-per-query search: heap entries per lane kept in shared memory (6 levels + 8)
 constexpr int kLaneWpb = 2;    // ... warps per block
 constexpr int kLaneMinB = 16;  // ... and resident warps per SM its register budget must allow
+constexpr int kLaneF = 3;     // ... and its code shape: one replay loop body, L2 policies created once (hbn_astar_lane.h)
 constexpr int kLaneV = 10;     // ... and its code variant: L2 residency by kind of data, no closed flag (hbn_astar_lane.h)
 constexpr int kSnapW = 8;     // lanes per point in k_snap
 constexpr int kRandW = 8;
@@ -92,7 +93,6 @@ struct Options {
   int blocksPerSm = 0;      // cap on resident one-warp blocks per SM of the search (0 = occupancy)
   int64_t laneScratchBytes = 0;  // cap on the per-lane search state in HBM (0 = half of the free memory)
   int nvtx = 1;             // NVTX range around every batched call
-  int groupCap = 0;         // testing: groups a node-directory search may open (0 = kLaneGroupsMax); small values force the overflow path
 };
 
 struct NvtxRange {
@@ -126,12 +126,11 @@ struct hbn_navmesh {
   DevBuf folS, folT, folE, folF, folGeo, folObs, folGeo0, folPos;  // batched follower: primitives of all agents
   DevBuf envG, envPt, envFlag, envPos;  // env step: find_path's start projection, fix-up flags, the goals' polys
   // find_path pipeline: class, cost class, search list, status, corridor rings
-  DevBuf fpCls, fpBucket, fpWork, fpStat, fpLen, fpCorr, fpOvf;
+  DevBuf fpCls, fpBucket, fpWork, fpStat, fpLen, fpCorr;
   DevBuf snapCnt, snapOff, snapG, snapQ, snapD, snapOut, snapBest, snapTmp, snapTodo;  // candidate-list snap (hbn_snap.cuh)
   // lane-per-query search: per-lane node table + records + heap tail in HBM, sized from the batch
   DevBuf wsLane, laneGen;
   int64_t laneSlots = 0;    // lane slots the scratch holds (tables zeroed, generations 0 when allocated)
-  bool laneDir = false;     // the configured search kernel keeps a node directory (scratch layout, overflow launch)
   int blocksFpLane = 0;     // resident WARPS of the search kernel (occupancy x SMs); the grid unit of laneGrid / laneScratch
   // pinned staging for the host-buffer entry points
   void* pinned = nullptr;
@@ -172,24 +171,15 @@ int upload(hbn_navmesh* nm, const std::vector<T>& v, const T** out) {
   return HBN_OK;
 }
 
-// Per-lane search state of k_astar_lane for a grid of `blocks` one-warp blocks: node directory, node records
-// and heap tail per lane slot, and a node table for the lane slots of table kernels -- every slot when the
-// table kernel is the configured one, else the first kLaneTabWarpsPerSm warps per SM (the grid of the kernel
-// that redoes the searches whose directory overflowed).  Sized from what the batch needs, grown on demand
-// (new directories and tables are zeroed, generations reset), capped by Options::laneScratchBytes or half of
-// the free device memory: under the cap the grid shrinks and every lane serves more queries.  On any
-// failure both buffers are released, so a later call starts from a clean state.
-constexpr int kLaneTabWarpsPerSm = 2;
-int64_t laneTabSlots(const hbn_navmesh* nm, int64_t slots) {
-  return nm->laneDir ? std::min<int64_t>(slots, static_cast<int64_t>(kLaneTabWarpsPerSm) * nm->smCount * 32) : slots;
-}
+// Per-lane search state of k_astar_lane (node table + node records + heap tail per lane slot) for a
+// grid of `blocks` one-warp blocks.  Sized from what the batch needs, grown on demand (new tables are
+// zeroed, generations reset), capped by Options::laneScratchBytes or half of the free device memory:
+// under the cap the grid shrinks and every lane serves more queries.  On any failure both buffers are
+// released, so a later call starts from a clean state.
 int laneScratch(hbn_navmesh* nm, cudaStream_t st, int* blocks, int lanesPerBlock, LaneScratch* out) {
-  const size_t tabB = laneTabBytes(nm->view.numKeys), dirB = laneDirBytes(nm->view.numKeys);
-  const size_t per = dirB + kLaneRecBytesMax + kLaneHeapBytes + (nm->laneDir ? 0 : tabB);
+  const size_t tabB = laneTabBytes(nm->view.numKeys);
+  const size_t per = laneScratchBytes(nm->view.numKeys);
   const auto slotsFor = [&](int64_t b) { return (b * lanesPerBlock + 31) / 32 * 32; };
-  const auto bytesFor = [&](int64_t slots) {
-    return static_cast<size_t>(slots) * per + (nm->laneDir ? static_cast<size_t>(laneTabSlots(nm, slots)) * tabB : 0);
-  };
   int64_t want = slotsFor(*blocks);
   if (want > nm->laneSlots) {
     size_t budget = nm->opt.laneScratchBytes > 0 ? static_cast<size_t>(nm->opt.laneScratchBytes) : 0;
@@ -198,22 +188,19 @@ int laneScratch(hbn_navmesh* nm, cudaStream_t st, int* blocks, int lanesPerBlock
       CK(cudaMemGetInfo(&freeB, &totalB));
       budget = (freeB + nm->wsLane.cap) / 2;
     }
-    int64_t maxSlots = static_cast<int64_t>(budget / (per + tabB)) / 32 * 32;  // (a lower bound under the cap)
-    while (bytesFor(maxSlots + 32) <= budget) maxSlots += 32;
+    const int64_t maxSlots = static_cast<int64_t>(budget / per) / 32 * 32;
     if (maxSlots < 32) return fail(HBN_ERR_CUDA, "not enough device memory for the find_path search state");
     if (want > maxSlots) want = maxSlots;
     if (want > nm->laneSlots) {
       nm->laneSlots = 0;
       int rc;
-      if ((rc = nm->wsLane.ensure(bytesFor(want), false)) ||
+      if ((rc = nm->wsLane.ensure(static_cast<size_t>(want) * per, false)) ||
           (rc = nm->laneGen.ensure(static_cast<size_t>(want) * 4, false))) {
         nm->wsLane.release();
         nm->laneGen.release();
         return rc;
       }
-      // directories and tables come first
-      const size_t zeroB = static_cast<size_t>(want) * dirB + static_cast<size_t>(laneTabSlots(nm, want)) * tabB;
-      if (cudaMemsetAsync(nm->wsLane.p, 0, zeroB, st) != cudaSuccess ||
+      if (cudaMemsetAsync(nm->wsLane.p, 0, static_cast<size_t>(want) * tabB, st) != cudaSuccess ||  // the tables come first
           cudaMemsetAsync(nm->laneGen.p, 0, static_cast<size_t>(want) * 4, st) != cudaSuccess) {
         nm->wsLane.release();
         nm->laneGen.release();
@@ -225,14 +212,11 @@ int laneScratch(hbn_navmesh* nm, cudaStream_t st, int* blocks, int lanesPerBlock
   if (slotsFor(*blocks) > nm->laneSlots) *blocks = static_cast<int>(std::max<int64_t>(1, nm->laneSlots / lanesPerBlock));
   const size_t lanes = static_cast<size_t>(nm->laneSlots);
   char* p = static_cast<char*>(nm->wsLane.p);
-  out->dir = p;
-  out->tab = p + lanes * dirB;
-  out->rec = out->tab + static_cast<size_t>(laneTabSlots(nm, nm->laneSlots)) * tabB;
-  out->heap = out->rec + lanes * kLaneRecBytesMax;
+  out->tab = p;
+  out->rec = p + lanes * tabB;
+  out->heap = out->rec + lanes * kLaneRecBytes;
   out->gen = static_cast<uint32_t*>(nm->laneGen.p);
   out->tabBytes = tabB;
-  out->dirBytes = dirB;
-  out->groupCap = nm->opt.groupCap > 0 ? std::min<int>(nm->opt.groupCap, kLaneGroupsMax) : static_cast<int>(kLaneGroupsMax);
   return HBN_OK;
 }
 
@@ -240,9 +224,8 @@ int laneScratch(hbn_navmesh* nm, cudaStream_t st, int* blocks, int lanesPerBlock
 // entries in shared memory, resident warps per SM, links per load stage, code variant V of LaneSearch.
 // All are bit-exact (tests/test_zz_tuning_variants.py); the measurements that picked the shipped one are in
 // profiles/r2_summary.md (and profiles/r1_summary.md for the variants deleted since).
-const void* laneKernel(int cfg, size_t* shared, int* wpb, bool* dir) {
+const void* laneKernel(int cfg, size_t* shared, int* wpb) {
   *wpb = 1;
-  *dir = false;
 #define HBN_LANE_CASE(N, TS, W, ...) \
   case N: *shared = laneSharedBytes<TS>() * W; *wpb = W; return reinterpret_cast<const void*>(&__VA_ARGS__);
   switch (cfg) {
@@ -251,27 +234,11 @@ const void* laneKernel(int cfg, size_t* shared, int* wpb, bool* dir) {
     HBN_LANE_CASE(30, 63, 1, k_astar_lane<63, 16, 4, 8>)      // records evict_first (32 B accesses), links evict_last: 146.8
     HBN_LANE_CASE(31, 63, 1, k_astar_lane<63, 16, 4, 9>)      // + no closed-flag store: 129.7
     HBN_LANE_CASE(32, 63, 1, k_astar_lane<63, 16, 4, 10>)     // + node table evict_last: 126.2
-    HBN_LANE_CASE(39, 63, 2, k_astar_lane<63, 16, 4, 10, 2>)  // the same in two-warp blocks: 126.2
     HBN_LANE_CASE(34, 95, 1, k_astar_lane<95, 11, 4, 10>)     // 95 shared heap entries at 11 warps per SM: 139.3
-    HBN_LANE_CASE(38, 71, 2, k_astar_lane<71, 16, 4, 10, 2>)  // two-warp blocks, 71 shared heap entries: 122.5
-    case 50: *dir = true;  // node directory instead of the node table (records addressed by key)
-    HBN_LANE_CASE(-50, 71, 2, k_astar_lane<71, 16, 4, 40, 2>)
-    case 51: *dir = true;  // the same without L2 policies on the directory
-    HBN_LANE_CASE(-51, 71, 2, k_astar_lane<71, 16, 4, 41, 2>)
-    // code size (instruction cache): rolled replay loop (1), policies created once (2)
-    HBN_LANE_CASE(60, 71, 2, k_astar_lane<71, 16, 4, 10, 2, 1>)
-    HBN_LANE_CASE(61, 71, 2, k_astar_lane<71, 16, 4, 10, 2, 3>)
-    case 62: *dir = true;
-    HBN_LANE_CASE(-62, 71, 2, k_astar_lane<71, 16, 4, 40, 2, 1>)
-    case 63: *dir = true;
-    HBN_LANE_CASE(-63, 71, 2, k_astar_lane<71, 16, 4, 40, 2, 3>)
-    case 64: *dir = true;
-    HBN_LANE_CASE(-64, 71, 2, k_astar_lane<71, 16, 4, 41, 2, 3>)
-    HBN_LANE_CASE(65, 71, 2, k_astar_lane<71, 16, 4, 10, 2, 7>)
-    case 66: *dir = true;
-    HBN_LANE_CASE(-66, 71, 2, k_astar_lane<71, 16, 4, 40, 2, 7>)
-    case 67: *dir = true;
-    HBN_LANE_CASE(-67, 71, 2, k_astar_lane<71, 16, 4, 41, 2, 7>)
+    // two-warp blocks (a block costs 1 KB of reserved shared memory) leave room for 71 heap entries per lane
+    // at 16 warps per SM: 122.5
+    HBN_LANE_CASE(38, 71, 2, k_astar_lane<71, 16, 4, 10, 2>)
+    HBN_LANE_CASE(60, 71, 2, k_astar_lane<71, 16, 4, 10, 2, 1>)  // + one replay loop body (40.6 -> 29.8 KB of SASS): 118.0
 #ifdef HBN_DIAG_KERNELS  // one kind of data tagged at a time: ncu's per-eviction-class L2 counters then read per kind
     HBN_LANE_CASE(40, 63, 1, k_astar_lane<63, 16, 4, 20>)  // node table
     HBN_LANE_CASE(41, 63, 1, k_astar_lane<63, 16, 4, 21>)  // heap tail
@@ -279,10 +246,9 @@ const void* laneKernel(int cfg, size_t* shared, int* wpb, bool* dir) {
     HBN_LANE_CASE(43, 63, 1, k_astar_lane<63, 16, 4, 23>)  // node records
     HBN_LANE_CASE(44, 63, 1, k_astar_lane<63, 16, 4, 24>)  // nothing tagged (no closed-flag store only)
 #endif
-    // shipped: two-warp blocks (a block costs 1 KB of reserved shared memory) leave room for 71 heap
-    // entries per lane at 16 warps per SM: 122.5
+    // shipped: + the L2 policies created once (26.9 KB of SASS, under the 32 KB instruction cache level): 115.2
     default: *shared = laneSharedBytes<kLaneTS>() * kLaneWpb; *wpb = kLaneWpb;
-             return reinterpret_cast<const void*>(&k_astar_lane<kLaneTS, kLaneMinB, 4, kLaneV, kLaneWpb>);
+             return reinterpret_cast<const void*>(&k_astar_lane<kLaneTS, kLaneMinB, 4, kLaneV, kLaneWpb, kLaneF>);
   }
 #undef HBN_LANE_CASE
 }
@@ -293,29 +259,10 @@ int envInt(const char* name, int dflt) {
 }
 
 // (re)select the search kernel of Options::laneCfg: shared-memory opt-in, occupancy, grid size
-// the table kernel that redoes the searches whose node directory overflowed
-constexpr int kLaneFallbackCfg = 38;
-
 int laneConfigure(hbn_navmesh* nm) {
   size_t smLane = 0;
   int wpb = 1;
-  bool dir = false;
-  const void* fn = laneKernel(nm->opt.laneCfg, &smLane, &wpb, &dir);
-  if (dir != nm->laneDir && nm->wsLane.p) {  // another scratch layout
-    CK(cudaDeviceSynchronize());
-    nm->wsLane.release();
-    nm->laneGen.release();
-    nm->laneSlots = 0;
-  }
-  nm->laneDir = dir;
-  if (dir) {
-    size_t sm2 = 0;
-    int wpb2 = 1;
-    bool dir2 = false;
-    const void* fb = laneKernel(kLaneFallbackCfg, &sm2, &wpb2, &dir2);
-    CK(cudaFuncSetAttribute(fb, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm2)));
-    CK(cudaFuncSetAttribute(fb, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  }
+  const void* fn = laneKernel(nm->opt.laneCfg, &smLane, &wpb);
   CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smLane)));
   CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   int occ = 0;
@@ -385,14 +332,6 @@ int finishCreate(HostNavMesh& meshIn, const int32_t* islands, const float* radii
   nm->opt.blocksPerSm = envInt("HBN_FP_BLOCKS_PER_SM", 0);
   nm->opt.laneScratchBytes = static_cast<int64_t>(envInt("HBN_LANE_SCRATCH_MB", 0)) << 20;
   nm->opt.nvtx = envInt("HBN_NVTX", 1);
-  nm->opt.groupCap = envInt("HBN_LANE_GROUP_CAP", 0);
-  if (const int mb = envInt("HBN_L2_PERSIST_MB", 0)) {  // experiment: L2 set-aside for evict_last / persisting lines
-    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, static_cast<size_t>(mb) << 20);
-    size_t got = 0;
-    cudaDeviceGetLimit(&got, cudaLimitPersistingL2CacheSize);
-    fprintf(stderr, "[hbn] persisting L2 limit %zu MB (max %d MB, L2 %d MB)\n", got >> 20, prop.persistingL2CacheMaxSize >> 20,
-            prop.l2CacheSize >> 20);
-  }
   CK(cudaEventCreateWithFlags(&nm->lastDone, cudaEventDisableTiming));
 
   // opt in to large dynamic shared memory and size the persistent grids from occupancy
@@ -618,7 +557,7 @@ void hbn_navmesh_destroy(hbn_navmesh_t nm) {
                     &nm->mgBounds, &nm->mgOrder, &nm->mgEnd, &nm->mgMask, &nm->envG, &nm->envPt, &nm->envFlag, &nm->envPos,
                     &nm->folS, &nm->folT, &nm->folE, &nm->folF, &nm->folGeo, &nm->folObs, &nm->folGeo0, &nm->folPos,
                     &nm->fpCls, &nm->fpWork, &nm->fpStat,
-                    &nm->fpLen, &nm->fpCorr, &nm->fpBucket, &nm->fpOvf, &nm->wsLane, &nm->laneGen, &nm->snapCnt, &nm->snapOff,
+                    &nm->fpLen, &nm->fpCorr, &nm->fpBucket, &nm->wsLane, &nm->laneGen, &nm->snapCnt, &nm->snapOff,
                     &nm->snapG, &nm->snapQ, &nm->snapD, &nm->snapOut, &nm->snapBest, &nm->snapTmp, &nm->snapTodo})
     b->release();
   if (nm->pinned) cudaFreeHost(nm->pinned);
@@ -696,7 +635,6 @@ int hbn_navmesh_set_option(hbn_navmesh_t nm, const char* key, int64_t value) {
   else if (k == "snap_group") nm->opt.snapGroup = value != 0;
   else if (k == "snap_cap") nm->opt.snapCap = value;
   else if (k == "nvtx") nm->opt.nvtx = value != 0;
-  else if (k == "lane_group_cap") nm->opt.groupCap = static_cast<int>(value);
   else if (k == "lane_scratch_bytes") {
     // a smaller cap takes effect at once: the search state is released and re-made on the next call
     nm->opt.laneScratchBytes = value;
@@ -718,7 +656,7 @@ int64_t hbn_navmesh_scratch_bytes(hbn_navmesh_t nm) {
                           &nm->lists, &nm->counters, &nm->wsL, &nm->io, &nm->work, &nm->mgDist, &nm->mgBounds,
                           &nm->mgOrder, &nm->mgEnd, &nm->mgMask, &nm->envG, &nm->envPt, &nm->envFlag, &nm->envPos,
                           &nm->folS, &nm->folT, &nm->folE, &nm->folF, &nm->folGeo, &nm->folObs, &nm->folGeo0, &nm->folPos,
-                          &nm->fpCls, &nm->fpWork, &nm->fpStat, &nm->fpLen, &nm->fpCorr, &nm->fpBucket, &nm->fpOvf, &nm->wsLane,
+                          &nm->fpCls, &nm->fpWork, &nm->fpStat, &nm->fpLen, &nm->fpCorr, &nm->fpBucket, &nm->wsLane,
                           &nm->laneGen, &nm->snapCnt, &nm->snapOff, &nm->snapG, &nm->snapQ, &nm->snapD, &nm->snapOut,
                           &nm->snapBest, &nm->snapTmp, &nm->snapTodo})
     total += static_cast<int64_t>(b->cap);
@@ -865,7 +803,6 @@ static int findPathReserve(hbn_navmesh* nm, int64_t n, int64_t nStarts, int star
   if ((rc = nm->sG.ensure(nStarts * 4)) || (rc = nm->eG.ensure(n * 4)) || (rc = nm->sPt.ensure(nStarts * 12)) ||
       (rc = nm->ePt.ensure(n * 12)) || (rc = nm->counters.ensure(static_cast<size_t>(nChunks) * kFpCounterBytes)) ||
       (rc = nm->fpCls.ensure(cmax)) || (rc = nm->fpBucket.ensure(cmax)) || (rc = nm->fpWork.ensure(cmax * 4)) ||
-      (rc = nm->fpOvf.ensure(cmax * 4)) ||
       (rc = nm->fpStat.ensure(cmax * 4)) || (rc = nm->fpLen.ensure(cmax * 4)) ||
       (rc = nm->fpCorr.ensure(static_cast<size_t>(cmax) * kMaxPathPolys * 4)))
     return rc;
@@ -975,33 +912,11 @@ static int findPathLaunch(hbn_navmesh_t nm, const float* starts, const float* en
       ga.numWarps = blocks;
       size_t smLane = 0;
       int wpb = 1;
-      bool dir = false;
-      const void* fn = laneKernel(nm->opt.laneCfg, &smLane, &wpb, &dir);
-      ga.overflow = static_cast<uint32_t*>(nm->fpOvf.p);
-      ga.overflowCount = cnt + 6;
+      const void* fn = laneKernel(nm->opt.laneCfg, &smLane, &wpb);
       void* kargs[] = {&nm->view, &ga, &sc};
       CK(cudaLaunchKernel(fn, dim3(static_cast<unsigned>((blocks + wpb - 1) / wpb)), dim3(32 * wpb), kargs, smLane, st));
       nm->launches++;
       CK(cudaGetLastError());
-      // Searches that ran out of directory groups are redone by the table kernel, which has no such limit.
-      // (A mesh with no more key blocks than groups cannot overflow: no second launch on its latency chain.)
-      if (dir && (nm->view.numKeys + kLaneBlockKeys - 1) / kLaneBlockKeys > static_cast<uint32_t>(sc.groupCap)) {
-        SearchArgs gb = ga;
-        gb.work = ga.overflow;
-        gb.workCount = ga.overflowCount;
-        gb.counter = cnt + 7;
-        gb.overflow = nullptr;
-        gb.overflowCount = nullptr;
-        gb.laneLimit = 32;
-        gb.numWarps = static_cast<int>(std::min<int64_t>(laneTabSlots(nm, nm->laneSlots) / 32, blocks));
-        if (gb.numWarps < 1) return fail(HBN_ERR_CUDA, "no search state for the overflow kernel");
-        bool dir2 = false;
-        const void* fb = laneKernel(kLaneFallbackCfg, &smLane, &wpb, &dir2);
-        void* kargs2[] = {&nm->view, &gb, &sc};
-        CK(cudaLaunchKernel(fb, dim3(static_cast<unsigned>((gb.numWarps + wpb - 1) / wpb)), dim3(32 * wpb), kargs2, smLane, st));
-        nm->launches++;
-        CK(cudaGetLastError());
-      }
     }
     FpFunnelArgs fa{};
     fa.starts = starts + 3 * s0; fa.ends = ends + 3 * c0;

@@ -34,8 +34,6 @@ struct SearchArgs {
   const uint32_t* work;       // queries that need a search (k_fp_classify)
   const uint32_t* workCount;
   uint32_t* counter;          // atomic work cursor
-  uint32_t* overflow;         // k_astar_lane with a node directory: queries that ran out of groups ...
-  uint32_t* overflowCount;    // ... and their number: the work list of the table kernel that follows
   uint32_t* astat;            // [n] findPath status word
   int32_t* fullLen;           // [n] untruncated corridor length (0 = not extracted)
   uint32_t* corrVia;          // [n, 256] corridor as entering links; element i at (first + i) & 255

@@ -1129,6 +1129,169 @@ HBN_HD uint32_t distanceToWall(const NavView& nav, const AStarWs& w, uint32_t st
 }
 
 // ---------------------------------------------------------------------------------------
+// The same search for ONE LANE (k_wall_lane: a query per thread).  The radius shrinks to the nearest wall
+// found so far, so the search stays tiny (at most 16 nodes on every query of the C2-C5 workloads at the
+// default 2 m radius, 5 m too): the whole node pool is C nodes of 6 words in shared memory, word j of a
+// thread at ws[j * S] (S = threads per block: conflict-free whatever the lanes index).  With so few
+// nodes the pool's hash and the heap's position array are linear scans, and a heap entry is just the
+// node index (its key is the node's total, which only changes together with the heap -- DQ.cpp:3625-3639).
+// Same operations in the same order as distanceToWall above; 0xffffffff = more than C nodes (the query
+// goes to the warp-per-query tiers).
+//   words [0,C) px  [C,2C) py  [2C,3C) pz  [3C,4C) total  [4C,5C) poly | open << 24 | closed << 25 |
+//   (parent node + 1) << 26   [5C,6C) heap
+// ---------------------------------------------------------------------------------------
+constexpr uint32_t kWsOpen = 1u << 24, kWsClosed = 1u << 25;
+constexpr int kWallLaneCap = 16;
+template <int C, int S>
+HBN_HD uint32_t distanceToWallSmall(const NavView& nav, uint32_t* ws, uint32_t startG, const float* centerPos,
+                                    float maxRadius, float* hitDist, float* hitPos, float* hitNormal) {
+  static_assert(C <= 32, "parent index + 1 must fit 6 bits");
+  if (startG == kNoPoly || !vfinite(centerPos) || maxRadius < 0 || !finitef(maxRadius))
+    return kDtFailure | kDtInvalidParam;
+  float* fw = reinterpret_cast<float*>(ws);
+#define HBN_WS(kind, i) ((kind) * C + (i)) * S
+  int nodeCount = 1, hsize = 1;
+  fw[HBN_WS(0, 0)] = centerPos[0]; fw[HBN_WS(1, 0)] = centerPos[1]; fw[HBN_WS(2, 0)] = centerPos[2];
+  fw[HBN_WS(3, 0)] = 0.f;
+  ws[HBN_WS(4, 0)] = startG | kWsOpen;
+  ws[HBN_WS(5, 0)] = 0u;
+  float radiusSqr = sqr(maxRadius);
+  // dtNodeQueue::bubbleUp (DNode.cpp:156-167) of `node` (total `key`) from heap position i
+  const auto bubbleUp = [&](int i, uint32_t node, float key) {
+    while (i > 0) {
+      const int parent = (i - 1) / 2;
+      const uint32_t pn = ws[HBN_WS(5, parent)];
+      if (!(fw[HBN_WS(3, pn)] > key)) break;
+      ws[HBN_WS(5, i)] = pn;
+      i = parent;
+    }
+    ws[HBN_WS(5, i)] = node;
+  };
+  while (hsize > 0) {
+    // pop (DNode.cpp:169-184 via DNode.h:124-130)
+    const uint32_t best = ws[HBN_WS(5, 0)];
+    hsize--;
+    {
+      const uint32_t last = ws[HBN_WS(5, hsize)];
+      const float lkey = fw[HBN_WS(3, last)];
+      int i = 0, child = 1;
+      while (child < hsize) {
+        uint32_t cn = ws[HBN_WS(5, child)];
+        if ((child + 1) < hsize) {
+          const uint32_t c1 = ws[HBN_WS(5, child + 1)];
+          if (fw[HBN_WS(3, cn)] > fw[HBN_WS(3, c1)]) {
+            cn = c1;
+            child++;
+          }
+        }
+        ws[HBN_WS(5, i)] = cn;
+        i = child;
+        child = (i * 2) + 1;
+      }
+      bubbleUp(i, last, lkey);
+    }
+    uint32_t bg = ws[HBN_WS(4, best)];
+    bg = (bg & ~kWsOpen) | kWsClosed;
+    ws[HBN_WS(4, best)] = bg;
+    const uint32_t bestG = bg & kNodeGMask;
+    const PolyRec* bp = &nav.polys[bestG];
+    const uint32_t ppi = bg >> 26;
+    const uint32_t parentG = ppi ? (ws[HBN_WS(4, ppi - 1)] & kNodeGMask) : kNoPoly;
+    const int nv = bp->nv;
+    const uint32_t l0 = bp->linkStart, ln = bp->linkCount;
+    // hit test walls
+    for (int i = 0, j = nv - 1; i < nv; j = i++) {
+      const uint16_t nj = bp->neis[j];
+      if (nj & kExtLink) {
+        bool solid = true;
+        for (uint32_t k = 0; k < ln; ++k) {
+          const LinkRec L = nav.links[l0 + k];
+          if ((L.meta & kLinkEdgeMask) == static_cast<uint32_t>(j)) {
+            if (L.nei != kNoPoly && (L.meta & kLinkPassBit)) solid = false;
+            break;
+          }
+        }
+        if (!solid) continue;
+      } else if (nj) {
+        const uint32_t g = nav.tiles[bp->tile].polyStart + static_cast<uint32_t>(nj - 1);
+        if ((nav.polys[g].flags & kFlagWalk) != 0) continue;
+      }
+      const float* vj = &bp->v[j * 3];
+      const float* vi = &bp->v[i * 3];
+      float tseg;
+      const float distSqr = distPtSegSqr2D(centerPos, vj, vi, tseg);
+      if (distSqr > radiusSqr) continue;
+      radiusSqr = distSqr;
+      hitPos[0] = vj[0] + (vi[0] - vj[0]) * tseg;
+      hitPos[1] = vj[1] + (vi[1] - vj[1]) * tseg;
+      hitPos[2] = vj[2] + (vi[2] - vj[2]) * tseg;
+    }
+    const float bpos[3] = {fw[HBN_WS(0, best)], fw[HBN_WS(1, best)], fw[HBN_WS(2, best)]};
+    const float btotal = fw[HBN_WS(3, best)];
+    for (uint32_t k = 0; k < ln; ++k) {
+      const LinkRec L = nav.links[l0 + k];
+      const uint32_t nei = L.nei;
+      if (nei == kNoPoly || nei == parentG) continue;
+      if (L.meta & kLinkOffmeshBit) continue;
+      const int edge = static_cast<int>(L.meta & kLinkEdgeMask);
+      const float* va = &bp->v[edge * 3];
+      const float* vb = &bp->v[((edge + 1) % nv) * 3];
+      float tseg;
+      const float distSqr = distPtSegSqr2D(centerPos, va, vb, tseg);
+      if (distSqr > radiusSqr) continue;
+      if ((L.meta & kLinkPassBit) == 0) continue;
+      // dtNodePool::getNode(nei, 0)
+      int n = -1;
+      for (int t = 0; t < nodeCount; ++t)
+        if ((ws[HBN_WS(4, t)] & kNodeGMask) == nei) {
+          n = t;
+          break;
+        }
+      const bool isNew = n < 0;
+      if (isNew) {
+        if (nodeCount >= C) return 0xffffffffu;
+        n = nodeCount++;
+        ws[HBN_WS(4, n)] = nei;
+        fw[HBN_WS(3, n)] = 0.f;
+      }
+      const uint32_t ng = ws[HBN_WS(4, n)];
+      if (ng & kWsClosed) continue;
+      float npos[3];
+      if (isNew) {
+        npos[0] = L.mid[0]; npos[1] = L.mid[1]; npos[2] = L.mid[2];
+        fw[HBN_WS(0, n)] = npos[0]; fw[HBN_WS(1, n)] = npos[1]; fw[HBN_WS(2, n)] = npos[2];
+      } else {
+        npos[0] = fw[HBN_WS(0, n)]; npos[1] = fw[HBN_WS(1, n)]; npos[2] = fw[HBN_WS(2, n)];
+      }
+      const float total = btotal + vdist(bpos, npos);
+      if ((ng & kWsOpen) && total >= fw[HBN_WS(3, n)]) continue;
+      fw[HBN_WS(3, n)] = total;
+      if (ng & kWsOpen) {
+        ws[HBN_WS(4, n)] = (ng & 0x03ffffffu) | ((best + 1u) << 26);
+        int pos = 0;
+        while (ws[HBN_WS(5, pos)] != static_cast<uint32_t>(n)) pos++;  // dtNodeQueue::modify's scan
+        bubbleUp(pos, static_cast<uint32_t>(n), total);
+      } else {
+        ws[HBN_WS(4, n)] = (ng & 0x03ffffffu) | kWsOpen | ((best + 1u) << 26);
+        hsize++;
+        bubbleUp(hsize - 1, static_cast<uint32_t>(n), total);
+      }
+    }
+  }
+#undef HBN_WS
+  // hit normal (dtVsub + dtVnormalize, DetourCommon.h:263-269)
+  hitNormal[0] = centerPos[0] - hitPos[0];
+  hitNormal[1] = centerPos[1] - hitPos[1];
+  hitNormal[2] = centerPos[2] - hitPos[2];
+  const float d = 1.0f / fsqrt(sqr(hitNormal[0]) + sqr(hitNormal[1]) + sqr(hitNormal[2]));
+  hitNormal[0] *= d;
+  hitNormal[1] *= d;
+  hitNormal[2] *= d;
+  *hitDist = fsqrt(radiusSqr);
+  return kDtSuccess;
+}
+
+// ---------------------------------------------------------------------------------------
 // findRandomPoint, DQ.cpp:226-315 + dtRandomPointInConvexPoly DetourCommon.cpp:332-369.
 // The reference consumes its uniform stream sequentially: one draw per tile with a header,
 // one per ground poly passing the filter in the chosen tile, then s and t.  With a

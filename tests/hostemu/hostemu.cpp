@@ -206,9 +206,7 @@ void emu_key_stats(void* h, long* out) {
 // out_corridor [n,256] poly refs of the (possibly truncated) corridor.
 }  // extern "C"
 
-static uint32_t g_groupCap = kLaneGroupsMax;  // emu_set_group_cap
-static long g_overflows = 0;
-template <int TS, int V>
+template <int TS, int V, int F = 0>
 static void laneSearchRun(void* h, const float* starts, const float* ends, long n, int fastFail, int allCorridors,
                           unsigned* out_corridor, unsigned* out_info) {
   Emu* e = static_cast<Emu*>(h);
@@ -220,14 +218,12 @@ static void laneSearchRun(void* h, const float* starts, const float* ends, long 
   std::vector<float> K(TS);
   std::vector<uint16_t> S(TS);
   std::vector<uint32_t> ring(kMaxPathPolys);
-  LaneSearch<1, TS, 4, V> s{};  // 4 links per load stage, as shipped
+  LaneSearch<1, TS, 4, V, F> s{};  // 4 links per load stage, as shipped
   s.K = K.data(); s.S = S.data();
-  s.dir = reinterpret_cast<uint32_t*>(base);
-  s.tab = reinterpret_cast<uint16_t*>(base + laneDirBytes(nav.numKeys));
-  s.rec = base + laneDirBytes(nav.numKeys) + laneTabBytes(nav.numKeys);
-  s.G = reinterpret_cast<LaneHeapEnt*>(s.rec + kLaneRecBytesMax);
+  s.tab = reinterpret_cast<uint16_t*>(base);
+  s.rec = base + laneTabBytes(nav.numKeys);
+  s.G = reinterpret_cast<LaneHeapEnt*>(s.rec + kLaneRecBytes);
   s.gen = 0;
-  s.groupCap = g_groupCap;
   s.mode = kLIdle;
   for (long i = 0; i < n; ++i) {
     unsigned* o = out_info + i * 4;
@@ -244,27 +240,7 @@ static void laneSearchRun(void* h, const float* starts, const float* ends, long 
     s.begin(nav, static_cast<uint32_t>(i), a.g, a.pt, b.g, b.pt, ring.data());
     int ev = kLEvNone;
     while (ev == kLEvNone) ev = s.step(nav, fastFail != 0, allCorridors != 0);
-    if (ev == kLEvOverflow) {  // as on the device: the query is redone by the table kernel
-      g_overflows++;
-      std::vector<char> scratch2(laneScratchBytes(nav.numKeys) + 64, 0);
-      char* base2 = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(scratch2.data()) + 15) & ~uintptr_t(15));
-      LaneSearch<1, TS, 4, 10> t{};
-      t.K = K.data(); t.S = S.data();
-      t.dir = reinterpret_cast<uint32_t*>(base2);
-      t.tab = reinterpret_cast<uint16_t*>(base2 + laneDirBytes(nav.numKeys));
-      t.rec = base2 + laneDirBytes(nav.numKeys) + laneTabBytes(nav.numKeys);
-      t.G = reinterpret_cast<LaneHeapEnt*>(t.rec + kLaneRecBytesMax);
-      t.gen = 0;
-      t.mode = kLIdle;
-      t.begin(nav, static_cast<uint32_t>(i), a.g, a.pt, b.g, b.pt, ring.data());
-      ev = kLEvNone;
-      while (ev == kLEvNone) ev = t.step(nav, fastFail != 0, allCorridors != 0);
-      s.status = t.status; s.xk = t.xk; s.nodeCount = t.nodeCount;
-    }
     o[3] = static_cast<unsigned>(ev);
-    if (s.kGroups)  // a finished search leaves its node directory all zero
-      for (size_t w = 0; w < laneDirBytes(nav.numKeys) / 4; ++w)
-        if (s.dir[w] != 0) o[3] = kLEvFault;
     if (o[3] != kLEvFinished) continue;
     o[0] = s.status;
     o[1] = static_cast<unsigned>(s.xk);
@@ -397,13 +373,11 @@ static long laneLockstep(void* h, const float* starts, const float* ends, long n
   auto carve = [&](auto& s, std::vector<char>& buf, std::vector<float>& K, std::vector<uint16_t>& S) {
     char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(buf.data()) + 15) & ~uintptr_t(15));
     s.K = K.data(); s.S = S.data();
-    s.dir = reinterpret_cast<uint32_t*>(base);
-    s.tab = reinterpret_cast<uint16_t*>(base + laneDirBytes(nav.numKeys));
-    s.rec = base + laneDirBytes(nav.numKeys) + laneTabBytes(nav.numKeys);
-    s.G = reinterpret_cast<LaneHeapEnt*>(s.rec + kLaneRecBytesMax);
+    s.tab = reinterpret_cast<uint16_t*>(base);
+    s.rec = base + laneTabBytes(nav.numKeys);
+    s.G = reinterpret_cast<LaneHeapEnt*>(s.rec + kLaneRecBytes);
     s.gen = 0;
-    s.groupCap = g_groupCap;
-    s.mode = kLIdle;
+      s.mode = kLIdle;
   };
   carve(a, sa, Ka, Sa);
   carve(b, sb, Kb, Sb);
@@ -422,15 +396,7 @@ static long laneLockstep(void* h, const float* starts, const float* ends, long n
     while (ev == kLEvNone) {
       ev = a.step(nav, fastFail != 0, true);
       const int evb = b.step(nav, fastFail != 0, true);
-      if (b.kGroups && evb == kLEvOverflow) { ev = evb; break; }  // (the table kernel's job; not under test here)
-      // node ids are allocation order in one variant and group-relative in the other: the nodes are
-      // compared through the (poly, entering link) of their records
-      const auto same = [&](uint32_t na, uint32_t nb) {
-        if (!b.kGroups) return na == nb;
-        const LaneRecB x = *a.recB(na), y = *b.recB(nb);
-        return x.poly == y.poly && x.w1 == y.w1 && x.lnk == y.lnk && laneCost(a.recA(na)->cost) == laneCost(b.recA(nb)->cost);
-      };
-      if (ev != evb || a.size != b.size || a.nodeCount != b.nodeCount || !same(a.lastBest, b.lastBest) ||
+      if (ev != evb || a.size != b.size || a.nodeCount != b.nodeCount || a.lastBest != b.lastBest ||
           a.mode != b.mode || a.xk != b.xk)
         return i + 1;
       if (a.mode == kLSearch)
@@ -439,10 +405,9 @@ static long laneLockstep(void* h, const float* starts, const float* ends, long n
           uint32_t na, nb;
           a.hget(j, ka, na);
           b.hget(j, kb, nb);
-          if (ka != kb || !same(na, nb)) return i + 1;
+          if (ka != kb || na != nb) return i + 1;
         }
     }
-    if (ev == kLEvOverflow) continue;
     if (a.status != b.status || memcmp(ra.data(), rb.data(), sizeof(uint32_t) * kMaxPathPolys) != 0) return i + 1;
   }
   return 0;
@@ -450,18 +415,9 @@ static long laneLockstep(void* h, const float* starts, const float* ends, long n
 
 extern "C" {
 
-// groups a search of the node-directory variants may open (default kLaneGroupsMax); returns the number of
-// searches that overflowed to the table variant since the last call
-long emu_set_group_cap(int cap) {
-  g_groupCap = cap < 1 ? 1u : static_cast<uint32_t>(cap);
-  const long r = g_overflows;
-  g_overflows = 0;
-  return r;
-}
-
 void emu_find_path_lane(void* h, const float* starts, const float* ends, long n, int fastFail, int allCorridors,
                         unsigned* out_corridor, unsigned* out_info) {
-  laneSearchRun<63, 1>(h, starts, ends, n, fastFail, allCorridors, out_corridor, out_info);  // the shipped configuration
+  laneSearchRun<71, 10, 3>(h, starts, ends, n, fastFail, allCorridors, out_corridor, out_info);  // the shipped configuration
 }
 
 // The same with `ts` heap entries in the "shared" array (small values push most heap levels
@@ -472,7 +428,6 @@ int emu_find_path_lane_v(void* h, int ts, int v, const float* starts, const floa
 #define HBN_EMU_LANE(T, VV) \
   if (ts == T && v == VV) { laneSearchRun<T, VV>(h, starts, ends, n, fastFail, allCorridors, out_corridor, out_info); return 0; }
   HBN_EMU_LANE(3, 1) HBN_EMU_LANE(3, 9) HBN_EMU_LANE(63, 9) HBN_EMU_LANE(95, 9) HBN_EMU_LANE(71, 10) HBN_EMU_LANE(7, 10) HBN_EMU_LANE(31, 10)
-  HBN_EMU_LANE(71, 40) HBN_EMU_LANE(3, 40)
 #undef HBN_EMU_LANE
   return -1;
 }
@@ -495,10 +450,9 @@ void emu_lane_stats(void* h, const float* starts, const float* ends, long n, lon
   std::vector<uint32_t> ring(kMaxPathPolys);
   LaneSearch<1, TS, 4, 10> s{};
   s.K = K.data(); s.S = S.data();
-  s.dir = reinterpret_cast<uint32_t*>(base);
-  s.tab = reinterpret_cast<uint16_t*>(base + laneDirBytes(nav.numKeys));
-  s.rec = base + laneDirBytes(nav.numKeys) + laneTabBytes(nav.numKeys);
-  s.G = reinterpret_cast<LaneHeapEnt*>(s.rec + kLaneRecBytesMax);
+  s.tab = reinterpret_cast<uint16_t*>(base);
+  s.rec = base + laneTabBytes(nav.numKeys);
+  s.G = reinterpret_cast<LaneHeapEnt*>(s.rec + kLaneRecBytes);
   s.gen = 0;
   s.mode = kLIdle;
   for (int i = 0; i < 32; ++i) out[i] = 0;
@@ -695,11 +649,10 @@ long emu_lane_heap_fuzz(int ts, int v, unsigned seed, long ops, int keyLevels) {
 long emu_lane_lockstep(void* h, int ts, int v, const float* starts, const float* ends, long n, int fastFail) {
 #define HBN_EMU_LOCK(T, VV) if (ts == T && v == VV) return laneLockstep<T, VV>(h, starts, ends, n, fastFail);
 #define HBN_EMU_LOCKF(T, VV, FF) if (ts == T && v == VV + 100 * FF) return laneLockstep<T, VV, FF>(h, starts, ends, n, fastFail);
-  // v = V + 100 * F: code-shape bits of LaneSearch (rolled loops, hoisted policies)
-  HBN_EMU_LOCKF(71, 10, 1) HBN_EMU_LOCKF(71, 40, 1) HBN_EMU_LOCKF(3, 40, 7) HBN_EMU_LOCKF(71, 40, 7) HBN_EMU_LOCKF(71, 10, 7) HBN_EMU_LOCKF(3, 10, 5)
+  // v = V + 100 * F: code-shape bits of LaneSearch (one replay loop body, policies created once)
+  HBN_EMU_LOCKF(71, 10, 1) HBN_EMU_LOCKF(71, 10, 3) HBN_EMU_LOCKF(3, 10, 3) HBN_EMU_LOCKF(63, 1, 1)
   HBN_EMU_LOCK(3, 1) HBN_EMU_LOCK(7, 1) HBN_EMU_LOCK(31, 1) HBN_EMU_LOCK(47, 1) HBN_EMU_LOCK(55, 1) HBN_EMU_LOCK(39, 1) HBN_EMU_LOCK(59, 1) HBN_EMU_LOCK(95, 1)
   HBN_EMU_LOCK(3, 9) HBN_EMU_LOCK(63, 9) HBN_EMU_LOCK(95, 9) HBN_EMU_LOCK(63, 10) HBN_EMU_LOCK(71, 10) HBN_EMU_LOCK(95, 10) HBN_EMU_LOCK(63, 8)
-  HBN_EMU_LOCK(71, 40) HBN_EMU_LOCK(3, 40)
 #undef HBN_EMU_LOCK
 #undef HBN_EMU_LOCKF
   return -1;

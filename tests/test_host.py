@@ -250,7 +250,7 @@ def test_hostemu_lane_search_matches_oracle(name):
     emu.emu_destroy(h)
 
 
-@pytest.mark.parametrize("ts,v", [(3, 1), (3, 9), (7, 10), (31, 10), (63, 9), (95, 9), (71, 10), (71, 40), (3, 40)])
+@pytest.mark.parametrize("ts,v", [(3, 1), (3, 9), (7, 10), (31, 10), (63, 9), (95, 9), (71, 10)])
 @pytest.mark.parametrize("name", ["c3_multiroom", "c4_building"])
 def test_hostemu_lane_search_variants(name, ts, v):
     """The variants of hbn_astar_lane.h (V = 9 / 10: no closed flag -- a re-improved node is looked for
@@ -293,40 +293,6 @@ def test_hostemu_lane_search_variants(name, ts, v):
     emu.emu_destroy(h)
 
 
-@pytest.mark.parametrize("cap", [1, 4, 40])
-def test_hostemu_lane_directory_overflow(cap):
-    """The node-directory search (V = 40) with few groups allowed: a search that runs out of groups gives up,
-    leaves its directory zeroed and is redone by the table variant -- results are Detour's either way."""
-    name = "c4_building"
-    emu, h = _emu_handle(name)
-    pf = ref_pathfinder(name)
-    n = 500
-    from workloads.scenes import NavMeshGeom, pointnav_pairs
-    st, en = pointnav_pairs(NavMeshGeom(navmesh_image(name)), n, 11)
-    r = pf.find_path_raw_batch(st, en)
-    emu.emu_find_path_lane_v.restype = C.c_int
-    emu.emu_set_group_cap.restype = C.c_long
-    emu.emu_set_group_cap(cap)
-    try:
-        corr = np.zeros((n, 256), np.uint32)
-        info = np.zeros((n, 4), np.uint32)
-        assert emu.emu_find_path_lane_v(h, 71, 40, P(st, f32p), P(en, f32p), C.c_long(n), 0, 1, P(corr, u32p),
-                                        P(info, u32p)) == 0
-    finally:
-        overflows = emu.emu_set_group_cap(256)
-    assert overflows > (n // 3 if cap <= 4 else 0)
-    assert (info[:, 3] != 3).all(), "fault event"
-    done = info[:, 3] == 1
-    assert done.sum() > n // 2
-    assert (info[done, 0] == r["astar_status"][done]).all()
-    assert (info[done, 2] == r["nodes_used"][done]).all()
-    for i in np.nonzero(done)[0]:
-        k = r["num_polys"][i]
-        assert min(info[i, 1], 256) == k
-        assert (corr[i, :k] == r["corridor"][i, :k]).all(), i
-    emu.emu_destroy(h)
-
-
 @pytest.mark.parametrize("ts,v", [(3, 1), (7, 1), (31, 1), (39, 1), (47, 1), (55, 1), (63, 1), (71, 10), (95, 10)])
 def test_hostemu_lane_heap_fuzz(ts, v):
     """The heap code of hbn_astar_lane.h (two-level storage, one or two levels per round trip)
@@ -340,8 +306,7 @@ def test_hostemu_lane_heap_fuzz(ts, v):
             assert emu.emu_lane_heap_fuzz(ts, v, seed, C.c_long(8000), levels) == 0, (levels, seed)
 
 
-@pytest.mark.parametrize("ts,v", [(3, 1), (7, 1), (31, 1), (39, 1), (47, 1), (55, 1), (59, 1), (95, 1), (3, 9), (63, 8), (63, 9), (95, 9), (63, 10), (71, 10), (95, 10), (71, 40), (3, 40),
-                                  (71, 110), (71, 140), (3, 740), (71, 740), (71, 710), (3, 510)])
+@pytest.mark.parametrize("ts,v", [(3, 1), (7, 1), (31, 1), (39, 1), (47, 1), (55, 1), (59, 1), (95, 1), (3, 9), (63, 8), (63, 9), (95, 9), (63, 10), (71, 10), (95, 10), (71, 110), (71, 310), (3, 310), (63, 101)])
 @pytest.mark.parametrize("name", ["c3_multiroom", "c4_building"])
 def test_hostemu_lane_variants_lockstep(name, ts, v):
     """Every variant in lock step with the shipped one: same heap entries, node count, best node

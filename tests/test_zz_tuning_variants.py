@@ -1,6 +1,6 @@
 """GPU parity of the tuning variants: HBN_LANE_CFG = other instantiations of k_astar_lane (shared
-heap entries, warps per SM, links per stage, heap code variant 2, prefetches; opt-in, none
-faster so far), lane spreading (a batch smaller than the grid uses fewer lanes per warp) and
+heap entries, warps per SM, L2 policies, code shape; opt-in, the steps that led to the shipped one),
+lane spreading (a batch smaller than the grid uses fewer lanes per warp) and
 the small-batch snap launches (one lane group per warp, two batches per launch); the last
 three are on by default and can be switched off (HBN_LANE_SPREAD / HBN_SNAP_SPREAD /
 HBN_SNAP_DUAL = 0).  Their host twins are checked on the CPU
@@ -41,9 +41,9 @@ def _pairs(name, n, seed):
     return pts[:n].copy(), pts[n:].copy()
 
 
-# one instantiation per idea by default (heap variant 2, 47 entries / 20 warps, table prefetch, sift
-# prefetch, __maxnreg__, 59 entries, shared-first scan, 95 entries); HBN_TEST_ALL_CFGS=1 runs all
-_CFGS = ["1", "30", "31", "32", "39", "34"]
+# the instantiations kept next to the shipped one (hbn_capi.cu laneKernel): round 1's kernel, the L2-policy
+# steps, 95 shared entries, two-warp blocks without / with the single replay loop body
+_CFGS = ["1", "30", "31", "32", "34", "38", "60"]
 
 
 @pytest.mark.parametrize("cfg", _CFGS)
