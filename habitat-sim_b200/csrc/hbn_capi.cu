@@ -16,7 +16,6 @@
 #include "hbn_astar_lane.cuh"
 #include "hbn_snap.cuh"
 #include "hbn_follower.cuh"
-#include <cub/device/device_scan.cuh>
 
 using namespace hbn;
 
@@ -127,7 +126,7 @@ struct hbn_navmesh {
   DevBuf envG, envPt, envFlag, envPos;  // env step: find_path's start projection, fix-up flags, the goals' polys
   // find_path pipeline: class, cost class, search list, status, corridor rings
   DevBuf fpCls, fpBucket, fpWork, fpStat, fpLen, fpCorr;
-  DevBuf snapCnt, snapOff, snapG, snapQ, snapD, snapOut, snapBest, snapTmp, snapTodo;  // candidate-list snap (hbn_snap.cuh)
+  DevBuf snapWin, snapG, snapQ, snapD, snapOut, snapBest, snapTodo;  // candidate-list snap (hbn_snap.cuh)
   // lane-per-query search: per-lane node table + records + heap tail in HBM, sized from the batch
   DevBuf wsLane, laneGen;
   int64_t laneSlots = 0;    // lane slots the scratch holds (tables zeroed, generations 0 when allocated)
@@ -423,8 +422,29 @@ bool snapDualLaunch(hbn_navmesh* nm, SnapJob a, SnapJob b, SnapJob c, cudaStream
   return true;
 }
 
-// projectToPoly for n points.  Large batches: count -> scan -> fill -> eval -> select
-// (hbn_snap.cuh), nothing read back by the host; small ones: the lane-group kernel.
+// scratch of the candidate-list snap pipeline for chunks of up to cmax points
+int snapScratch(hbn_navmesh* nm, int64_t cmax, SnapScratch* sc) {
+  size_t cap = static_cast<size_t>(cmax) * kSnapAvgCap;
+  if (nm->opt.snapCap > 0) cap = static_cast<size_t>(nm->opt.snapCap);  // testing: force the fallback
+  int rc;
+  if ((rc = nm->snapWin.ensure(cmax * 4)) || (rc = nm->snapG.ensure(cap * 4)) || (rc = nm->snapQ.ensure(cap * 4)) ||
+      (rc = nm->snapD.ensure(cap * 4)) || (rc = nm->snapOut.ensure(cap * 4)) || (rc = nm->snapBest.ensure(cmax * 8)) ||
+      (rc = nm->snapTodo.ensure(16)))
+    return rc;
+  sc->todo = static_cast<uint32_t*>(nm->snapTodo.p);
+  sc->total = sc->todo + 1;
+  sc->cap = static_cast<uint32_t>(cap);
+  sc->candG = static_cast<uint32_t*>(nm->snapG.p);
+  sc->candTag = static_cast<uint32_t*>(nm->snapQ.p);
+  sc->candLb = static_cast<float*>(nm->snapOut.p);
+  sc->candD = static_cast<float*>(nm->snapD.p);
+  sc->best = static_cast<unsigned long long*>(nm->snapBest.p);
+  sc->winner = static_cast<uint32_t*>(nm->snapWin.p);
+  return HBN_OK;
+}
+
+// projectToPoly for n points.  Large batches: walk -> eval -> mark -> select (hbn_snap.cuh), nothing
+// read back by the host; small ones: the lane-group kernel.
 int snapLaunch(hbn_navmesh* nm, const float* pts, const int32_t* islands, int64_t n, float* out_pts,
                uint32_t* out_g, uint32_t* out_refs, int32_t* out_isl, uint8_t* out_nav,
                float maxYDelta, cudaStream_t st) {
@@ -448,50 +468,30 @@ int snapLaunch(hbn_navmesh* nm, const float* pts, const int32_t* islands, int64_
     CK(cudaGetLastError());
     return HBN_OK;
   }
-  const int64_t cmax = std::min(n, kSnapChunk);
-  size_t cap = static_cast<size_t>(cmax) * kSnapAvgCap;
-  if (nm->opt.snapCap > 0) cap = static_cast<size_t>(nm->opt.snapCap);  // testing: force the fallback
-  size_t tmpBytes = 0;
-  CK(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr),
-                                   static_cast<int>(cmax + 1), st));
+  static_assert(kSnapChunk <= (1ll << kSnapQBits), "a slot tag holds the point index of a chunk");
+  SnapScratch sc{};
   int rc;
-  if ((rc = nm->snapCnt.ensure((cmax + 1) * 4)) || (rc = nm->snapOff.ensure((cmax + 1) * 4)) ||
-      (rc = nm->snapG.ensure(cap * 4)) || (rc = nm->snapQ.ensure(cap * 4)) || (rc = nm->snapD.ensure(cap * 4)) ||
-      (rc = nm->snapOut.ensure(cap * 4)) || (rc = nm->snapBest.ensure(cmax * 8)) || (rc = nm->snapTmp.ensure(tmpBytes)) ||
-      (rc = nm->snapTodo.ensure(16)))
-    return rc;
-  uint32_t* cnt = static_cast<uint32_t*>(nm->snapCnt.p);
-  uint32_t* off = static_cast<uint32_t*>(nm->snapOff.p);
-  uint32_t* cg = static_cast<uint32_t*>(nm->snapG.p);
-  uint32_t* cq = static_cast<uint32_t*>(nm->snapQ.p);
-  float* cd = static_cast<float*>(nm->snapD.p);
-  float* clb = static_cast<float*>(nm->snapOut.p);
-  uint32_t* best = static_cast<uint32_t*>(nm->snapBest.p);
-  float* rxz = reinterpret_cast<float*>(best + cmax);
-  uint32_t* todo = static_cast<uint32_t*>(nm->snapTodo.p);
+  if ((rc = snapScratch(nm, std::min(n, kSnapChunk), &sc))) return rc;
   for (int64_t c0 = 0; c0 < n; c0 += kSnapChunk) {
     const int64_t cn = std::min(kSnapChunk, n - c0);
     const float* p = pts + 3 * c0;
     const int32_t* isl = islands ? islands + c0 : nullptr;
     const unsigned pb = static_cast<unsigned>((cn + 255) / 256);
-    CK(cudaMemsetAsync(cnt + cn, 0, 4, st));
-    k_snap_count<<<pb, 256, 0, st>>>(nm->view, p, isl, cn, cnt, best, rxz);
-    CK(cub::DeviceScan::ExclusiveSum(nm->snapTmp.p, tmpBytes, cnt, off, static_cast<int>(cn + 1), st));
-    k_snap_fill<<<pb, 256, 0, st>>>(nm->view, p, cn, off, static_cast<uint32_t>(cap), rxz, cg, cq, clb);
-    for (int pass = 0; pass < 2; ++pass)
-      k_snap_eval<<<static_cast<unsigned>(nm->smCount * 16), 256, 0, st>>>(
-          nm->view, p, isl, cn, off, static_cast<uint32_t>(cap), cg, cq, clb, pass, cd, best);
-    k_snap_select<<<pb, 256, 0, st>>>(nm->view, p, isl, cn, off, static_cast<uint32_t>(cap), cg, cd,
-                                      out_pts ? out_pts + 3 * c0 : nullptr, out_g ? out_g + c0 : nullptr,
-                                      out_refs ? out_refs + c0 : nullptr, out_isl ? out_isl + c0 : nullptr,
-                                      out_nav ? out_nav + c0 : nullptr, maxYDelta, todo);
+    CK(cudaMemsetAsync(sc.todo, 0, 8, st));  // todo flag + slot counter
+    k_snap_walk<<<pb, 256, 0, st>>>(nm->view, p, isl, cn, sc);
+    const unsigned eb = static_cast<unsigned>(nm->smCount * 16);
+    for (int pass = 0; pass < 2; ++pass) k_snap_eval<<<eb, 256, 0, st>>>(nm->view, p, isl, sc, pass);
+    k_snap_mark<<<eb, 256, 0, st>>>(sc);
+    k_snap_select<<<pb, 256, 0, st>>>(nm->view, p, isl, cn, sc, out_pts ? out_pts + 3 * c0 : nullptr,
+                                      out_g ? out_g + c0 : nullptr, out_refs ? out_refs + c0 : nullptr,
+                                      out_isl ? out_isl + c0 : nullptr, out_nav ? out_nav + c0 : nullptr, maxYDelta);
     // redone here only if the chunk's candidates did not fit the scratch (decided on the device)
     const int64_t blocks = std::min(maxBlocks, (cn + groupsPerBlock - 1) / groupsPerBlock);
     k_snap<kSnapW><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
         nm->view, p, isl, cn, out_pts ? out_pts + 3 * c0 : nullptr, out_g ? out_g + c0 : nullptr,
         out_refs ? out_refs + c0 : nullptr, out_isl ? out_isl + c0 : nullptr, out_nav ? out_nav + c0 : nullptr,
-        maxYDelta, todo);
-    nm->launches += 8;  // 6 kernels here + cub's scan (2 kernels)
+        maxYDelta, sc.todo);
+    nm->launches += 6;
     CK(cudaGetLastError());
   }
   return HBN_OK;
@@ -557,8 +557,8 @@ void hbn_navmesh_destroy(hbn_navmesh_t nm) {
                     &nm->mgBounds, &nm->mgOrder, &nm->mgEnd, &nm->mgMask, &nm->envG, &nm->envPt, &nm->envFlag, &nm->envPos,
                     &nm->folS, &nm->folT, &nm->folE, &nm->folF, &nm->folGeo, &nm->folObs, &nm->folGeo0, &nm->folPos,
                     &nm->fpCls, &nm->fpWork, &nm->fpStat,
-                    &nm->fpLen, &nm->fpCorr, &nm->fpBucket, &nm->wsLane, &nm->laneGen, &nm->snapCnt, &nm->snapOff,
-                    &nm->snapG, &nm->snapQ, &nm->snapD, &nm->snapOut, &nm->snapBest, &nm->snapTmp, &nm->snapTodo})
+                    &nm->fpLen, &nm->fpCorr, &nm->fpBucket, &nm->wsLane, &nm->laneGen, &nm->snapWin,
+                    &nm->snapG, &nm->snapQ, &nm->snapD, &nm->snapOut, &nm->snapBest, &nm->snapTodo})
     b->release();
   if (nm->pinned) cudaFreeHost(nm->pinned);
   if (nm->faultHost) cudaFreeHost(nm->faultHost);
@@ -657,8 +657,8 @@ int64_t hbn_navmesh_scratch_bytes(hbn_navmesh_t nm) {
                           &nm->mgOrder, &nm->mgEnd, &nm->mgMask, &nm->envG, &nm->envPt, &nm->envFlag, &nm->envPos,
                           &nm->folS, &nm->folT, &nm->folE, &nm->folF, &nm->folGeo, &nm->folObs, &nm->folGeo0, &nm->folPos,
                           &nm->fpCls, &nm->fpWork, &nm->fpStat, &nm->fpLen, &nm->fpCorr, &nm->fpBucket, &nm->wsLane,
-                          &nm->laneGen, &nm->snapCnt, &nm->snapOff, &nm->snapG, &nm->snapQ, &nm->snapD, &nm->snapOut,
-                          &nm->snapBest, &nm->snapTmp, &nm->snapTodo})
+                          &nm->laneGen, &nm->snapWin, &nm->snapG, &nm->snapQ, &nm->snapD, &nm->snapOut,
+                          &nm->snapBest, &nm->snapTodo})
     total += static_cast<int64_t>(b->cap);
   return total;
 }
@@ -669,20 +669,12 @@ int hbn_navmesh_reserve(hbn_navmesh_t nm, int64_t n) {
   DeviceGuard g(nm->device);
   std::lock_guard<std::recursive_mutex> lk(nm->mu);
   int rc;
-  if ((rc = envStepReserve(nm, n)) || (rc = nm->lists.ensure(n * 4)) || (rc = nm->io.ensure(n * 64 + 8192)) ||
+  if ((rc = envStepReserve(nm, n)) || (rc = nm->lists.ensure(n * 8)) || (rc = nm->io.ensure(n * 64 + 8192)) ||
       (rc = nm->wsL.ensure(static_cast<size_t>(nm->blocksWallL) * kFpWarps * wsGlobalBytes(kCapL, kWsHybrid))))
     return rc;
   if (n >= kSnapSmall) {  // the candidate-list snap pipeline's scratch
-    const int64_t cmax = std::min(n, kSnapChunk);
-    const size_t cap = nm->opt.snapCap > 0 ? static_cast<size_t>(nm->opt.snapCap) : static_cast<size_t>(cmax) * kSnapAvgCap;
-    size_t tmpBytes = 0;
-    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr),
-                                     static_cast<int>(cmax + 1), nm->stream));
-    if ((rc = nm->snapCnt.ensure((cmax + 1) * 4)) || (rc = nm->snapOff.ensure((cmax + 1) * 4)) ||
-        (rc = nm->snapG.ensure(cap * 4)) || (rc = nm->snapQ.ensure(cap * 4)) || (rc = nm->snapD.ensure(cap * 4)) ||
-        (rc = nm->snapOut.ensure(cap * 4)) || (rc = nm->snapBest.ensure(cmax * 8)) || (rc = nm->snapTmp.ensure(tmpBytes)) ||
-        (rc = nm->snapTodo.ensure(16)))
-      return rc;
+    SnapScratch sc{};
+    if ((rc = snapScratch(nm, std::min(n, kSnapChunk), &sc))) return rc;
   }
   CK(cudaStreamSynchronize(nm->stream));  // the zeroing of new search state
   return HBN_OK;
@@ -1204,7 +1196,7 @@ int hbn_closest_obstacle_dev(hbn_navmesh_t nm, const float* pts, int64_t n, floa
   NvtxRange nv(nm->opt.nvtx, "hbn_closest_obstacle");
   CallOrder order(nm, st);
   int rc;
-  if ((rc = nm->sG.ensure(n * 4)) || (rc = nm->sPt.ensure(n * 12)) || (rc = nm->lists.ensure(n * 4)) ||
+  if ((rc = nm->sG.ensure(n * 4)) || (rc = nm->sPt.ensure(n * 12)) || (rc = nm->lists.ensure(n * 8)) ||
       (rc = nm->wsL.ensure(static_cast<size_t>(nm->blocksWallL) * kFpWarps * wsGlobalBytes(kCapL, kWsHybrid))))
     return rc;
   uint32_t* cnt = static_cast<uint32_t*>(nm->counters.p);
@@ -1222,14 +1214,23 @@ int hbn_closest_obstacle_dev(hbn_navmesh_t nm, const float* pts, int64_t n, floa
   a.maxRadius = max_radius;
   a.out_pos = out_hit_pos; a.out_normal = out_hit_normal; a.out_dist = out_hit_dist;
   const int threads = kFpWarps * 32;
-  int64_t blocks = std::min<int64_t>(nm->blocksWallS, (n + kFpWarps - 1) / kFpWarps);
-  k_wall<kWallCapS, kWsShared><<<static_cast<unsigned>(blocks), threads,
-                                kFpWarps * wsSharedBytes(kWallCapS, kWsShared), st>>>(nm->view, a);
+  // three tiers, each working off the overflow list of the one before: a query per thread with a
+  // 8-node pool, a query per warp with 128 nodes in shared memory, and the reference's 2048 nodes
+  k_wall_lane<<<static_cast<unsigned>((n + kWallLaneThreads - 1) / kWallLaneThreads), kWallLaneThreads, 0, st>>>(nm->view, a);
   nm->launches++;
   CK(cudaGetLastError());
-  WallArgs b = a;
-  b.work = a.overflow;
-  b.workCount = a.overflowCount;
+  WallArgs a1 = a;
+  a1.work = a.overflow;
+  a1.workCount = a.overflowCount;
+  a1.counter = cnt + 4;
+  a1.overflow = static_cast<uint32_t*>(nm->lists.p) + n;
+  a1.overflowCount = cnt + 5;
+  k_wall<kWallCapS, kWsShared><<<nm->blocksWallS, threads, kFpWarps * wsSharedBytes(kWallCapS, kWsShared), st>>>(nm->view, a1);
+  nm->launches++;
+  CK(cudaGetLastError());
+  WallArgs b = a1;
+  b.work = a1.overflow;
+  b.workCount = a1.overflowCount;
   b.counter = cnt + 2;
   b.overflowCount = cnt + 3;
   b.scratch = static_cast<char*>(nm->wsL.p);

@@ -306,6 +306,33 @@ __global__ void __launch_bounds__(128) k_wall(NavView nav, WallArgs a) {
   }
 }
 
+// Tier 0 of closestObstacleSurfacePoint: ONE QUERY PER THREAD (distanceToWallSmall, hbn_query.h).  The search
+// is a handful of nodes, so its pool is 6 x kWallLaneCap words per thread in shared memory; the rare query
+// that needs more goes to the warp-per-query tiers above through the overflow list.
+constexpr int kWallLaneThreads = 128;
+__global__ void __launch_bounds__(kWallLaneThreads) k_wall_lane(NavView nav, WallArgs a) {
+  __shared__ uint32_t ws[6 * kWallLaneCap * kWallLaneThreads];
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * kWallLaneThreads + threadIdx.x;
+  if (q >= a.n) return;
+  // closestObstacleSurfacePoint, PF.cpp:1794-1812
+  float hp[3] = {0.f, 0.f, 0.f}, hn[3] = {0.f, 0.f, 0.f};
+  float hd = infF();
+  const uint32_t g = a.sG[q];
+  if (g != kNoPoly) {
+    const float c[3] = {a.sPt[3 * q], a.sPt[3 * q + 1], a.sPt[3 * q + 2]};
+    hd = nanF();
+    const uint32_t st = distanceToWallSmall<kWallLaneCap, kWallLaneThreads>(nav, ws + threadIdx.x, g, c, a.maxRadius,
+                                                                           &hd, hp, hn);
+    if (st == 0xffffffffu) {
+      a.overflow[atomicAdd(a.overflowCount, 1u)] = static_cast<uint32_t>(q);
+      return;
+    }
+  }
+  if (a.out_pos) { a.out_pos[3 * q] = hp[0]; a.out_pos[3 * q + 1] = hp[1]; a.out_pos[3 * q + 2] = hp[2]; }
+  if (a.out_normal) { a.out_normal[3 * q] = hn[0]; a.out_normal[3 * q + 1] = hn[1]; a.out_normal[3 * q + 2] = hn[2]; }
+  a.out_dist[q] = hd;
+}
+
 // ------------------------------------------------------------------------------------
 // tryStep phase A / B (PF.cpp:1575-1722), one thread per query
 __global__ void __launch_bounds__(128) k_trystep_a(NavView nav, const float* __restrict__ ends,

@@ -195,6 +195,11 @@ HBN_HD float snapEval(const NavView& nav, const float* center, int islandFilter,
   return d;
 }
 
+// The same choice as a minimum: key = distance bits << 32 | visit index (distances are >= +0, so bit order is
+// value order; the smallest visit index among equal distances is the first strictly smaller one).  "No
+// candidate yet" is FLT_MAX as the distance, m_nearestDistanceSqr's start value (DQ.cpp:649), above every key.
+constexpr unsigned long long kSnapBestInit = 0x7f7fffffffffffffull;
+
 // "if (d < m_nearestDistanceSqr)" over the candidates in visit order (DQ.cpp:670).
 // Returns the index of the winner in [begin, end) or end if none.  (A NaN distance never wins,
 // as in the reference; negative = hidden by the island filter or skipped by its lower bound.)

@@ -98,7 +98,7 @@ void emu_snap(void* h, const float* pts, const int* islands, long n, float* out_
   }
 }
 
-// The candidate-list findNearestPoly (hbn_snap.h: walk -> eval -> select), serially.
+// The candidate-list findNearestPoly (hbn_snap.h / hbn_snap.cuh: walk -> eval -> mark -> select), serially.
 void emu_snap_list(void* h, const float* pts, const int* islands, long n, float* out_pts,
                    unsigned* out_refs, int* out_isl, long* out_ncand) {
   Emu* e = static_cast<Emu*>(h);
@@ -114,19 +114,29 @@ void emu_snap_list(void* h, const float* pts, const int* islands, long n, float*
     total += static_cast<long>(cand.size());
     d.assign(cand.size(), -1.f);
     SnapCandOut o;
-    float best = kFltMax;
-    for (int pass = 0; pass < 2; ++pass)  // as k_snap_eval
+    // as k_snap_eval / k_snap_mark: the minimum of {distance bits << 32 | visit index} over both passes
+    unsigned long long best = kSnapBestInit;
+    for (int pass = 0; pass < 2; ++pass)
       for (size_t c = 0; c < cand.size(); ++c) {
         if ((lb[c] == 0.f) != (pass == 0)) continue;
-        if (pass == 1 && !snapMayWin(lb[c], best)) continue;
+        float bd;
+        const uint32_t bb = static_cast<uint32_t>(best >> 32);
+        memcpy(&bd, &bb, 4);
+        if (pass == 1 && !snapMayWin(lb[c], bd)) continue;
         d[c] = snapEval(e->nav, pts + 3 * i, isl, cand[c], &o);
         evaluated++;
-        if (pass == 0 && d[c] >= 0.f && d[c] < best) best = d[c];
+        if (d[c] >= 0.f && d[c] < kFltMax) {
+          uint32_t db;
+          memcpy(&db, &d[c], 4);
+          const unsigned long long key = (static_cast<unsigned long long>(db) << 32) | c;
+          if (key < best) best = key;
+        }
         // the bound must never exceed the distance it bounds
         if (d[c] >= 0.f && lb[c] * 0.999f - 1e-6f > d[c]) { fprintf(stderr, "snap lower bound violated: pt %ld cand %zu g %u lb %g d %g over %u center %g %g %g cp %g %g %g\n", i, c, cand[c], lb[c], d[c], o.over, pts[3*i], pts[3*i+1], pts[3*i+2], o.cp[0], o.cp[1], o.cp[2]); abort(); }
       }
-    const uint32_t w = snapSelect(d.data(), 0, static_cast<uint32_t>(cand.size()));
-    const bool ok = w < cand.size();
+    const bool ok = best != kSnapBestInit;
+    const uint32_t w = ok ? static_cast<uint32_t>(best & 0xffffffffu) : 0u;
+    if (ok && w != snapSelect(d.data(), 0, static_cast<uint32_t>(cand.size()))) { fprintf(stderr, "snap: the packed minimum is not the first strict minimum (pt %ld)\n", i); abort(); }
     if (ok) snapEval(e->nav, pts + 3 * i, isl, cand[w], &o);
     for (int k = 0; k < 3; ++k) out_pts[3 * i + k] = ok ? o.cp[k] : NAN;
     if (out_refs) out_refs[i] = ok ? e->nav.polys[cand[w]].ref : 0u;
@@ -327,7 +337,12 @@ static long laneHeapFuzz(unsigned seed, long ops, int keyLevels) {
       const uint32_t a = ref.pop();
       const uint32_t b = h.S[0];
       h.size--;
-      h.heapPopSift(h.size);
+      {
+        float lk;
+        uint32_t ls;
+        h.hget(h.size, lk, ls);
+        h.heapPopSift(h.size, lk, ls);
+      }
       open[a] = 0;
       if (a != b) return op + 1;
     } else {  // decrease-key of a random open node
@@ -599,6 +614,40 @@ void emu_obstacle(void* h, const float* pts, long n, float maxRadius, int cap, f
     float hitDist = NAN;
     const uint32_t st = distanceToWall(e->nav, w, s.g, s.pt, maxRadius, &hitDist, o, o + 3);
     if (st == 0xffffffffu && out_overflow) out_overflow[i] = 1;
+    o[6] = hitDist;
+  }
+}
+
+// The same through the tiers of hbn_closest_obstacle_dev: the per-thread search with its small pool
+// (distanceToWallSmall, k_wall_lane), then the 128- and 2048-node workspaces for what overflows.
+// out_tier[i] = tier that answered (0, 1, 2).  smallCap: 4 to exercise the hand-over even more, else the device's kWallLaneCap.
+void emu_obstacle_tiers(void* h, const float* pts, long n, float maxRadius, int smallCap, float* out, int* out_tier) {
+  Emu* e = static_cast<Emu*>(h);
+  HostGroup grp;
+  uint32_t q[2];
+  std::vector<uint32_t> small(6 * kWallLaneCap);
+  for (long i = 0; i < n; ++i) {
+    float* o = out + 7 * i;
+    const Nearest s = findNearestPoly(e->nav, grp, pts + 3 * i, kExt, -1, q);
+    for (int k = 0; k < 6; ++k) o[k] = 0.f;
+    o[6] = INFINITY;
+    out_tier[i] = 0;
+    if (s.g == kNoPoly) continue;
+    float hitDist = NAN;
+    uint32_t st = smallCap == 4 ? distanceToWallSmall<4, 1>(e->nav, small.data(), s.g, s.pt, maxRadius, &hitDist, o, o + 3)
+                                : distanceToWallSmall<kWallLaneCap, 1>(e->nav, small.data(), s.g, s.pt, maxRadius, &hitDist, o, o + 3);
+    for (int cap : {128, 2048}) {
+      if (st != 0xffffffffu) break;
+      out_tier[i]++;
+      // (the overflowing tier may have moved the hit position: the device restarts from zeros too)
+      for (int k = 0; k < 6; ++k) o[k] = 0.f;
+      std::vector<char> buf(astarWsBytes(cap) + 64);
+      void* aligned = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(buf.data()) + 15) & ~uintptr_t(15));
+      AStarWs w = astarWsCarve(aligned, cap);
+      memset(w.hash, 0, sizeof(uint32_t) * 2 * cap);
+      hitDist = NAN;
+      st = distanceToWall(e->nav, w, s.g, s.pt, maxRadius, &hitDist, o, o + 3);
+    }
     o[6] = hitDist;
   }
 }

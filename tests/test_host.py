@@ -153,6 +153,11 @@ def test_hostemu_queries_match_oracle(name):
     ovf = np.zeros(len(pts), np.int32)
     emu.emu_obstacle(h, P(pts, f32p), C.c_long(len(pts)), C.c_float(2.0), 2048, P(got, f32p), P(ovf, i32p))
     assert ovf.sum() == 0 and beq(want, got).all()
+    # ... and through the tiers of the device entry point (a query per thread with a small pool first)
+    got = np.zeros((len(pts), 7), np.float32)
+    tier = np.zeros(len(pts), np.int32)
+    emu.emu_obstacle_tiers(h, P(pts, f32p), C.c_long(len(pts)), C.c_float(2.0), 16, P(got, f32p), P(tier, i32p))
+    assert beq(want, got).all() and (tier == 0).mean() > 0.9
     # random points, plain and island restricted, same counter-based stream
     m = 600
     ri = np.full(m, -1, np.int32)
@@ -350,6 +355,7 @@ def test_hostemu_out_of_the_ordinary_inputs(name):
         got = np.zeros_like(s)
         emu.emu_try_step(h, P(s, f32p), P(t, f32p), C.c_long(n), sliding, P(got, f32p))
         assert beq(got, want).all(), sliding
+    tiers_seen = set()
     for r in (0.0, 0.05, 7.5, 1e6):
         hp, hn, hd = ref.obstacle_batch(s, r, 4)
         out = np.zeros((n, 7), np.float32)
@@ -357,6 +363,13 @@ def test_hostemu_out_of_the_ordinary_inputs(name):
         emu.emu_obstacle(h, P(s, f32p), C.c_long(n), C.c_float(r), 2048, P(out, f32p), P(ov, i32p))
         assert not ov.any()
         assert beq(out[:, 6], hd).all() and beq(out[:, :3], hp).all() and beq(out[:, 3:6], hn).all(), r
+        out = np.zeros((n, 7), np.float32)
+        tier = np.zeros(n, np.int32)
+        for small_cap in (16, 4):
+            emu.emu_obstacle_tiers(h, P(s, f32p), C.c_long(n), C.c_float(r), small_cap, P(out, f32p), P(tier, i32p))
+            assert beq(out[:, 6], hd).all() and beq(out[:, :3], hp).all() and beq(out[:, 3:6], hn).all(), r
+            tiers_seen |= set(np.unique(tier).tolist())
+    assert {0, 1} <= tiers_seen  # a 4-node pool overflows to the warp-per-query workspace
     p2 = s.copy()
     p2[:, 1] += rng.choice([-4.2, -4.0, -3.99, -1.0, -0.2, 0.19, 0.2, 0.21, 1.0, 2.9, 3.99, 4.0, 4.01],
                            size=n).astype(np.float32)

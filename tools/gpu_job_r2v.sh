@@ -1,0 +1,24 @@
+#!/bin/bash
+# single-walk snap pipeline + k_wall_lane with an 8-node pool: GPU tests, bench lines, launch list of the snap kernels
+tag=r2v
+out=gpurun_out
+export HBN_QUERY_CACHE=/tmp/hbn_queries
+echo "== gpu tests"; timeout 1800 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 | tee $out/${tag}_pytest.log
+for c in c4snap c5wall c4; do echo "== bench --config $c"; timeout 900 python bench.py --config $c > $out/${tag}_bench_$c.json 2> $out/${tag}_bench_$c.err; cut -c1-200 $out/${tag}_bench_$c.json; tail -2 $out/${tag}_bench_$c.err; done
+echo "== launch list (c4snap)"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $out/${tag}_snap_launches.csv \
+  python bench.py --config c4snap --steps 1 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
+python - <<'PY'
+import csv, collections
+rows=[r for r in csv.reader(open("gpurun_out/r2v_snap_launches.csv")) if len(r)>10]
+h=rows[0]; ik=h.index("Kernel Name"); iv=h.index("Metric Value")
+agg=collections.OrderedDict()
+for r in rows[1:]:
+    k=r[ik].split("(")[0][:40]; agg.setdefault(k,[0,0.0]); agg[k][0]+=1; agg[k][1]+=float(r[iv].replace(",",""))
+for k,(n,t) in agg.items(): print(f"  {k:42s} {n:4d} launches  {t/1e6:.3f} ms total  {t/n/1000:.1f} us each")
+PY
+echo "== ncu wall"
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_wall_lane -s 3 -c 1 -o $out/${tag}_wall -f python bench.py --config c5wall --queries 2000000 --steps 1 --no-cpu-baseline > /dev/null 2>&1
+ncu -i $out/${tag}_wall.ncu-rep --page raw --csv > $out/${tag}_wall_lane_raw.csv 2>/dev/null
+rm -f $out/${tag}_wall.ncu-rep
+python tools/ncu_summary.py $out/${tag}_wall_lane_raw.csv | grep -E "^==|time_duration|thread_inst_executed_per|issue_active|inst_executed.sum|warps_active|long_scoreboard"
