@@ -459,8 +459,10 @@ struct LaneSearch {
     return *reinterpret_cast<const LaneHeapPair*>(p);
   }
   // dtNodeQueue::pop's trickleDown (DNode.cpp:169-184) for a heap that has `n` entries left
-  // (lk, ls) = entry n, the one that moves to the top: loaded by the caller (hget), early
-  HBN_HD void heapPopSift(const int n, const float lk, const uint32_t ls) const {
+  HBN_HD void heapPopSift(const int n) const {
+    float lk;
+    uint32_t ls;
+    hget(n, lk, ls);
     int i = 0, child = 1;
     while (child < n) {  // child is odd; child + 1 <= n is inside the arrays
       float c0, c1;
@@ -631,15 +633,10 @@ struct LaneSearch {
       } else {
         // ---- pop (DQ.cpp:1027-1040) ------------------------------------------------------
         bslot = S[0];
-        size--;
-        // the heap's last entry (beyond the shared levels: an HBM access) and the popped record are
-        // independent loads: both are issued before the first wait
-        float lastKey;
-        uint32_t lastSlot;
-        hget(size, lastKey, lastSlot);
         LaneRecA ba;
         LaneRecB bb;
         loadRec(bslot, ba, bb);
+        size--;
 #if defined(__CUDA_ARCH__)
         {  // the popped poly's link records are needed right after the sift: start them towards L1 now
           const char* lp = reinterpret_cast<const char*>(&nav.links[bb.lnk & 0x07ffffffu]);
@@ -649,7 +646,7 @@ struct LaneSearch {
             if (k < cnt) asm volatile("prefetch.global.L1 [%0];" ::"l"(lp + 32 * k));
         }
 #endif
-        heapPopSift(size, lastKey, lastSlot);
+        heapPopSift(size);
         storeClosed(bslot, ba.cost);
 #if defined(__CUDA_ARCH__)
         // The next pop takes the new top unless one of this poly's neighbours (whose records are

@@ -123,7 +123,8 @@ def multigoal_find_path(path: MultiGoalShortestPath, snap_refs, find_paths, sort
         moved = np.float32(find_paths(start[None], path._prev_requested_start[None], 0)["geodesic_distance"][0])
         l2 = _mn_length(ends - start[None])
         with np.errstate(invalid="ignore"):
-            path._min_theoretical_dist = np.maximum((path._min_theoretical_dist - moved).astype(np.float32), l2)
+            a = (path._min_theoretical_dist - moved).astype(np.float32)
+            path._min_theoretical_dist = np.where(a < l2, l2, a)  # std::max(a, l2), PF.cpp:1533: a NaN l2 keeps a
         path._prev_requested_start = start.copy()
     if g == 0:
         return False

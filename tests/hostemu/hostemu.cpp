@@ -337,12 +337,7 @@ static long laneHeapFuzz(unsigned seed, long ops, int keyLevels) {
       const uint32_t a = ref.pop();
       const uint32_t b = h.S[0];
       h.size--;
-      {
-        float lk;
-        uint32_t ls;
-        h.hget(h.size, lk, ls);
-        h.heapPopSift(h.size, lk, ls);
-      }
+      h.heapPopSift(h.size);
       open[a] = 0;
       if (a != b) return op + 1;
     } else {  // decrease-key of a random open node
