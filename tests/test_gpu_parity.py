@@ -212,6 +212,20 @@ def test_closest_obstacle(scene):
     assert beq(pf.distances_to_closest_obstacle(pts[:2000], 0.5), hd5).all()
 
 
+def test_closest_obstacle_tiers_on_the_multi_storey_mesh():
+    """distance_to_closest_obstacle through all its tiers: on c4_building under 1 % of the queries need more
+    than the 8-node per-thread pool of k_wall_lane and go on to the warp-per-query workspaces; radii from
+    0 to 1e6 (PF.cpp:1794-1812 passes the radius through; DQ.cpp:3470-3655 shrinks it to the nearest wall)."""
+    name = "c4_building"
+    from workloads.scenes import NavMeshGeom, pointnav_pairs
+    pf, ref = gpu_pathfinder(name), ref_pathfinder(name)
+    pts = pointnav_pairs(NavMeshGeom(navmesh_image(name)), 60_000, 9, jitter=0.05)[0]
+    for radius, n in ((2.0, 60_000), (0.0, 3000), (0.05, 3000), (7.5, 20_000), (1e6, 20_000)):
+        hp, hn, hd = ref.obstacle_batch(pts[:n], radius, 8)
+        gp, gn, gd = pf.closest_obstacle_surface_points(pts[:n], radius)
+        assert beq(gd, hd).all() and beq(gp, hp).all() and beq(gn, hn).all(), radius
+
+
 def test_random_points_near(scene):
     """get_random_navigable_point_near (getRandomNavigablePointInCircle, PF.cpp:1283-1332, trap T6): the
     oracle's samples on the same uniform stream, plain and island restricted; and the properties the
