@@ -7,6 +7,7 @@
 #include <string.h>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/hbn.h"
@@ -1314,9 +1315,44 @@ struct IoPlan {
     return HBN_OK;
   }
   template <class T> T* dev(size_t o) { return reinterpret_cast<T*>(static_cast<char*>(nm->io.p) + o); }
+  // A copy between a user buffer and the pinned staging area.  One thread moves ~10 GB/s, and for the
+  // cheap queries that IS the call (16 M wall-distance queries: 192 MB in, 64 MB out, 9 ms of kernels): large
+  // copies are cut over a few threads.
+  static void copyPar(void* dst, const void* src, size_t bytes) {
+    constexpr size_t kPerThread = 4u << 20;  // (1 MB per thread measured slower: the threads are made per call)
+    unsigned nt = static_cast<unsigned>(std::min<size_t>(bytes / kPerThread, 8));
+    nt = std::min(nt, std::max(1u, std::thread::hardware_concurrency()));
+    if (nt <= 1) {
+      memcpy(dst, src, bytes);
+      return;
+    }
+    const size_t part = ((bytes + nt - 1) / nt + 4095) & ~size_t(4095);
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; ++t) {
+      const size_t o = static_cast<size_t>(t) * part;
+      if (o >= bytes) break;
+      th.emplace_back([=] { memcpy(static_cast<char*>(dst) + o, static_cast<const char*>(src) + o, std::min(part, bytes - o)); });
+    }
+    memcpy(dst, src, std::min(part, bytes));
+    for (auto& x : th) x.join();
+  }
   void stage() {  // user buffers -> pinned
     for (auto& it : items)
-      if (it.src) memcpy(static_cast<char*>(nm->pinned) + it.off, it.src, it.bytes);
+      if (it.src) copyPar(static_cast<char*>(nm->pinned) + it.off, it.src, it.bytes);
+  }
+  // user buffers -> pinned -> device in pieces: the DMA of a piece runs while the next one is staged
+  int stageAndEnqueueH2D() {
+    constexpr size_t kPiece = 32u << 20;
+    for (auto& it : items) {
+      if (!it.src) continue;
+      for (size_t o = 0; o < it.bytes; o += kPiece) {
+        const size_t b = std::min(kPiece, it.bytes - o);
+        copyPar(static_cast<char*>(nm->pinned) + it.off + o, static_cast<const char*>(it.src) + o, b);
+        CK(cudaMemcpyAsync(static_cast<char*>(nm->io.p) + it.off + o, static_cast<char*>(nm->pinned) + it.off + o, b,
+                           cudaMemcpyHostToDevice, nm->stream));
+      }
+    }
+    return HBN_OK;
   }
   int enqueueH2D() {
     for (auto& it : items)
@@ -1335,13 +1371,10 @@ struct IoPlan {
   int finish() {  // wait, pinned -> user buffers
     CK(cudaStreamSynchronize(nm->stream));
     for (auto& it : items)
-      if (it.dst) memcpy(it.dst, static_cast<char*>(nm->pinned) + it.off, it.bytes);
+      if (it.dst) copyPar(it.dst, static_cast<char*>(nm->pinned) + it.off, it.bytes);
     return checkFault(nm);
   }
-  int h2d() {
-    stage();
-    return enqueueH2D();
-  }
+  int h2d() { return stageAndEnqueueH2D(); }
   int d2h() {
     int rc = enqueueD2H();
     if (rc) return rc;
