@@ -1328,12 +1328,18 @@ struct IoPlan {
     }
     const size_t part = ((bytes + nt - 1) / nt + 4095) & ~size_t(4095);
     std::vector<std::thread> th;
+    size_t done = std::min(part, bytes);  // [0, done) is this thread's; a piece whose thread cannot be made too
     for (unsigned t = 1; t < nt; ++t) {
       const size_t o = static_cast<size_t>(t) * part;
       if (o >= bytes) break;
-      th.emplace_back([=] { memcpy(static_cast<char*>(dst) + o, static_cast<const char*>(src) + o, std::min(part, bytes - o)); });
+      const size_t b = std::min(part, bytes - o);
+      try {
+        th.emplace_back([=] { memcpy(static_cast<char*>(dst) + o, static_cast<const char*>(src) + o, b); });
+      } catch (...) {  // out of threads: copy the piece here
+        memcpy(static_cast<char*>(dst) + o, static_cast<const char*>(src) + o, b);
+      }
     }
-    memcpy(dst, src, std::min(part, bytes));
+    memcpy(dst, src, done);
     for (auto& x : th) x.join();
   }
   void stage() {  // user buffers -> pinned
