@@ -156,7 +156,7 @@ def test_hostemu_queries_match_oracle(name):
     # ... and through the tiers of the device entry point (a query per thread with a small pool first)
     got = np.zeros((len(pts), 7), np.float32)
     tier = np.zeros(len(pts), np.int32)
-    emu.emu_obstacle_tiers(h, P(pts, f32p), C.c_long(len(pts)), C.c_float(2.0), 16, P(got, f32p), P(tier, i32p))
+    emu.emu_obstacle_tiers(h, P(pts, f32p), C.c_long(len(pts)), C.c_float(2.0), 8, P(got, f32p), P(tier, i32p))
     assert beq(want, got).all() and (tier == 0).mean() > 0.9
     # random points, plain and island restricted, same counter-based stream
     m = 600
@@ -365,7 +365,7 @@ def test_hostemu_out_of_the_ordinary_inputs(name):
         assert beq(out[:, 6], hd).all() and beq(out[:, :3], hp).all() and beq(out[:, 3:6], hn).all(), r
         out = np.zeros((n, 7), np.float32)
         tier = np.zeros(n, np.int32)
-        for small_cap in (16, 4):
+        for small_cap in (8, 4):
             emu.emu_obstacle_tiers(h, P(s, f32p), C.c_long(n), C.c_float(r), small_cap, P(out, f32p), P(tier, i32p))
             assert beq(out[:, 6], hd).all() and beq(out[:, :3], hp).all() and beq(out[:, 3:6], hn).all(), r
             tiers_seen |= set(np.unique(tier).tolist())
@@ -486,6 +486,13 @@ def test_hostemu_fuzz_random_scenes(seed):
         for i in np.nonzero(done)[0]:
             k = r["num_polys"][i]
             assert min(info[i, 1], 256) == k and (corr[i, :k] == r["corridor"][i, :k]).all()
+        # wall distance through the tiers of the device entry point (per-thread pool first), two radii
+        for radius in (2.0, 30.0):
+            hp, hn, hd = ref.obstacle_batch(st, radius, 4)
+            out = np.zeros((n, 7), np.float32)
+            tier = np.zeros(n, np.int32)
+            emu.emu_obstacle_tiers(h, P(st, f32p), C.c_long(n), C.c_float(radius), 8, P(out, f32p), P(tier, i32p))
+            assert beq(out[:, 6], hd).all() and beq(out[:, :3], hp).all() and beq(out[:, 3:6], hn).all(), radius
         emu.emu_destroy(h)
 
 
