@@ -39,9 +39,39 @@ __global__ void __launch_bounds__(256) k_snap_walk(NavView nav, const float* __r
   sc.winner[q] = kSnapNoSlot;
   const float c[3] = {pts[3 * q], pts[3 * q + 1], pts[3 * q + 2]};
   const float ext[3] = {2.f, 4.f, 2.f};  // polyPickExt, PF.cpp:134
-  const float r = snapRadius(nav, c, ext, islands ? islands[q] : -1);
-  uint32_t count = 0, base = 0;
+  const int isl = islands ? islands[q] : -1;
   bool lost = false;
+  // A point over a flat part of the mesh (nearly all of them) ends up with the smallest radius, kSnapRadiusMin:
+  // its candidates are what a walk of THAT box collects.  So the walk that looks for a poly under the point
+  // (snapRadius) uses that box and keeps what it finds: if the radius it arrives at is the minimum, these are
+  // the candidates and the point is done after one walk instead of two.
+  float r = ext[0];
+  if (nav.bvXzTight) {
+    float ub = kFltMax;
+    uint32_t n1 = 0;
+    const uint32_t base1 = atomicAdd(sc.total, kSnapBlock);
+    const bool fits = base1 + kSnapBlock <= sc.cap;
+    snapWalk(nav, c, ext, kSnapRadiusMin, [&](uint32_t g, float lb) {
+      snapUbUpdate(nav, c, isl, g, lb, ub);
+      if (n1 < kSnapBlock && fits) {
+        sc.candG[base1 + n1] = g;
+        sc.candTag[base1 + n1] = static_cast<uint32_t>(q) | (n1 << kSnapQBits);
+        sc.candLb[base1 + n1] = lb;
+      }
+      n1++;
+    });
+    r = snapRadiusFromUb(ub, ext[0]);
+    const bool done = fits && n1 <= kSnapBlock && !(r > kSnapRadiusMin);
+    if (fits)  // the unused slots of the block -- all of them if a wider walk follows
+      for (uint32_t k = done ? n1 : 0u; k < kSnapBlock; ++k) sc.candTag[base1 + k] = kSnapNoSlot;
+    else
+      lost = true;
+    if (done) {
+      if (lost) atomicOr(sc.todo, 1u);
+      return;
+    }
+  }
+  uint32_t count = 0, base = 0;
   snapWalk(nav, c, ext, r, [&](uint32_t g, float lb) {
     const uint32_t k = count & (kSnapBlock - 1u);
     if (k == 0u) base = atomicAdd(sc.total, kSnapBlock);

@@ -148,24 +148,31 @@ HBN_HD uint32_t snapWalk(const NavView& nav, const float* center, const float* h
 // (bvXzTight) its BV leaf box within sqrt(ub) of the point in xz.  On a multi-storey tile the
 // reference's +-2 m x +-4 m box collects ~70 candidates from ~350 BV nodes per point; the narrowed
 // walk of an on-mesh point sees the handful of polys stacked under it.
+// One candidate of the column walk: if the point lies inside poly g in xz, the winner's distance is at most
+// (max |dy| over g's height range - climb)^2.
+HBN_HD void snapUbUpdate(const NavView& nav, const float* center, int islandFilter, uint32_t g, float lb, float& ub) {
+  if (lb >= ub) return;
+  const PolyRec* p = &nav.polys[g];
+  if (islandFilter >= 0 && p->island != islandFilter) return;
+  if ((p->areaType >> 6) == 1 || !pointInPolygon(center, p->v, p->nv)) return;  // getPolyHeight would fail
+  const float* b = nav.polyBox + 8 * static_cast<size_t>(g);
+  const float dlo = fabsf(center[1] - b[1]), dhi = fabsf(center[1] - b[5]);
+  const float e = (dlo > dhi ? dlo : dhi) - nav.tiles[p->tile].walkableClimb;
+  const float u = e > 0.f ? e * e : 0.f;
+  if (u < ub) ub = u;
+}
+constexpr float kSnapRadiusMin = 0.11f;  // two BV quanta (0.05 m cells) and rounding
+HBN_HD float snapRadiusFromUb(float ub, float full) {
+  if (!(ub < kFltMax)) return full;
+  const float r = fsqrt(ub) * 1.001f + kSnapRadiusMin;
+  return r < full ? r : full;
+}
 HBN_HD float snapRadius(const NavView& nav, const float* center, const float* halfExt, int islandFilter) {
   const float full = halfExt[0];
   if (!nav.bvXzTight) return full;
   float ub = kFltMax;
-  snapWalk(nav, center, halfExt, 0.1f, [&](uint32_t g, float lb) {
-    if (lb >= ub) return;
-    const PolyRec* p = &nav.polys[g];
-    if (islandFilter >= 0 && p->island != islandFilter) return;
-    if ((p->areaType >> 6) == 1 || !pointInPolygon(center, p->v, p->nv)) return;  // getPolyHeight would fail
-    const float* b = nav.polyBox + 8 * static_cast<size_t>(g);
-    const float dlo = fabsf(center[1] - b[1]), dhi = fabsf(center[1] - b[5]);
-    const float e = (dlo > dhi ? dlo : dhi) - nav.tiles[p->tile].walkableClimb;
-    const float u = e > 0.f ? e * e : 0.f;
-    if (u < ub) ub = u;
-  });
-  if (!(ub < kFltMax)) return full;
-  const float r = fsqrt(ub) * 1.001f + 0.11f;  // + two BV quanta (0.05 m cells) and rounding
-  return r < full ? r : full;
+  snapWalk(nav, center, halfExt, 0.1f, [&](uint32_t g, float lb) { snapUbUpdate(nav, center, islandFilter, g, lb, ub); });
+  return snapRadiusFromUb(ub, full);
 }
 
 struct SnapCandOut {
