@@ -98,6 +98,16 @@ void emu_snap(void* h, const float* pts, const int* islands, long n, float* out_
   }
 }
 
+static int g_snapOneWalk = 1;  // emu_snap_one_walk: the device's one-walk path (default) or the two-walk form
+static long g_snapSecondWalks = 0;
+// returns the number of points that needed the wider second walk since the last call
+long emu_snap_one_walk(int on) {
+  g_snapOneWalk = on;
+  const long r = g_snapSecondWalks;
+  g_snapSecondWalks = 0;
+  return r;
+}
+
 // The candidate-list findNearestPoly (hbn_snap.h / hbn_snap.cuh: walk -> eval -> mark -> select), serially.
 void emu_snap_list(void* h, const float* pts, const int* islands, long n, float* out_pts,
                    unsigned* out_refs, int* out_isl, long* out_ncand) {
@@ -109,8 +119,26 @@ void emu_snap_list(void* h, const float* pts, const int* islands, long n, float*
     cand.clear();
     lb.clear();
     const int isl = islands ? islands[i] : -1;
-    const float r = snapRadius(e->nav, pts + 3 * i, kExt, isl);
-    snapWalk(e->nav, pts + 3 * i, kExt, r, [&](uint32_t g, float b) { cand.push_back(g); lb.push_back(b); });
+    if (g_snapOneWalk && e->nav.bvXzTight) {
+      // as k_snap_walk: the column walk with the minimum radius keeps its candidates; a wider walk only if the
+      // radius it arrives at is larger (or it found more than a block of candidates)
+      float ub = kFltMax;
+      snapWalk(e->nav, pts + 3 * i, kExt, kSnapRadiusMin, [&](uint32_t g, float b) {
+        snapUbUpdate(e->nav, pts + 3 * i, isl, g, b, ub);
+        cand.push_back(g);
+        lb.push_back(b);
+      });
+      const float r = snapRadiusFromUb(ub, kExt[0]);
+      if (cand.size() > 8 || r > kSnapRadiusMin) {
+        cand.clear();
+        lb.clear();
+        snapWalk(e->nav, pts + 3 * i, kExt, r, [&](uint32_t g, float b) { cand.push_back(g); lb.push_back(b); });
+        g_snapSecondWalks++;
+      }
+    } else {
+      const float r = snapRadius(e->nav, pts + 3 * i, kExt, isl);
+      snapWalk(e->nav, pts + 3 * i, kExt, r, [&](uint32_t g, float b) { cand.push_back(g); lb.push_back(b); });
+    }
     total += static_cast<long>(cand.size());
     d.assign(cand.size(), -1.f);
     SnapCandOut o;

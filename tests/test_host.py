@@ -215,6 +215,40 @@ def test_hostemu_snap_list_on_multi_storey_tiles(name):
     emu.emu_destroy(h)
 
 
+@pytest.mark.parametrize("name", ["c1_room", "c3_multiroom", "t_building", "c4_building"])
+def test_hostemu_snap_one_walk_and_two_walk_forms(name):
+    """k_snap_walk keeps the candidates of the column walk (minimum radius) and walks again only when the
+    radius comes out larger; the plain form walks the column, then the box.  Both must give the oracle's
+    nearest poly, point and island, on-mesh points, jittered ones (walls, other storeys) and island-restricted."""
+    emu, h = _emu_handle(name)
+    pf = ref_pathfinder(name)
+    rng = np.random.default_rng(12)
+    n = 3000
+    pts = query_points(name, n, 41, jitter=0.0)
+    pts[n // 3:] += rng.normal(0, 0.35, (n - n // 3, 3)).astype(np.float32)
+    pts = np.ascontiguousarray(pts, np.float32)
+    isl = np.full(n, -1, np.int32)
+    isl[::4] = rng.integers(0, pf.num_islands, len(isl[::4]))
+    emu.emu_snap_one_walk.restype = C.c_long
+    for islands in (None, isl):
+        want_p, want_r, want_i = (pf.snap_island_batch(pts, islands) + (None,)) if islands is not None else pf.snap_batch(pts, 4)
+        for one_walk in (1, 0):
+            emu.emu_snap_one_walk(one_walk)
+            e_pts = np.zeros_like(pts)
+            e_refs = np.zeros(n, np.uint32)
+            e_isl = np.zeros(n, np.int32)
+            nc = (C.c_long * 2)()
+            emu.emu_snap_list(h, P(pts, f32p), P(islands, i32p), C.c_long(n), P(e_pts, f32p), P(e_refs, u32p),
+                              P(e_isl, i32p), nc)
+            second = emu.emu_snap_one_walk(1)
+            assert (want_r == e_refs).all() and beq(want_p, e_pts).all(), (one_walk, islands is not None)
+            if want_i is not None:
+                assert (want_i == e_isl).all()
+            if one_walk:
+                assert second < n  # most points are done after the first walk
+    emu.emu_destroy(h)
+
+
 @pytest.mark.parametrize("name", ["c2_apartment", "c3_multiroom", "t_building", "c4_building"])
 def test_hostemu_lane_search_matches_oracle(name):
     """hbn_astar_lane.h (the per-lane state machine of k_astar_lane) against Detour's findPath:
